@@ -1,0 +1,147 @@
+"""Generates tests/golden/*.pt by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only:  python tests/golden/make_golden.py
+The reference is imported through oracle/ref_harness (import stubs + FakeGym); every random draw it
+makes is logged by oracle.rng.Recorder so the oracle restatement can replay it.
+"""
+import contextlib
+import io
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import dtc_b200  # noqa: E402
+from dtc_b200 import sim_stub  # noqa: E402
+from oracle import ref_harness as RH  # noqa: E402
+from oracle.rng import Recorder  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def digest(t):
+    t = t.detach().double().flatten()
+    return torch.tensor([t.sum(), t.abs().sum(), (t * torch.arange(1, t.numel() + 1, dtype=torch.float64)).sum() / t.numel()])
+
+
+def env_golden(N=16, steps=10, seed=11):
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    hs, tor = sim_stub.make_heightmap("stones", 0)
+    layout = sim_stub.initial_env_layout(N, tor, seed)
+    fg = sim_stub.FakeGym(N)
+    g = torch.Generator().manual_seed(seed + 1)
+    states = [sim_stub.synth_state(N, layout[2], g) for _ in range(steps + 1)]
+    # make sure the nasty paths are hit: tilt one robot over, drop one into a pit
+    states[3]["root_states"][1, 3:7] = torch.tensor([0.9, 0.0, 0.0, 0.435])
+    states[5]["root_states"][2, 2] -= 0.4
+    env = RH.build_ref_env(N, hs, tor, layout, fg)
+    rec = Recorder()
+    out = dict(N=N, steps=steps, seed=seed, states=states, heightmap=("stones", 0), layout=layout, frames=[])
+    with rec:
+        fg.queue.append(states[0])
+        env.reset()
+        out["reset_log"] = rec.take()
+        out["after_reset"] = dict(obs=env.obs_buf.clone(), priv_digest=digest(env.privileged_obs_buf),
+                                  commands=env.commands.clone(), rew=env.rew_buf.clone())
+        # pokes applied identically to the oracle (exercise resample @500, timeout @1000, push @750)
+        env.episode_length_buf[0:4] = 498
+        env.episode_length_buf[4:6] = 999
+        env.common_step_counter = 747
+        ag = torch.Generator().manual_seed(seed + 2)
+        for t in range(steps):
+            actions = torch.randn(N, 12, generator=ag) * (150.0 if t == 2 else 1.0)
+            fg.queue.append(states[t + 1])
+            obs, priv, rew, done, extras = env.step(actions)
+            fr = dict(actions=actions, log=rec.take(), obs=obs.clone(), priv=priv.clone(), rew=rew.clone(),
+                      done=done.clone(), time_outs=env.time_out_buf.clone(),
+                      measured_heights=env.measured_heights.clone(), pred_footholds=env.pred_footholds.clone(),
+                      optimal_idx=env.optimal_foothold_indice.squeeze(1).clone(),
+                      nominal_idx=env.nominal_footholds_indice.clone(), foothold_obs=env.foothold_obs.clone(),
+                      optimal_footholds_world=env.optimal_footholds_world.clone(),
+                      foothold_score=env.foothold_score.clone(), slope=env.slope.clone(),
+                      commands=env.commands.clone(), torques=env.torques.clone(),
+                      base_lin_vel=env.base_lin_vel.clone(), clearance=env.measured_foot_clearance.clone(),
+                      episode_sums={k: v.clone() for k, v in env.episode_sums.items()},
+                      terrain_levels=env.terrain_levels.clone(), env_origins=env.env_origins.clone(),
+                      episode_length=env.episode_length_buf.clone(), root_after=env.root_states.clone(),
+                      dof_after=env.dof_state.clone(), motor=env.motor_strengths[:, 0].clone(),
+                      hno=env.height_noise_offset[:, 0].clone(), feet_air_time=env.feet_air_time.clone(),
+                      pitch_est=env.pitch_est.clone(), base_vel=env.get_base_vel().clone(),
+                      extras_episode={k: (v.clone() if torch.is_tensor(v) else v) for k, v in extras.get("episode", {}).items()})
+            out["frames"].append(fr)
+    torch.save(out, os.path.join(OUT, "env_n16.pt"))
+    print("env golden: resets per step", [int(f["done"].sum()) for f in out["frames"]])
+
+
+def learner_golden(N=8, iters=2, seed=5):
+    RH.import_reference()
+    from rsl_rl.runners import OnPolicyRunner
+    from legged_gym.envs.lite3.lite3_dtc_config import Lite3DTCCfgPPO
+    from legged_gym.utils.helpers import class_to_dict
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    hs, tor = sim_stub.make_heightmap("stones", 0)
+    layout = sim_stub.initial_env_layout(N, tor, seed)
+    fg = sim_stub.FakeGym(N)
+    T = 24
+    g = torch.Generator().manual_seed(seed + 1)
+    states = [sim_stub.synth_state(N, layout[2], g) for _ in range(1 + iters * T)]
+    env = RH.build_ref_env(N, hs, tor, layout, fg)
+    fg.queue.extend(states)
+    train_cfg = class_to_dict(Lite3DTCCfgPPO())
+    rec = Recorder()
+    out = dict(N=N, T=T, iters=iters, seed=seed, states=states, layout=layout, heightmap=("stones", 0))
+    with tempfile.TemporaryDirectory() as d, rec:
+        with contextlib.redirect_stdout(io.StringIO()):
+            torch.manual_seed(seed + 7)
+            runner = OnPolicyRunner(env, train_cfg, log_dir=d, device="cpu")
+        out["init_log"] = rec.take()
+        ac = runner.alg.actor_critic
+        out["param_seed"] = seed + 7
+        out["param_digest0"] = {k: digest(v) for k, v in ac.state_dict().items()}
+        out["num_params"] = sum(p.numel() for p in ac.parameters())
+        # capture per-minibatch gradients of the first iteration through a hook on clip_grad_norm_
+        grads = []
+        orig_clip = torch.nn.utils.clip_grad_norm_
+
+        def clip(params, max_norm, *a, **k):
+            params = list(params)
+            grads.append(digest(torch.cat([p.grad.flatten() for p in params if p.grad is not None])))
+            return orig_clip(params, max_norm, *a, **k)
+
+        import rsl_rl.algorithms.ppo as ppo_mod
+        ppo_mod.nn.utils.clip_grad_norm_ = clip
+        out["iters_out"] = []
+        for it in range(iters):
+            with contextlib.redirect_stdout(io.StringIO()):
+                # learn(1) == one iteration; the reference saves a checkpoint into the temp dir
+                st_before = None
+                runner.learn(1, init_at_random_ep_len=(it == 0))
+            st = runner.alg.storage
+            out["iters_out"].append(dict(
+                log=rec.take(), grad_digests=list(grads), lr=runner.alg.learning_rate,
+                param_digest={k: digest(v) for k, v in ac.state_dict().items()},
+                std=ac.std.detach().clone(),
+                advantages=st.advantages.clone(), returns=st.returns.clone(), values=st.values.clone(),
+                rewards=st.rewards.clone(), dones=st.dones.clone(), actions=st.actions.clone(),
+                mu=st.mu.clone(), logp=st.actions_log_prob.clone(),
+                actor_last_w=ac.actor_body[6].weight.detach().clone(),
+                latent_var_w=ac.vae.latent_var.weight.detach().clone()))
+            grads.clear()
+        ppo_mod.nn.utils.clip_grad_norm_ = orig_clip
+        ck = torch.load(os.path.join(d, "model_%d.pt" % iters), weights_only=True)
+        out["checkpoint_keys"] = list(ck["model_state_dict"].keys())
+    torch.save(out, os.path.join(OUT, "learner_n8.pt"))
+    print("learner golden: lr", [o["lr"] for o in out["iters_out"]], "params", out["num_params"])
+
+
+if __name__ == "__main__":
+    env_golden()
+    learner_golden()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
