@@ -1,0 +1,158 @@
+"""ctypes binding of libdtc_b200.so (include/dtc_b200.h).  The product path has no CPU fallback: if the
+library is missing or no CUDA device is present, the ops raise."""
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libdtc_b200.so")
+_lib = None
+
+f32p = C.POINTER(C.c_float)
+vp = C.c_void_p
+
+
+class EnvConfig(C.Structure):
+    _fields_ = [
+        ("num_envs", C.c_int32), ("map_rows", C.c_int32), ("map_cols", C.c_int32),
+        ("horizontal_scale", C.c_float), ("vertical_scale", C.c_float), ("border_size", C.c_float),
+        ("dt", C.c_float), ("max_episode_length", C.c_int32), ("resampling_steps", C.c_int32),
+        ("push_interval", C.c_int32), ("max_push_vel_xy", C.c_float),
+        ("cmd_lin_x", C.c_float * 2), ("cmd_lin_y", C.c_float * 2), ("cmd_heading", C.c_float * 2),
+        ("motor_strength", C.c_float * 2), ("cmd_lin_x_max", C.c_float), ("cmd_ang_yaw_max", C.c_float),
+        ("base_height_target", C.c_float), ("tracking_sigma", C.c_float), ("max_acc", C.c_float),
+        ("terrain_length", C.c_float), ("max_terrain_level", C.c_int32), ("num_terrain_cols", C.c_int32),
+        ("episode_length_s", C.c_float),
+        ("p_gain", C.c_float), ("d_gain", C.c_float), ("action_scale", C.c_float), ("torque_limit", C.c_float),
+        ("default_dof_pos", C.c_float * 12), ("dof_pos_lower", C.c_float * 12), ("dof_pos_upper", C.c_float * 12),
+        ("base_init_state", C.c_float * 13), ("grid_x", C.c_float * 33), ("grid_y", C.c_float * 21),
+        ("plane_op", C.c_float * (2 * 693)), ("reward_scale", C.c_float * 24), ("noise_scale_vec", C.c_float * 53),
+        ("obs_scale_lin_vel", C.c_float), ("obs_scale_ang_vel", C.c_float), ("obs_scale_dof_pos", C.c_float),
+        ("obs_scale_dof_vel", C.c_float), ("obs_scale_height", C.c_float), ("obs_scale_force", C.c_float),
+        ("clip_obs", C.c_float), ("clip_actions", C.c_float),
+    ]
+
+
+ENV_BUFFER_NAMES = [
+    "root_states", "dof_state", "contact_forces", "rigid_body_state", "height_samples",
+    "actions", "torques", "lag_buffer", "base_lin_vel", "base_ang_vel", "projected_gravity", "commands",
+    "cmd_buffer", "lin_vel_buffer", "ang_vel_buffer", "measured_heights", "pred_footholds", "optimal_idx",
+    "nominal_idx", "foothold_obs", "optimal_footholds_world", "center_clear_mean", "plane_ab", "foot_clearance",
+    "contact_filt", "last_contacts", "stumb_buffer", "feet_air_time", "pitch_est", "last_actions", "last_actions_2",
+    "last_dof_vel", "last_root_vel", "last_foot_vel", "motor_strengths", "robot_mass", "height_noise_offset",
+    "forces0", "episode_length_buf", "terrain_levels", "terrain_types", "env_origins", "terrain_origins",
+    "reset_buf", "time_out_buf", "rew_buf", "episode_sums", "reward_terms", "obs_buf", "privileged_obs_buf",
+    "obs_history", "episode_stats",
+]
+
+
+class EnvBuffers(C.Structure):
+    _fields_ = [(n, vp) for n in ENV_BUFFER_NAMES] + [("priv_ld", C.c_int32), ("hist_ld", C.c_int32)]
+
+
+class EnvNoise(C.Structure):
+    _fields_ = [(n, vp) for n in ("resample_u", "push_u", "reset_u", "priv_u", "obs_u")]
+
+
+STORAGE_PTRS = ["observations", "next_observations", "privileged_observations", "observation_histories", "rewards",
+                "actions", "actions_log_prob", "values", "returns", "advantages", "mu", "sigma", "base_vel", "dones"]
+
+
+class Storage(C.Structure):
+    _fields_ = [(n, vp) for n in STORAGE_PTRS] + [(n, C.c_int32) for n in ("T", "N", "obs_ld", "priv_ld", "hist_ld", "bv_ld")]
+
+
+class PPOHParams(C.Structure):
+    _fields_ = [("clip_param", C.c_float), ("value_loss_coef", C.c_float), ("entropy_coef", C.c_float),
+                ("max_grad_norm", C.c_float), ("desired_kl", C.c_float), ("adaptive_lr", C.c_int32)]
+
+
+class ParamInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("offset", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32), ("ld", C.c_int32)]
+
+
+class DtcError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads the library (once).  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DtcError(f"{LIB_PATH} not found - run `python __graft_entry__.py` (build()) first; there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.dtc_last_error.restype = C.c_char_p
+    L.dtc_launch_count.restype = C.c_int64
+    L.dtc_env_create.argtypes = [C.POINTER(EnvConfig), C.POINTER(vp)]
+    L.dtc_env_destroy.argtypes = [vp]
+    L.dtc_env_destroy.restype = None
+    L.dtc_env_bind.argtypes = [vp, C.POINTER(EnvBuffers)]
+    L.dtc_env_pre_physics.argtypes = [vp, vp, C.POINTER(C.c_int32), vp]
+    L.dtc_env_state_prep.argtypes = [vp, C.c_int64, C.c_uint64, C.POINTER(EnvNoise), vp]
+    L.dtc_foothold_step.argtypes = [vp, C.c_int, vp, vp]
+    L.dtc_env_reward_reset.argtypes = [vp, C.c_int64, C.c_uint64, C.c_float, C.POINTER(EnvNoise), vp]
+    L.dtc_env_observe.argtypes = [vp, C.c_int64, C.c_uint64, C.POINTER(EnvNoise), vp]
+    if not hasattr(L, "dtc_learner_create"):
+        if os.environ.get("DTC_ALLOW_PARTIAL") != "1":
+            raise DtcError("libdtc_b200.so was built without the learner kernels - rebuild")
+        _lib = L
+        return L
+    L.dtc_param_total_floats.restype = C.c_int64
+    L.dtc_learner_workspace_bytes.restype = C.c_int64
+    L.dtc_learner_workspace_bytes.argtypes = [C.c_int32]
+    L.dtc_learner_stats.restype = C.c_void_p
+    L.dtc_learner_stats.argtypes = [vp]
+    L.dtc_param_get.argtypes = [C.c_int, C.POINTER(ParamInfo)]
+    L.dtc_param_range.argtypes = [C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.dtc_learner_create.argtypes = [C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.POINTER(vp)]
+    L.dtc_learner_destroy.argtypes = [vp]
+    L.dtc_learner_destroy.restype = None
+    i32, u64 = C.c_int32, C.c_uint64
+    L.dtc_policy_act.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, u64, u64, vp, vp, vp, vp, vp, vp]
+    L.dtc_policy_evaluate.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp, vp]
+    L.dtc_store_transition.argtypes = [C.POINTER(Storage), i32, vp, i32, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp,
+                                       vp, i32, C.c_float, vp]
+    L.dtc_gae.argtypes = [C.POINTER(Storage), vp, C.c_float, C.c_float, vp, C.c_int, vp]
+    L.dtc_gae_normalize.argtypes = [C.POINTER(Storage), vp, vp]
+    L.dtc_gather_minibatch.argtypes = [C.POINTER(Storage), C.POINTER(Storage), vp, C.c_int64, vp]
+    step_args = [vp, C.POINTER(Storage), C.c_int64, i32, vp, u64, u64, C.POINTER(PPOHParams), C.c_int, C.c_float, vp]
+    L.dtc_vae_step.argtypes = step_args
+    L.dtc_ppo_step.argtypes = step_args
+    L.dtc_optimizer_apply.argtypes = [vp, C.c_int, C.POINTER(PPOHParams), vp]
+    L.dtc_learner_set_lr.argtypes = [vp, C.c_double, vp]
+    L.dtc_learner_reset_stats.argtypes = [vp, vp]
+    L.dtc_learner_set_adam_steps.argtypes = [vp, C.c_int64, C.c_int64]
+    L.dtc_learner_debug_buffer.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.dtc_linear_forward.argtypes = [i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp]
+    for which, st in enumerate((EnvConfig, EnvBuffers, EnvNoise, Storage, PPOHParams, ParamInfo)):
+        got = L.dtc_struct_size(which)
+        if got != C.sizeof(st):
+            raise DtcError(f"ABI mismatch: {st.__name__} is {C.sizeof(st)} B in Python, {got} B in the library")
+    _lib = L
+    return L
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise DtcError(f"{what} failed ({rc}): {lib().dtc_last_error().decode()}")
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise DtcError(f"{name}: expected a CUDA tensor (the hot path has no CPU fallback)")
+    return t
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def launch_count():
+    return int(lib().dtc_launch_count())

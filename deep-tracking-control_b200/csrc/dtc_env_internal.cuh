@@ -1,0 +1,12 @@
+#pragma once
+#include <cuda.h>
+#include "dtc_common.cuh"
+
+struct dtc_env {
+  dtc_env_config cfg;
+  dtc_env_buffers buf;
+  bool bound;
+  dtc_env_config* d_cfg;  // device copy (tables are too large for kernel parameters)
+  CUtensorMap tmap;       // heightmap descriptor for the TMA variant of the foothold kernel
+  bool tmap_ready;
+};

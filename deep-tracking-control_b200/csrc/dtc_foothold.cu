@@ -1,0 +1,281 @@
+// E5 + E7..E10: THE foothold-scoring kernel (legged_robot.py:1279-1317; legged_robot_dtc.py:100-201).
+//
+// One warp per environment, FH_WARPS environments per CTA.
+//   phase 1  693 grid points (22 per lane): yaw-rotate, cell index, three int16 taps -> measured height
+//            (coalesced 2772-B row store), fp64 running sums for mean/variance, the termination mean and
+//            the least-squares plane fit; heights parked in shared memory.
+//   phase 2  per point: torch.gradient stencil from shared memory, slope/roughness/edge score, and the
+//            leg-independent fall-back argmin (used when a leg has no admissible candidate within 0.16 m).
+//   phase 3  per leg: Raibert nominal foothold, 9x9 lattice window around it (covers the 0.16 m radius with
+//            0.04 m to spare), exact distance + score, lexicographic (value,index) warp argmin, decode.
+// Why the window is exact: a candidate inside the radius that is not an exception point scores
+// <= 0.2*10 + 0.8*0.16 = 2.128, every other point scores >= 8, so if the window holds one the global argmin of
+// the reference's brute-force 693x4 scan is inside the window; otherwise every in-radius point is an exception
+// (score 10) and the scan reduces to argmin_p (exc ? 10 : 0.2*s_p + 8), which phase 2 already has.
+// Height taps: variant 0 reads the int16 map through L1/L2 (3.9 MB, L2 resident); variant 1 stages the 48x48
+// patch under the robot with one TMA 2-D box load (cp.async.bulk.tensor.2d + mbarrier) and taps shared memory.
+#include <cuda.h>
+#include "dtc_common.cuh"
+#include "dtc_env_internal.cuh"
+
+#define FH_WARPS 4
+#define PATCH 48  // cells per side; sampling box <= 1.89 m = 38 cells (+1 halo); 48*2 B rows are 16-B multiples for TMA
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int VARIANT>
+__global__ void __launch_bounds__(FH_WARPS * 32)
+k_foothold(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, float* __restrict__ dbg_score,
+           const __grid_constant__ CUtensorMap tmap) {
+  __shared__ float mh_s[FH_WARPS][NP + 3];
+  __shared__ float sc_s[FH_WARPS][NP + 3];  // s in [0,0.1) or 10; negative marks an exception point
+  __shared__ float gx_s[GXN], gy_s[GYN];
+  __shared__ __align__(128) int16_t patch_s[VARIANT == 1 ? FH_WARPS : 1][VARIANT == 1 ? PATCH * PATCH : 8];
+  __shared__ __align__(8) uint64_t mbar_s[FH_WARPS];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = cfg->num_envs;
+  const int n = blockIdx.x * FH_WARPS + warp;
+  if (threadIdx.x < GXN) gx_s[threadIdx.x] = cfg->grid_x[threadIdx.x];
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + GYN) gy_s[threadIdx.x - 64] = cfg->grid_y[threadIdx.x - 64];
+  if (VARIANT == 1 && lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar_s[warp])));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (n >= N) return;
+
+  const float* rs = b.root_states + (size_t)n * 13;
+  const float root_x = rs[0], root_y = rs[1], root_z = rs[2];
+  float yz, yw;
+  yaw_quat_exact(rs[5], rs[6], yz, yw);
+  const int rows = cfg->map_rows, cols = cfg->map_cols;
+  const float border = cfg->border_size, hscale = cfg->horizontal_scale, vscale = cfg->vertical_scale;
+  const int16_t* __restrict__ hs = b.height_samples;
+
+  int ox = 0, oy = 0;
+  if (VARIANT == 1) {
+    // patch origin: cell of the robot minus 21 (radius 0.943 m = 18.9 cells, +1 tap, +1 truncation slack)
+    ox = (int)floorf((root_x + border) / hscale) - 21;
+    oy = (int)floorf((root_y + border) / hscale) - 21;
+    if (lane == 0) {
+      uint32_t mb = smem_u32(&mbar_s[warp]);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(PATCH * PATCH * 2) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+              smem_u32(&patch_s[warp][0])),
+          "l"(&tmap), "r"(oy), "r"(ox), "r"(mb)
+          : "memory");
+    }
+    // all lanes wait for the box (phase parity 0; one box per warp lifetime)
+    uint32_t done = 0, mb = smem_u32(&mbar_s[warp]);
+    while (!done) {
+      asm volatile(
+          "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+          : "=r"(done)
+          : "r"(mb)
+          : "memory");
+    }
+  }
+
+  // ---------------------------------------------------------------- phase 1
+  double sum = 0.0, sumsq = 0.0, csum = 0.0;
+  float pa = 0.f, pb = 0.f;
+  float* mh_out = b.measured_heights + (size_t)n * NP;
+  const float* P0 = cfg->plane_op;
+  const float* P1 = cfg->plane_op + NP;
+#pragma unroll 2
+  for (int p = lane; p < NP; p += 32) {
+    int ix = p / GYN, iy = p - ix * GYN;
+    float rx, ry;
+    yaw_apply_exact(yz, yw, gx_s[ix], gy_s[iy], rx, ry);
+    float wx = __fadd_rn(__fadd_rn(rx, root_x), border);
+    float wy = __fadd_rn(__fadd_rn(ry, root_y), border);
+    int px = (int)__fdiv_rn(wx, hscale);  // .long(): truncation toward zero
+    int py = (int)__fdiv_rn(wy, hscale);
+    px = min(max(px, 0), rows - 2);
+    py = min(max(py, 0), cols - 2);
+    int h1, h2, h3;
+    int lx = px - ox, ly = py - oy;
+    if (VARIANT == 1 && lx >= 0 && ly >= 0 && lx < PATCH - 1 && ly < PATCH - 1) {
+      const int16_t* pt = &patch_s[warp][lx * PATCH + ly];
+      h1 = pt[0]; h2 = pt[PATCH]; h3 = pt[1];
+    } else {
+      const int16_t* g = hs + (size_t)px * cols + py;
+      h1 = __ldg(g); h2 = __ldg(g + cols); h3 = __ldg(g + 1);
+    }
+    float mh = __fmul_rn((float)min(min(h1, h2), h3), vscale);
+    mh_out[p] = mh;
+    mh_s[warp][p] = mh;
+    float gc = clampf(__fsub_rn(mh, root_z), -0.5f, 0.5f);
+    sum += (double)gc;
+    sumsq += (double)gc * (double)gc;
+    if (p >= 10 * GYN && p < (GXN - 10) * GYN) csum += (double)__fsub_rn(root_z, fmaxf(mh, 0.f));
+    pa = fmaf(__ldg(P0 + p), mh, pa);
+    pb = fmaf(__ldg(P1 + p), mh, pb);
+  }
+  sum = warp_sum(sum);
+  sumsq = warp_sum(sumsq);
+  csum = warp_sum(csum);
+  pa = warp_sum(pa);
+  pb = warp_sum(pb);
+  const double mean_d = sum / (double)NP;
+  double var_d = (sumsq - (double)NP * mean_d * mean_d) / (double)(NP - 1);
+  var_d = var_d < 0.0 ? 0.0 : var_d;
+  const float mean = (float)mean_d;
+  const float edge = clampf(__fsqrt_rn((float)var_d), 0.0f, 0.3f);
+  if (lane == 0) {
+    b.center_clear_mean[n] = (float)(csum / (double)((GXN - 20) * GYN));
+    b.plane_ab[n * 2] = pa;
+    b.plane_ab[n * 2 + 1] = pb;
+  }
+  __syncwarp();
+
+  // ---------------------------------------------------------------- phase 2
+  const float c8 = __fmul_rn(10.0f, 0.8f);
+  const float e02 = __fmul_rn(0.2f, edge);
+  float fbv = 3.0e38f;
+  int fbi = 0x7fffffff;
+  const float* mhw = mh_s[warp];
+  for (int p = lane; p < NP; p += 32) {
+    int ix = p / GYN, iy = p - ix * GYN;
+    float graw = __fsub_rn(mhw[p], root_z);
+    float gc = clampf(graw, -0.5f, 0.5f);
+    auto G = [&](int q) { return clampf(__fsub_rn(mhw[q], root_z), -0.5f, 0.5f); };
+    float dx, dy;
+    if (ix == 0) dx = __fdiv_rn(__fsub_rn(G(p + GYN), gc), 0.05f);
+    else if (ix == GXN - 1) dx = __fdiv_rn(__fsub_rn(gc, G(p - GYN)), 0.05f);
+    else dx = __fmul_rn(__fdiv_rn(__fsub_rn(G(p + GYN), G(p - GYN)), 0.05f), 0.5f);
+    if (iy == 0) dy = __fdiv_rn(__fsub_rn(G(p + 1), gc), 0.05f);
+    else if (iy == GYN - 1) dy = __fdiv_rn(__fsub_rn(gc, G(p - 1)), 0.05f);
+    else dy = __fmul_rn(__fdiv_rn(__fsub_rn(G(p + 1), G(p - 1)), 0.05f), 0.5f);
+    float slope = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    float rough = fabsf(__fsub_rn(gc, mean));
+    float s = __fadd_rn(__fadd_rn(e02, slope), __fmul_rn(0.3f, rough));
+    s = s < 0.1f ? s : 10.0f;
+    bool exc = (graw > 1.0f) || (graw < -1.0f);
+    sc_s[warp][p] = exc ? -1.0f : s;
+    float v = exc ? 10.0f : __fadd_rn(__fmul_rn(s, 0.2f), c8);
+    if (v < fbv) { fbv = v; fbi = p; }  // ascending p per lane: strict < keeps the first minimum
+  }
+  warp_argmin(fbv, fbi);
+  __syncwarp();
+
+  // ---------------------------------------------------------------- phase 3
+  const float cmd_x = b.commands[n * 4 + 0], cmd_y = b.commands[n * 4 + 1], cmd_yaw = b.commands[n * 4 + 2];
+  const float vx = b.base_lin_vel[n * 3 + 0], vy = b.base_lin_vel[n * 3 + 1], vz = b.base_lin_vel[n * 3 + 2];
+  const float cth = cosf(cmd_yaw), sth = sinf(cmd_yaw);
+  const float cpsi = 1.0f - 2.0f * yz * yz, spsi = 2.0f * yz * yw;
+  const float sym_x = __fadd_rn(__fmul_rn(0.01f, vx), __fmul_rn(0.03f, __fsub_rn(vx, cmd_x)));
+  const float sym_y = __fadd_rn(__fmul_rn(0.01f, vy), __fmul_rn(0.03f, __fsub_rn(vy, cmd_y)));
+  const float sym_z = __fadd_rn(__fmul_rn(0.01f, vz), __fmul_rn(0.03f, vz));
+  const float* rb = b.rigid_body_state + (size_t)n * 17 * 13;
+#pragma unroll 1
+  for (int l = 0; l < 4; ++l) {
+    const float* th = rb + (2 + 4 * l) * 13;  // thigh bodies 2,6,10,14 (legged_robot_dtc.py:100)
+    float hx = __fsub_rn(th[0], root_x), hy = __fsub_rn(th[1], root_y), hz = __fsub_rn(th[2], root_z);
+    float rxh = __fadd_rn(__fmul_rn(cth, hx), __fmul_rn(-sth, hy));
+    float ryh = __fadd_rn(__fmul_rn(sth, hx), __fmul_rn(cth, hy));
+    float pfx = __fadd_rn(__fadd_rn(root_x, rxh), sym_x);
+    float pfy = __fadd_rn(__fadd_rn(root_y, ryh), sym_y);
+    float pfz = __fadd_rn(__fadd_rn(root_z, hz), sym_z);
+    // lattice cell nearest to the nominal foothold, in the yaw frame
+    float relx = pfx - root_x, rely = pfy - root_y;
+    float lxf = cpsi * relx + spsi * rely, lyf = -spsi * relx + cpsi * rely;
+    int ci = (int)floorf((lxf + 0.8f) * 20.0f + 0.5f), cj = (int)floorf((lyf + 0.5f) * 20.0f + 0.5f);
+    float bs = 3.0e38f, bd = 3.0e38f;
+    int bsi = 0x7fffffff, bdi = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      int slot = lane + 32 * k;
+      int wi = slot / 9, wj = slot - wi * 9;
+      int i = ci - 4 + wi, j = cj - 4 + wj;
+      if (slot < 81 && i >= 0 && i < GXN && j >= 0 && j < GYN) {
+        int p = i * GYN + j;
+        float rx, ry;
+        yaw_apply_exact(yz, yw, gx_s[i], gy_s[j], rx, ry);
+        float ddx = __fsub_rn(pfx, __fadd_rn(rx, root_x)), ddy = __fsub_rn(pfy, __fadd_rn(ry, root_y));
+        float d = __fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
+        if (d < 0.16f) {
+          if (d < bd || (d == bd && p < bdi)) { bd = d; bdi = p; }
+          float s = sc_s[warp][p];
+          if (s >= 0.f) {
+            float v = __fadd_rn(__fmul_rn(s, 0.2f), __fmul_rn(d, 0.8f));
+            if (v < bs || (v == bs && p < bsi)) { bs = v; bsi = p; }
+          }
+        }
+      }
+    }
+    warp_argmin(bs, bsi);
+    warp_argmin(bd, bdi);
+    int idx = (bsi != 0x7fffffff) ? bsi : fbi;
+    int nom = (bdi != 0x7fffffff) ? bdi : 0;
+    if (lane == 0) {
+      int xi = idx % GYN, yi = idx / GYN;  // reference quirk: x list indexed by idx%21, y list by (idx//21)%21
+      float rx, ry;
+      yaw_apply_exact(yz, yw, gx_s[yi], gy_s[xi], rx, ry);
+      b.optimal_idx[n * 4 + l] = idx;
+      b.nominal_idx[n * 4 + l] = nom;
+      b.foothold_obs[n * 8 + l] = gx_s[xi];
+      b.foothold_obs[n * 8 + 4 + l] = gy_s[yi % GYN];
+      float* pf = b.pred_footholds + (size_t)n * 12 + l * 3;
+      pf[0] = pfx; pf[1] = pfy; pf[2] = pfz;
+      float* ow = b.optimal_footholds_world + (size_t)n * 12 + l * 3;
+      ow[0] = __fadd_rn(rx, root_x); ow[1] = __fadd_rn(ry, root_y); ow[2] = mhw[idx];
+    }
+    if (dbg_score) {  // test-only brute force dump of the reference's [N,693,4] score tensor
+      for (int p = lane; p < NP; p += 32) {
+        int ix = p / GYN, iy = p - ix * GYN;
+        float rx, ry;
+        yaw_apply_exact(yz, yw, gx_s[ix], gy_s[iy], rx, ry);
+        float ddx = __fsub_rn(pfx, __fadd_rn(rx, root_x)), ddy = __fsub_rn(pfy, __fadd_rn(ry, root_y));
+        float d = __fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
+        d = d < 0.16f ? d : 10.0f;
+        float s = sc_s[warp][p];
+        dbg_score[((size_t)n * NP + p) * 4 + l] = s < 0.f ? 10.0f : __fadd_rn(__fmul_rn(s, 0.2f), __fmul_rn(d, 0.8f));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_heightmap_tmap(dtc_env* e) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  DTC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) DTC_FAIL(DTC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  cuuint64_t dims[2] = {(cuuint64_t)e->cfg.map_cols, (cuuint64_t)e->cfg.map_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)e->cfg.map_cols * 2};
+  cuuint32_t box[2] = {PATCH, PATCH};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ((PFN_encodeTiled)fn)(&e->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, (void*)e->buf.height_samples, dims, strides, box,
+                                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) DTC_FAIL(DTC_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+  e->tmap_ready = true;
+  return DTC_OK;
+}
+
+extern "C" int dtc_foothold_step(dtc_env* e, int variant, float* debug_score, void* stream) {
+  if (!e || !e->bound) DTC_FAIL(DTC_ERR_STATE, "dtc_foothold_step: env not bound");
+  cudaStream_t st = (cudaStream_t)stream;
+  int N = e->cfg.num_envs;
+  dim3 grid(ceil_div(N, FH_WARPS)), block(FH_WARPS * 32);
+  if (variant == 1) {
+    if ((e->cfg.map_cols * 2) % 16 != 0) DTC_FAIL(DTC_ERR_ARG, "TMA variant needs 16-byte aligned heightmap rows");
+    if (!e->tmap_ready) { int rc = make_heightmap_tmap(e); if (rc) return rc; }
+    k_foothold<1><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score, e->tmap);
+  } else if (variant == 0) {
+    k_foothold<0><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score, e->tmap);
+  } else {
+    DTC_FAIL(DTC_ERR_ARG, "dtc_foothold_step: unknown variant %d", variant);
+  }
+  DTC_CHECK_LAUNCH("k_foothold");
+  return DTC_OK;
+}

@@ -1,0 +1,413 @@
+"""`LeggedRobotDTC` - the environment surface of the hot path, backed by the sm_100a kernels.
+
+Keeps the reference's attribute and method names (legged_gym/envs/base/legged_robot_dtc.py:29-288,
+legged_robot.py:92-122, base_task.py:41-119, rsl_rl/env/vec_env.py:36-59).  Everything the reference computes
+between two physics calls runs in five kernel launches (csrc/dtc_env.cu, csrc/dtc_foothold.cu); this class only
+owns the torch tensors, draws the two host-side random numbers the reference draws on the host
+(np.random.randint lag choice, np.random.normal reset offset) and sequences the launches.
+
+Scene construction (create_sim/_create_envs, viewer, debug drawing) is out of scope (SURVEY.md section 2 rows
+1-3): the simulator is whatever object `gym` is - FakeGym on the benchmark path - exposing the four state tensors.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from .... import _lib as B
+from .... import lite3 as L
+
+
+class _Scales:
+    def __init__(self, d):
+        self.__dict__.update(d)
+
+
+class LeggedRobotDTC:
+    def __init__(self, cfg, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True, *, gym,
+                 height_samples, terrain_origins, layout, seed=0, foothold_variant=0, robot_mass=12.0):
+        self.cfg = cfg
+        self.device = torch.device(sim_device)
+        if self.device.type != "cuda":
+            raise B.DtcError("LeggedRobotDTC runs on a CUDA device only (no CPU fallback)")
+        self.lib = B.lib()
+        self.gym = gym
+        self.sim = None
+        self.headless = headless
+        self.viewer = None
+        self.debug_viz = False
+        self.foothold_variant = foothold_variant
+        N = self.num_envs = int(cfg.env.num_envs)
+        if gym.num_envs != N:
+            raise ValueError("gym.num_envs != cfg.env.num_envs")
+        self.num_obs, self.num_privileged_obs, self.num_actions = L.NUM_OBS, L.NUM_PRIV, L.NUM_ACTIONS
+        self.num_bodies, self.num_dof = L.NUM_BODIES, L.NUM_DOF
+        self.dt = L.DT
+        self.max_episode_length_s = L.EPISODE_LENGTH_S
+        self.max_episode_length = float(L.MAX_EPISODE_LENGTH)
+        self.obs_scales = _Scales(L.OBS_SCALES)
+        self.reward_scales = {k: v * self.dt for k, v in L.REWARD_SCALES.items()}
+        self.reward_names = list(L.REWARD_NAMES)
+        self.command_ranges = {k: list(v) for k, v in L.CMD_RANGES.items()}
+        self.seed = int(seed)
+        self.np_rng = np.random.default_rng(seed)
+        self.common_step_counter = 0
+        self.extras = {}
+        self.init_done = True
+        dev = self.device
+        f = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        u8 = lambda *s: torch.zeros(*s, device=dev, dtype=torch.uint8)
+        i64 = lambda *s: torch.zeros(*s, device=dev, dtype=torch.int64)
+        # simulator tensors (legged_robot.py:759-779)
+        self.root_states = gym.acquire_actor_root_state_tensor(None)
+        self.dof_state = gym.acquire_dof_state_tensor(None)
+        self.contact_forces = gym.acquire_net_contact_force_tensor(None).view(N, -1, 3)
+        self.rigid_body_state = gym.acquire_rigid_body_state_tensor(None)
+        for t in (self.root_states, self.dof_state, self.contact_forces, self.rigid_body_state):
+            B.require_cuda(t, "simulator tensor")
+        self.dof_pos = self.dof_state.view(N, L.NUM_DOF, 2)[..., 0]
+        self.dof_vel = self.dof_state.view(N, L.NUM_DOF, 2)[..., 1]
+        self.base_quat = self.root_states[:, 3:7]
+        self.base_pos = self.root_states[:, :3]
+        self.height_samples = torch.as_tensor(np.asarray(height_samples)).to(dev).view(L.MAP_ROWS, L.MAP_COLS).contiguous()
+        assert self.height_samples.dtype == torch.int16
+        levels, types, origins, tor = layout
+        self.terrain_levels = levels.to(dev).clone()
+        self.terrain_types = types.to(dev).clone()
+        self.env_origins = origins.to(dev).float().contiguous().clone()
+        self.terrain_origins = tor.to(dev).float().contiguous().clone()
+        self.max_terrain_level = L.NUM_ROWS
+        self.custom_origins = True
+        # buffers (base_task.py:41-52; legged_robot.py:788-846)
+        self.priv_ld, self.hist_ld = 1392, 268
+        self._priv_store = f(N, self.priv_ld)
+        self.privileged_obs_buf = self._priv_store[:, :L.NUM_PRIV]
+        self.obs_buf = f(N, L.NUM_OBS)
+        self._hist_store = f(N, self.hist_ld)
+        self.rew_buf = f(N)
+        self.reset_buf = torch.ones(N, device=dev, dtype=torch.uint8)
+        self.episode_length_buf = i64(N)
+        self.time_out_buf = u8(N)
+        self.actions, self.torques = f(N, 12), f(N, 12)
+        self._lag = f(6, N, 12)
+        self.base_lin_vel, self.base_ang_vel, self.projected_gravity = f(N, 3), f(N, 3), f(N, 3)
+        self.commands = f(N, 4)
+        self.cmd_buffer, self.lin_vel_buffer, self.ang_vel_buffer = f(10, N, 4), f(10, N, 2), f(10, N, 1)
+        self.measured_heights = f(N, L.NUM_POINTS)
+        self.pred_footholds = f(N, 4, 3)
+        self._optimal_idx = torch.zeros(N, 4, device=dev, dtype=torch.int32)
+        self._nominal_idx = torch.zeros(N, 4, device=dev, dtype=torch.int32)
+        self.foothold_obs = f(N, 8)
+        self.optimal_footholds_world = f(N, 4, 3)
+        self._center_clear_mean, self._plane_ab = f(N), f(N, 2)
+        self.measured_foot_clearance = f(N, 4)
+        self._contact_filt, self._last_contacts, self._stumb = u8(N, 4), u8(N, 4), u8(5, N, 4)
+        self.feet_air_time, self.pitch_est = f(N, 4), f(N)
+        self.last_actions, self.last_actions_2, self.last_dof_vel = f(N, 12), f(N, 12), f(N, 12)
+        self.last_root_vel, self.last_foot_velocities = f(N, 6), f(N, 4, 3)
+        self.motor_strengths = torch.ones(N, 12, device=dev)
+        self.robot_mass = torch.full((N,), float(robot_mass), device=dev)
+        self._height_noise_offset = f(N)
+        self._forces0 = f(N, 3)
+        self._episode_sums = f(24, N)
+        self._reward_terms = f(24, N)
+        self._episode_stats = f(26)
+        self.episode_sums = {k: self._episode_sums[i] for i, k in enumerate(L.EPISODE_SUM_NAMES)}
+        self.default_dof_pos = torch.tensor(L.DEFAULT_DOF_POS, device=dev).unsqueeze(0)
+        self.dof_pos_limits = torch.tensor(L.soft_dof_pos_limits(), device=dev)
+        self.torque_limits = torch.full((12,), L.TORQUE_LIMIT, device=dev)
+        self.feet_indices = torch.tensor(L.FEET_INDICES, device=dev)
+        self.thigh_indices = torch.tensor(L.THIGH_INDICES, device=dev)
+        self.noise_scale_vec = self._noise_scale_vec().to(dev)
+        self.add_noise = True
+        self._debug_score = None
+        self._noise = None  # injected draws (tests): dict of CUDA tensors keyed like dtc_env_noise
+        self._host_draws = None  # injected host draws: dict(lag=[4 ints], reset_normal=float)
+        self._make_ctx()
+
+    # ------------------------------------------------------------------ construction helpers
+    def _noise_scale_vec(self):
+        ns, os_ = L.NOISE_SCALES, L.OBS_SCALES
+        v = torch.zeros(L.NUM_OBS)
+        v[:3] = ns["ang_vel"] * 1.0 * os_["ang_vel"]
+        v[3:6] = ns["gravity"] * 1.0
+        v[9:21] = ns["dof_pos"] * 1.0 * os_["dof_pos"]
+        v[21:33] = ns["dof_vel"] * 1.0 * os_["dof_vel"]
+        return v
+
+    def _plane_op(self):
+        # constant (A^T A)^-1 A^T of get_plane_norm (legged_robot.py:1541-1546); same torch ops, batch of one
+        x = torch.tensor(L.MEASURED_POINTS_X)
+        y = torch.tensor(L.MEASURED_POINTS_Y)
+        gx, gy = torch.meshgrid(x, y, indexing="ij")
+        A = torch.stack([gx.flatten(), gy.flatten(), torch.ones(L.NUM_POINTS)], dim=1)[None]
+        return torch.bmm(torch.linalg.inv(torch.bmm(A.transpose(1, 2), A)), A.transpose(1, 2))[0]
+
+    def _make_ctx(self):
+        c = B.EnvConfig()
+        c.num_envs, c.map_rows, c.map_cols = self.num_envs, L.MAP_ROWS, L.MAP_COLS
+        c.horizontal_scale, c.vertical_scale, c.border_size = L.HORIZONTAL_SCALE, L.VERTICAL_SCALE, L.BORDER_SIZE
+        c.dt = L.DT
+        c.max_episode_length, c.resampling_steps, c.push_interval = L.MAX_EPISODE_LENGTH, L.RESAMPLING_STEPS, L.PUSH_INTERVAL
+        c.max_push_vel_xy = L.MAX_PUSH_VEL_XY
+        for name, key in (("cmd_lin_x", "lin_vel_x"), ("cmd_lin_y", "lin_vel_y"), ("cmd_heading", "heading")):
+            lo, hi = L.CMD_RANGES[key]
+            getattr(c, name)[0], getattr(c, name)[1] = lo, hi - lo
+        lo, hi = L.MOTOR_STRENGTH_RANGE
+        c.motor_strength[0], c.motor_strength[1] = lo, hi - lo
+        c.cmd_lin_x_max, c.cmd_ang_yaw_max = L.CMD_RANGES["lin_vel_x"][1], L.CMD_RANGES["ang_vel_yaw"][1]
+        c.base_height_target, c.tracking_sigma, c.max_acc = L.BASE_HEIGHT_TARGET, L.TRACKING_SIGMA, L.MAX_ACC
+        c.terrain_length, c.max_terrain_level, c.num_terrain_cols = L.TERRAIN_LENGTH, L.NUM_ROWS, L.NUM_COLS
+        c.episode_length_s = L.EPISODE_LENGTH_S
+        c.p_gain, c.d_gain, c.action_scale, c.torque_limit = L.P_GAIN, L.D_GAIN, L.ACTION_SCALE, L.TORQUE_LIMIT
+        lim = L.soft_dof_pos_limits()
+        for j in range(12):
+            c.default_dof_pos[j] = L.DEFAULT_DOF_POS[j]
+            c.dof_pos_lower[j], c.dof_pos_upper[j] = lim[j]
+        for j in range(13):
+            c.base_init_state[j] = L.BASE_INIT_STATE[j]
+        for j in range(33):
+            c.grid_x[j] = L.MEASURED_POINTS_X[j]
+        for j in range(21):
+            c.grid_y[j] = L.MEASURED_POINTS_Y[j]
+        po = self._plane_op()
+        flat = po[:2].contiguous().flatten().tolist()
+        for j, v in enumerate(flat):
+            c.plane_op[j] = v
+        for j, k in enumerate(L.EPISODE_SUM_NAMES):
+            c.reward_scale[j] = self.reward_scales[k]
+        for j, v in enumerate(self.noise_scale_vec.cpu().tolist()):
+            c.noise_scale_vec[j] = v
+        s = L.OBS_SCALES
+        c.obs_scale_lin_vel, c.obs_scale_ang_vel, c.obs_scale_dof_pos = s["lin_vel"], s["ang_vel"], s["dof_pos"]
+        c.obs_scale_dof_vel, c.obs_scale_height, c.obs_scale_force = s["dof_vel"], s["height_measurements"], s["force"]
+        c.clip_obs, c.clip_actions = L.CLIP_OBS, L.CLIP_ACTIONS
+        self._cfg_struct = c
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            B.check(self.lib.dtc_env_create(C.byref(c), C.byref(h)), "dtc_env_create")
+        self._h = h
+        self._bind()
+
+    def _bind(self):
+        t = dict(
+            root_states=self.root_states, dof_state=self.dof_state, contact_forces=self.contact_forces,
+            rigid_body_state=self.rigid_body_state, height_samples=self.height_samples, actions=self.actions,
+            torques=self.torques, lag_buffer=self._lag, base_lin_vel=self.base_lin_vel, base_ang_vel=self.base_ang_vel,
+            projected_gravity=self.projected_gravity, commands=self.commands, cmd_buffer=self.cmd_buffer,
+            lin_vel_buffer=self.lin_vel_buffer, ang_vel_buffer=self.ang_vel_buffer, measured_heights=self.measured_heights,
+            pred_footholds=self.pred_footholds, optimal_idx=self._optimal_idx, nominal_idx=self._nominal_idx,
+            foothold_obs=self.foothold_obs, optimal_footholds_world=self.optimal_footholds_world,
+            center_clear_mean=self._center_clear_mean, plane_ab=self._plane_ab, foot_clearance=self.measured_foot_clearance,
+            contact_filt=self._contact_filt, last_contacts=self._last_contacts, stumb_buffer=self._stumb,
+            feet_air_time=self.feet_air_time, pitch_est=self.pitch_est, last_actions=self.last_actions,
+            last_actions_2=self.last_actions_2, last_dof_vel=self.last_dof_vel, last_root_vel=self.last_root_vel,
+            last_foot_vel=self.last_foot_velocities, motor_strengths=self.motor_strengths, robot_mass=self.robot_mass,
+            height_noise_offset=self._height_noise_offset, forces0=self._forces0, episode_length_buf=self.episode_length_buf,
+            terrain_levels=self.terrain_levels, terrain_types=self.terrain_types, env_origins=self.env_origins,
+            terrain_origins=self.terrain_origins, reset_buf=self.reset_buf, time_out_buf=self.time_out_buf,
+            rew_buf=self.rew_buf, episode_sums=self._episode_sums, reward_terms=self._reward_terms, obs_buf=self.obs_buf,
+            privileged_obs_buf=self._priv_store, obs_history=self._hist_store, episode_stats=self._episode_stats)
+        b = B.EnvBuffers()
+        for name in B.ENV_BUFFER_NAMES:
+            x = t[name]
+            assert x.is_contiguous() and x.is_cuda, name
+            setattr(b, name, x.data_ptr())
+        b.priv_ld, b.hist_ld = self.priv_ld, self.hist_ld
+        self._keep = t
+        B.check(self.lib.dtc_env_bind(self._h, C.byref(b)), "dtc_env_bind")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.lib.dtc_env_destroy(self._h)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ reference-shaped views
+    @property
+    def optimal_foothold_indice(self):
+        return self._optimal_idx.long().unsqueeze(1)  # [N,1,4] int64 like torch.topk's indices
+
+    @property
+    def nominal_footholds_indice(self):
+        return self._nominal_idx.long()
+
+    @property
+    def contact_filt(self):
+        return self._contact_filt.bool()
+
+    @property
+    def last_contacts(self):
+        return self._last_contacts.bool()
+
+    @property
+    def height_noise_offset(self):
+        return self._height_noise_offset.unsqueeze(1).expand(self.num_envs, L.NUM_POINTS)
+
+    @property
+    def obs_history(self):
+        return self._hist_store[:, :L.NUM_OBS_HIST]
+
+    @property
+    def foot_positions(self):
+        return self.rigid_body_state.view(self.num_envs, L.NUM_BODIES, 13)[:, L.FEET_INDICES, 0:3]
+
+    @property
+    def foot_velocities(self):
+        return self.rigid_body_state.view(self.num_envs, L.NUM_BODIES, 13)[:, L.FEET_INDICES, 7:10]
+
+    # ------------------------------------------------------------------ VecEnv surface
+    def get_observations(self):
+        return self.obs_buf
+
+    def get_privileged_observations(self):
+        return self.privileged_obs_buf
+
+    def get_reward_buf(self):
+        return self.rew_buf
+
+    def get_base_vel(self):
+        return self.base_lin_vel * self.obs_scales.lin_vel
+
+    def reset(self):
+        """base_task.py:115-119: reset every robot, then one zero-action step."""
+        self.reset_idx(torch.arange(self.num_envs, device=self.device))
+        obs, priv, _, _, _ = self.step(torch.zeros(self.num_envs, self.num_actions, device=self.device))
+        return obs, priv
+
+    def reset_idx(self, env_ids):
+        """Host-driven reset; only the full-batch call of reset() goes through here.  In-episode resets happen on
+        the device inside dtc_env_reward_reset (no nonzero()/len() host sync)."""
+        if len(env_ids) == 0:
+            return
+        if len(env_ids) != self.num_envs:
+            raise NotImplementedError("host-side reset_idx supports the full-batch reset of reset() only")
+        self._pre_reset_all(self._host_draws or {})
+
+    def _noise_struct(self):
+        nz = B.EnvNoise()
+        if self._noise:
+            for k, v in self._noise.items():
+                if v is not None:
+                    B.require_cuda(v, k)
+                    assert v.is_contiguous() and v.dtype == torch.float32
+                    setattr(nz, k, v.data_ptr())
+        return nz
+
+    def step(self, actions):
+        """legged_robot.py:92-122."""
+        lib, st = self.lib, B.stream_ptr(self.device)
+        B.require_cuda(actions, "actions")
+        actions = actions.contiguous().float()
+        hd = self._host_draws or {}
+        lag = hd.get("lag") or [int(self.np_rng.integers(1, 5)) for _ in range(L.DECIMATION)]
+        arr = (C.c_int32 * 4)(*lag)
+        B.check(lib.dtc_env_pre_physics(self._h, B.ptr(actions), arr, st), "dtc_env_pre_physics")
+        for _ in range(L.DECIMATION):
+            self.gym.simulate(self.sim)
+            self.gym.refresh_dof_state_tensor(self.sim)
+        self.post_physics_step()
+        return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def post_physics_step(self):
+        """legged_robot_dtc.py:56-223 in four launches."""
+        lib, st = self.lib, B.stream_ptr(self.device)
+        self.gym.refresh_actor_root_state_tensor(self.sim)
+        self.gym.refresh_net_contact_force_tensor(self.sim)
+        self.gym.refresh_rigid_body_state_tensor(self.sim)
+        self.common_step_counter += 1
+        nz = self._noise_struct()
+        hd = self._host_draws or {}
+        step, seed = self.common_step_counter, self.seed
+        B.check(lib.dtc_env_state_prep(self._h, step, seed, C.byref(nz), st), "dtc_env_state_prep")
+        dbg = B.ptr(self._debug_score) if self._debug_score is not None else C.c_void_p(0)
+        B.check(lib.dtc_foothold_step(self._h, self.foothold_variant, dbg, st), "dtc_foothold_step")
+        rn = hd["reset_normal"] if "reset_normal" in hd else float(self.np_rng.normal(0, 0.02))
+        B.check(lib.dtc_env_reward_reset(self._h, step, seed, rn, C.byref(nz), st), "dtc_env_reward_reset")
+        B.check(lib.dtc_env_observe(self._h, step, seed, C.byref(nz), st), "dtc_env_observe")
+        self.extras = _LazyExtras(self)
+
+    def _pre_reset_all(self, hd):
+        """Full-batch reset_idx (legged_robot.py:200-272) ahead of the first step: done with torch ops on the
+        device (init-time plumbing, not the hot path)."""
+        N, dev = self.num_envs, self.device
+        g = torch.Generator(device=dev).manual_seed(self.seed + 12345)
+        r = hd.get("reset0_u")
+        if r is None:
+            r = torch.rand(N, 25, generator=g, device=dev)
+        # curriculum at init: distance from origin vs command norm (all zero commands -> no move_down unless distance<0)
+        dxy = self.root_states[:, :2] - self.env_origins[:, :2]
+        dist = torch.linalg.vector_norm(dxy, dim=1)
+        up = dist > L.TERRAIN_LENGTH * 0.6
+        cn = torch.linalg.vector_norm(self.commands[:, :2], dim=1)
+        down = (dist < cn * L.EPISODE_LENGTH_S * 0.5) & ~up
+        lv = self.terrain_levels + up.long() - down.long()
+        rnd = torch.clamp((r[:, 0] * L.NUM_ROWS).long(), max=L.NUM_ROWS - 1)
+        lv = torch.where(lv >= self.max_terrain_level, rnd, torch.clip(lv, 0))
+        self.terrain_levels.copy_(lv)
+        self.env_origins.copy_(self.terrain_origins[self.terrain_levels, self.terrain_types])
+        self.dof_pos[:] = self.default_dof_pos * (1.0 * r[:, 1:13] + 0.5)
+        self.dof_vel[:] = 0.0
+        self.root_states[:] = torch.tensor(L.BASE_INIT_STATE, device=dev)
+        self.root_states[:, :3] += self.env_origins
+        self.root_states[:, :2] += 1.0 * r[:, 13:15] + -0.5
+        self.root_states[:, 7:13] = 1.0 * r[:, 15:21] + -0.5
+        R = L.CMD_RANGES
+        for col, key, k in ((0, "lin_vel_x", 21), (1, "lin_vel_y", 22), (3, "heading", 23)):
+            lo, hi = R[key]
+            self.commands[:, col] = (hi - lo) * r[:, k] + lo
+        nrm = torch.linalg.vector_norm(self.commands[:, :2], dim=1)
+        self.commands[:, :2] *= (nrm > 0.1).unsqueeze(1)
+        lo, hi = L.MOTOR_STRENGTH_RANGE
+        self.motor_strengths[:] = (r[:, 24] * (hi - lo) + lo).unsqueeze(1)
+        rn0 = hd["reset0_normal"] if "reset0_normal" in hd else float(self.np_rng.normal(0, 0.02))
+        self._height_noise_offset[:] = self._height_noise_offset * 0.0 + rn0
+        for t in (self.last_actions, self.last_actions_2, self.last_dof_vel, self.feet_air_time, self.pitch_est, self._lag,
+                  self._stumb, self._episode_sums, self._contact_filt, self._last_contacts, self.lin_vel_buffer,
+                  self.ang_vel_buffer, self.cmd_buffer, self._forces0):
+            t.zero_()
+        self.episode_length_buf.zero_()
+
+    # overridable hooks kept for API parity; the fused kernels implement them (see module docstring)
+    def check_termination(self):
+        raise NotImplementedError("fused into dtc_env_reward_reset; subclass hooks are not supported on the CUDA path")
+
+    compute_reward = compute_observations = check_termination
+
+
+class _LazyExtras(dict):
+    """`extras` of step(): "time_outs" [N] bool and, when some env was reset, "episode" means
+    (legged_robot.py:253-264).  The episode means need a device->host decision (was anything reset?), so they are
+    materialised only when a consumer actually looks - the training loop's logger - keeping the step sync-free."""
+
+    def __init__(self, env):
+        super().__init__()
+        self._env = env
+        self._stats = env._episode_stats.clone()
+        self["time_outs"] = env.time_out_buf.bool()
+        self._done = False
+
+    def _materialise(self):
+        if self._done:
+            return
+        self._done = True
+        s = self._stats.tolist()
+        if s[24] > 0:
+            ep = {"rew_" + k: torch.tensor(s[i] / s[24] / L.EPISODE_LENGTH_S) for i, k in enumerate(L.EPISODE_SUM_NAMES)}
+            ep["terrain_level"] = torch.mean(self._env.terrain_levels.float()).cpu()
+            dict.__setitem__(self, "episode", ep)
+
+    def __contains__(self, k):
+        if k == "episode":
+            self._materialise()
+        return dict.__contains__(self, k)
+
+    def __getitem__(self, k):
+        if k == "episode":
+            self._materialise()
+        return dict.__getitem__(self, k)
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default

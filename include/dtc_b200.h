@@ -1,0 +1,237 @@
+/* dtc_b200 - C ABI of the B200-native hot path of priest-yang/Deep-Tracking-Control.
+ *
+ * The reference has no FFI: its boundary is two duck-typed Python surfaces.  The
+ * Python shims in deep-tracking-control_b200/{legged_gym,rsl_rl}/ keep those surfaces and bind the entry
+ * points below through ctypes (INTEGRATION.md shows the stub).  Every function:
+ *   - takes raw DEVICE pointers (tensor.data_ptr()), explicit sizes and a cudaStream_t (as void*);
+ *   - returns 0 on success, a negative dtc_status otherwise (message: dtc_last_error());
+ *   - never throws, never synchronises the stream, never allocates caller-visible memory
+ *     (workspaces are sized by *_workspace_bytes and supplied by the caller).
+ * Each entry point cites the reference code it replaces (paths relative to the reference root).
+ */
+#ifndef DTC_B200_H
+#define DTC_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { DTC_OK = 0, DTC_ERR_ARG = -1, DTC_ERR_CUDA = -2, DTC_ERR_STATE = -3 } dtc_status;
+
+const char* dtc_last_error(void);
+int dtc_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t dtc_launch_count(void);
+/* sizeof() of the ABI structs, for binding self-checks: 0 env_config, 1 env_buffers, 2 env_noise, 3 storage,
+ * 4 ppo_hparams, 5 param_info */
+int dtc_struct_size(int which);
+
+/* ------------------------------------------------------------------ environment half */
+
+/* Constant task description: Lite3DTCCfg (legged_gym/envs/lite3/lite3_dtc_config.py:3-181). */
+typedef struct {
+  int32_t num_envs;
+  int32_t map_rows, map_cols;      /* height_samples [rows, cols] int16 (legged_gym/utils/terrain.py:26-30) */
+  float horizontal_scale, vertical_scale, border_size;
+  float dt;                        /* control dt = decimation * sim dt */
+  int32_t max_episode_length;      /* ceil(20 s / dt) */
+  int32_t resampling_steps;        /* int(10 s / dt) */
+  int32_t push_interval;           /* ceil(15 s / dt) */
+  float max_push_vel_xy;
+  /* ranges as {lower, upper-lower}; the width is computed in double by the host, as `(upper - lower) * rand + lower`
+   * does in torch_rand_float (legged_robot.py:573-578) */
+  float cmd_lin_x[2], cmd_lin_y[2], cmd_heading[2];
+  float motor_strength[2];
+  float cmd_lin_x_max, cmd_ang_yaw_max; /* command_ranges[...][1] used by the soft tracking rewards */
+  float base_height_target, tracking_sigma, max_acc;
+  float terrain_length;            /* env_length of the curriculum rule */
+  int32_t max_terrain_level;       /* num_rows */
+  int32_t num_terrain_cols;
+  float episode_length_s;
+  float p_gain, d_gain, action_scale, torque_limit;
+  float default_dof_pos[12];
+  float dof_pos_lower[12], dof_pos_upper[12];
+  float base_init_state[13];
+  float grid_x[33], grid_y[21];    /* measured_points_x / _y as float32 */
+  float plane_op[2 * 693];         /* rows 0,1 of (A^T A)^-1 A^T (legged_robot.py:1535-1547) */
+  float reward_scale[24];          /* scale*dt in EPISODE_SUM_NAMES (alphabetical) order, termination at its slot */
+  float noise_scale_vec[53];
+  float obs_scale_lin_vel, obs_scale_ang_vel, obs_scale_dof_pos, obs_scale_dof_vel, obs_scale_height, obs_scale_force;
+  float clip_obs, clip_actions;
+} dtc_env_config;
+
+/* Device buffers of one environment batch; all float32 unless noted.  Owned by the caller (torch tensors). */
+typedef struct {
+  /* simulator tensors (legged_robot.py:759-779) */
+  float* root_states;        /* [N,13] */
+  float* dof_state;          /* [N,12,2] */
+  float* contact_forces;     /* [N,17,3] */
+  float* rigid_body_state;   /* [N,17,13] */
+  const int16_t* height_samples; /* [rows, cols] */
+  /* per-step products */
+  float* actions;            /* [N,12] clipped */
+  float* torques;            /* [N,12] */
+  float* lag_buffer;         /* [6,N,12] */
+  float* base_lin_vel;       /* [N,3] */
+  float* base_ang_vel;       /* [N,3] */
+  float* projected_gravity;  /* [N,3] */
+  float* commands;           /* [N,4] */
+  float* cmd_buffer;         /* [10,N,4] */
+  float* lin_vel_buffer;     /* [10,N,2] */
+  float* ang_vel_buffer;     /* [10,N,1] */
+  float* measured_heights;   /* [N,693] */
+  float* pred_footholds;     /* [N,4,3] */
+  int32_t* optimal_idx;      /* [N,4] */
+  int32_t* nominal_idx;      /* [N,4] */
+  float* foothold_obs;       /* [N,8] */
+  float* optimal_footholds_world; /* [N,4,3] */
+  float* center_clear_mean;  /* [N] mean(root_z - clip(heights[210:483], 0)) for check_termination */
+  float* plane_ab;           /* [N,2] LS plane slopes for _reward_orientation */
+  float* foot_clearance;     /* [N,4] */
+  uint8_t* contact_filt;     /* [N,4] */
+  uint8_t* last_contacts;    /* [N,4] */
+  uint8_t* stumb_buffer;     /* [5,N,4] */
+  float* feet_air_time;      /* [N,4] */
+  float* pitch_est;          /* [N] */
+  float* last_actions;       /* [N,12] */
+  float* last_actions_2;     /* [N,12] */
+  float* last_dof_vel;       /* [N,12] */
+  float* last_root_vel;      /* [N,6] */
+  float* last_foot_vel;      /* [N,4,3] */
+  float* motor_strengths;    /* [N,12] */
+  float* robot_mass;         /* [N] */
+  float* height_noise_offset;/* [N] (reference stores it broadcast to [N,693]) */
+  float* forces0;            /* [N,3] forces[:,0,:] */
+  int64_t* episode_length_buf; /* [N] */
+  int64_t* terrain_levels;   /* [N] */
+  int64_t* terrain_types;    /* [N] */
+  float* env_origins;        /* [N,3] */
+  const float* terrain_origins; /* [rows, cols, 3] */
+  uint8_t* reset_buf;        /* [N] */
+  uint8_t* time_out_buf;     /* [N] */
+  float* rew_buf;            /* [N] */
+  float* episode_sums;       /* [24,N] */
+  float* reward_terms;       /* [24,N] this step's scaled terms (debug / tests) */
+  float* obs_buf;            /* [N,53] */
+  float* privileged_obs_buf; /* [N, priv_ld] */
+  float* obs_history;        /* [N, hist_ld] (HistoryWrapper state) */
+  float* episode_stats;      /* [26]: per-key sum of episode_sums over envs reset this step (24), count, unused */
+  int32_t priv_ld, hist_ld;
+} dtc_env_buffers;
+
+/* Optional injected randomness (tests); any pointer may be NULL -> in-kernel Philox(seed, step, env). */
+typedef struct {
+  const float* resample_u;   /* [N,3] U[0,1): lin_vel_x, lin_vel_y, heading (legged_robot.py:573-576) */
+  const float* push_u;       /* [N,2] (legged_robot.py:677) */
+  const float* reset_u;      /* [N,25]: 0 curriculum randint, 1..12 dof, 13..14 xy, 15..20 vel, 21..23 cmd, 24 motor */
+  const float* priv_u;       /* [N,693] rand_like(heights) (legged_robot_dtc.py:278) */
+  const float* obs_u;        /* [N,53]  rand_like(obs_buf)  (legged_robot_dtc.py:287) */
+} dtc_env_noise;
+
+typedef struct dtc_env dtc_env;
+int dtc_env_create(const dtc_env_config* cfg, dtc_env** out);
+void dtc_env_destroy(dtc_env* e);
+int dtc_env_bind(dtc_env* e, const dtc_env_buffers* buf);
+
+/* E1+E2: clip actions, 4x PD torque with the lag buffer (legged_robot.py:92-111,595-630).
+ * lag_choice[4]: the host draws np.random.randint(1,5) per sub-step like the reference (:608). */
+int dtc_env_pre_physics(dtc_env* e, const float* actions_in, const int32_t lag_choice[4], void* stream);
+
+/* E3+E4(commands part): base velocities, history buffers, command resampling, heading command
+ * (legged_robot_dtc.py:66-91, legged_robot.py:534-539,567-593). */
+int dtc_env_state_prep(dtc_env* e, int64_t common_step_counter, uint64_t seed, const dtc_env_noise* noise, void* stream);
+
+/* E5 + E7..E10: height sampling, Raibert footholds, terrain score, argmin, decode
+ * (legged_robot.py:1279-1317; legged_robot_dtc.py:100-201).  THE foothold-scoring kernel.
+ * variant 0 = L2 gathers, 1 = TMA-staged heightmap patch. debug_score may be NULL or [N,693,4]. */
+int dtc_foothold_step(dtc_env* e, int variant, float* debug_score, void* stream);
+
+/* E4(rest), E6, E11, E12, E13: push, foot clearance, contact filter, termination, 23 rewards, reset
+ * (legged_robot.py:546-564,1443-1472,274-291,200-272; legged_robot_dtc.py:229-245,522-586).
+ * reset_normal: the host's np.random.normal(0,0.02) of legged_robot.py:230. */
+int dtc_env_reward_reset(dtc_env* e, int64_t common_step_counter, uint64_t seed, float reset_normal,
+                         const dtc_env_noise* noise, void* stream);
+
+/* E14+E15+E1(clip): observations, privileged observations, noise, clip, history shift
+ * (legged_robot_dtc.py:254-287; legged_robot.py:118-121; history_wrapper.py:23) and the last_* roll (:215-219). */
+int dtc_env_observe(dtc_env* e, int64_t common_step_counter, uint64_t seed, const dtc_env_noise* noise, void* stream);
+
+/* ------------------------------------------------------------------ learner half */
+
+/* Parameter table: flat float32 buffer; weights stored [out, ld] with ld = round_up(in,4), zero padded. */
+typedef struct { char name[48]; int64_t offset; int32_t rows, cols, ld; } dtc_param_info;
+int dtc_param_count(void);
+int dtc_param_get(int i, dtc_param_info* out);
+int64_t dtc_param_total_floats(void);
+/* [begin,end) float ranges touched by the VAE optimizer step / the policy optimizer step */
+int dtc_param_range(int which /*0 vae-step, 1 policy-step, 2 all vae params, 3 all*/, int64_t* begin, int64_t* end);
+
+typedef struct dtc_learner dtc_learner;
+int64_t dtc_learner_workspace_bytes(int32_t max_rows);
+int dtc_learner_create(int32_t max_rows, float* params, float* grads, float* adam_main_m, float* adam_main_v,
+                       float* adam_vae_m, float* adam_vae_v, void* workspace, int64_t workspace_bytes,
+                       dtc_learner** out);
+void dtc_learner_destroy(dtc_learner* l);
+
+/* P6: PPO.act = ActorCriticDecoder.act + evaluate + log_prob (ppo.py:137-155; actor_critic_decoder.py:409-451,540-551).
+ * eps_z [M,16] / eps_a [M,12] standard normal draws or NULL (Philox). Outputs actions/mean/sigma [M,12], values/logp [M]. */
+int dtc_policy_act(dtc_learner* l, int32_t M, const float* obs, int32_t obs_ld, const float* hist, int32_t hist_ld,
+                   const float* priv, int32_t priv_ld, const float* base_vel, int32_t bv_ld,
+                   const float* eps_z, const float* eps_a, uint64_t seed, uint64_t counter,
+                   float* actions, float* values, float* logp, float* mean, float* sigma, void* stream);
+/* P4 alone (ppo.py:170-171) */
+int dtc_policy_evaluate(dtc_learner* l, int32_t M, const float* obs, int32_t obs_ld, const float* priv, int32_t priv_ld,
+                        const float* base_vel, int32_t bv_ld, float* values, void* stream);
+
+/* P7+P8: bootstrap-on-timeout and the 13 copies of RolloutStorage.add_transitions in one launch
+ * (ppo.py:157-168; rollout_storage.py:99-116). */
+typedef struct {
+  float *observations, *next_observations, *privileged_observations, *observation_histories;
+  float *rewards, *actions, *actions_log_prob, *values, *returns, *advantages, *mu, *sigma, *base_vel;
+  uint8_t* dones;
+  int32_t T, N, obs_ld, priv_ld, hist_ld, bv_ld;
+} dtc_storage;
+int dtc_store_transition(const dtc_storage* s, int32_t step, const float* obs, int32_t obs_ld_in, const float* next_obs,
+                         const float* priv, int32_t priv_ld_in, const float* hist, int32_t hist_ld_in,
+                         const float* actions, const float* rewards, const uint8_t* dones, const uint8_t* time_outs,
+                         const float* values, const float* logp, const float* mean, const float* sigma,
+                         const float* base_vel, int32_t bv_ld_in, float gamma, void* stream);
+
+/* P9: GAE reverse scan + advantage normalisation (rollout_storage.py:138-152).
+ * scratch: >= 4096 doubles.  If stats_only_local != 0 the {sum, sumsq, count} triple is left in scratch[0..2]
+ * for a cross-rank all-reduce and dtc_gae_normalize finishes the job. */
+int dtc_gae(const dtc_storage* s, const float* last_values, float gamma, float lam, double* scratch, int defer_normalize, void* stream);
+int dtc_gae_normalize(const dtc_storage* s, const double* stats3, void* stream);
+
+/* P10: minibatch row gather by permutation (rollout_storage.py:165-214); dst is a second dtc_storage with T*N rows. */
+int dtc_gather_minibatch(const dtc_storage* src, const dtc_storage* dst, const int64_t* perm, int64_t rows, void* stream);
+
+/* P11 / P12: one VAE optimizer step / one policy optimizer step on rows [row0,row0+M) of a (gathered) storage
+ * (ppo.py:197-254 / :265-338), forward + hand-written backward + clip_grad_norm_ + Adam.
+ * eps: [M,16] normal draws or NULL.  Loss sums accumulate into the learner's device-side statistics.
+ * If sync_grads != 0 the call stops after backward (gradients + grad-norm partials ready) so the caller can
+ * all-reduce `grads[range]`, then calls dtc_optimizer_apply. */
+typedef struct { float clip_param, value_loss_coef, entropy_coef, max_grad_norm, desired_kl; int32_t adaptive_lr; } dtc_ppo_hparams;
+int dtc_vae_step(dtc_learner* l, const dtc_storage* batch, int64_t row0, int32_t M, const float* eps, uint64_t seed,
+                 uint64_t counter, const dtc_ppo_hparams* hp, int sync_grads, float grad_scale, void* stream);
+int dtc_ppo_step(dtc_learner* l, const dtc_storage* batch, int64_t row0, int32_t M, const float* eps, uint64_t seed,
+                 uint64_t counter, const dtc_ppo_hparams* hp, int sync_grads, float grad_scale, void* stream);
+int dtc_optimizer_apply(dtc_learner* l, int which /*0 vae, 1 policy*/, const dtc_ppo_hparams* hp, void* stream);
+
+/* learner statistics (device doubles): [0] value_loss sum, [1] surrogate sum, [2] recons, [3] vel, [4] kld,
+ * [5] height, [6] entropy, [7] last kl_mean, [8] learning_rate, [9] last grad norm (vae), [10] last grad norm (policy) */
+double* dtc_learner_stats(dtc_learner* l);
+int dtc_learner_set_lr(dtc_learner* l, double lr, void* stream);
+int dtc_learner_reset_stats(dtc_learner* l, void* stream);
+int dtc_learner_set_adam_steps(dtc_learner* l, int64_t vae_steps, int64_t main_steps);
+/* debug access to named activation / gradient buffers of the last step (tests) */
+int dtc_learner_debug_buffer(dtc_learner* l, const char* name, float** ptr, int32_t* rows, int32_t* cols, int32_t* ld);
+
+/* plain GEMM entry (tests / microbench): C[M,N] = act(A[M,K] * W[N,K]^T + bias) */
+int dtc_linear_forward(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* W, int32_t ldw,
+                       const float* bias, int32_t act /*0 none,1 relu,2 elu*/, float* C, int32_t ldc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
