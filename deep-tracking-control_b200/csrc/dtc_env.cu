@@ -534,6 +534,7 @@ extern "C" int dtc_env_create(const dtc_env_config* cfg, dtc_env** out) {
   e->cfg = *cfg;
   e->bound = false;
   e->tmap_ready = false;
+  e->d_tmap = nullptr;
   cudaError_t ce = cudaMalloc(&e->d_cfg, sizeof(dtc_env_config));
   if (ce == cudaSuccess) ce = cudaMemcpy(e->d_cfg, cfg, sizeof(dtc_env_config), cudaMemcpyHostToDevice);
   if (ce != cudaSuccess) { delete e; DTC_FAIL(DTC_ERR_CUDA, "dtc_env_create: %s", cudaGetErrorString(ce)); }
@@ -543,6 +544,7 @@ extern "C" int dtc_env_create(const dtc_env_config* cfg, dtc_env** out) {
 extern "C" void dtc_env_destroy(dtc_env* e) {
   if (!e) return;
   cudaFree(e->d_cfg);
+  if (e->d_tmap) cudaFree(e->d_tmap);
   delete e;
 }
 extern "C" int dtc_env_bind(dtc_env* e, const dtc_env_buffers* buf) {

@@ -9,4 +9,5 @@ struct dtc_env {
   dtc_env_config* d_cfg;  // device copy (tables are too large for kernel parameters)
   CUtensorMap tmap;       // heightmap descriptor for the TMA variant of the foothold kernel
   bool tmap_ready;
+  CUtensorMap* d_tmap;    // device-memory copy of the descriptor (variant 2)
 };

@@ -20,6 +20,7 @@
 
 #define FH_WARPS 4
 #define PATCH 48  // cells per side; sampling box <= 1.89 m = 38 cells (+1 halo); 48*2 B rows are 16-B multiples for TMA
+#define PATCH_W 56  // row length of the 1-D bulk-copy variant (column origin rounded down to 8 cells = 16 B)
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
@@ -28,11 +29,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 template <int VARIANT>
 __global__ void __launch_bounds__(FH_WARPS * 32)
 k_foothold(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, float* __restrict__ dbg_score,
-           const __grid_constant__ CUtensorMap tmap) {
+           const __grid_constant__ CUtensorMap tmap, const CUtensorMap* __restrict__ tmap_g) {
+  // VARIANT 0: taps through L1/L2.  1: TMA tensor box, descriptor in kernel params.  2: same, descriptor in global
+  // memory.  3: TMA 1-D bulk row copies (cp.async.bulk, no descriptor).
+  constexpr bool STAGED = VARIANT != 0;
+  constexpr int PW = VARIANT == 3 ? PATCH_W : PATCH;
   __shared__ float mh_s[FH_WARPS][NP + 3];
   __shared__ float sc_s[FH_WARPS][NP + 3];  // s in [0,0.1) or 10; negative marks an exception point
   __shared__ float gx_s[GXN], gy_s[GYN];
-  __shared__ __align__(128) int16_t patch_s[VARIANT == 1 ? FH_WARPS : 1][VARIANT == 1 ? PATCH * PATCH : 8];
+  __shared__ __align__(128) int16_t patch_s[STAGED ? FH_WARPS : 1][STAGED ? PATCH * PW : 8];
   __shared__ __align__(8) uint64_t mbar_s[FH_WARPS];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -40,7 +45,7 @@ k_foothold(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, float* __r
   const int n = blockIdx.x * FH_WARPS + warp;
   if (threadIdx.x < GXN) gx_s[threadIdx.x] = cfg->grid_x[threadIdx.x];
   if (threadIdx.x >= 64 && threadIdx.x < 64 + GYN) gy_s[threadIdx.x - 64] = cfg->grid_y[threadIdx.x - 64];
-  if (VARIANT == 1 && lane == 0) {
+  if (STAGED && lane == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar_s[warp])));
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -56,21 +61,35 @@ k_foothold(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, float* __r
   const int16_t* __restrict__ hs = b.height_samples;
 
   int ox = 0, oy = 0;
-  if (VARIANT == 1) {
+  if (STAGED) {
     // patch origin: cell of the robot minus 21 (radius 0.943 m = 18.9 cells, +1 tap, +1 truncation slack)
     ox = (int)floorf((root_x + border) / hscale) - 21;
     oy = (int)floorf((root_y + border) / hscale) - 21;
-    if (lane == 0) {
-      uint32_t mb = smem_u32(&mbar_s[warp]);
+    const uint32_t mb = smem_u32(&mbar_s[warp]);
+    if (VARIANT == 3) {
+      oy = min(max(oy & ~7, 0), cols - PW);  // 16-byte aligned column origin, kept inside the map
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(PATCH * PW * 2) : "memory");
+      __syncwarp();
+      for (int r = lane; r < PATCH; r += 32) {
+        int row = min(max(ox + r, 0), rows - 1);
+        const int16_t* src = hs + (size_t)row * cols + oy;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(&patch_s[warp][r * PW])),
+                     "l"(src), "r"(PW * 2), "r"(mb)
+                     : "memory");
+      }
+    } else if (lane == 0) {
+      const void* desc = VARIANT == 1 ? (const void*)&tmap : (const void*)tmap_g;
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(PATCH * PATCH * 2) : "memory");
       asm volatile(
           "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
               smem_u32(&patch_s[warp][0])),
-          "l"(&tmap), "r"(oy), "r"(ox), "r"(mb)
+          "l"(desc), "r"(oy), "r"(ox), "r"(mb)
           : "memory");
     }
-    // all lanes wait for the box (phase parity 0; one box per warp lifetime)
-    uint32_t done = 0, mb = smem_u32(&mbar_s[warp]);
+    // all lanes wait for the patch (phase parity 0; one patch per warp lifetime)
+    uint32_t done = 0;
     while (!done) {
       asm volatile(
           "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
@@ -99,9 +118,9 @@ k_foothold(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, float* __r
     py = min(max(py, 0), cols - 2);
     int h1, h2, h3;
     int lx = px - ox, ly = py - oy;
-    if (VARIANT == 1 && lx >= 0 && ly >= 0 && lx < PATCH - 1 && ly < PATCH - 1) {
-      const int16_t* pt = &patch_s[warp][lx * PATCH + ly];
-      h1 = pt[0]; h2 = pt[PATCH]; h3 = pt[1];
+    if (STAGED && lx >= 0 && ly >= 0 && lx < PATCH - 1 && ly < PW - 1) {
+      const int16_t* pt = &patch_s[warp][lx * PW + ly];
+      h1 = pt[0]; h2 = pt[PW]; h3 = pt[1];
     } else {
       const int16_t* g = hs + (size_t)px * cols + py;
       h1 = __ldg(g); h2 = __ldg(g + cols); h3 = __ldg(g + 1);
@@ -258,6 +277,8 @@ static int make_heightmap_tmap(dtc_env* e) {
                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) DTC_FAIL(DTC_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+  if (!e->d_tmap) DTC_CUDA(cudaMalloc(&e->d_tmap, sizeof(CUtensorMap)));
+  DTC_CUDA(cudaMemcpy(e->d_tmap, &e->tmap, sizeof(CUtensorMap), cudaMemcpyHostToDevice));
   e->tmap_ready = true;
   return DTC_OK;
 }
@@ -267,12 +288,16 @@ extern "C" int dtc_foothold_step(dtc_env* e, int variant, float* debug_score, vo
   cudaStream_t st = (cudaStream_t)stream;
   int N = e->cfg.num_envs;
   dim3 grid(ceil_div(N, FH_WARPS)), block(FH_WARPS * 32);
-  if (variant == 1) {
-    if ((e->cfg.map_cols * 2) % 16 != 0) DTC_FAIL(DTC_ERR_ARG, "TMA variant needs 16-byte aligned heightmap rows");
+  if (variant >= 1 && variant <= 3 && (e->cfg.map_cols * 2) % 16 != 0)
+    DTC_FAIL(DTC_ERR_ARG, "TMA variants need 16-byte aligned heightmap rows");
+  if (variant == 1 || variant == 2) {
     if (!e->tmap_ready) { int rc = make_heightmap_tmap(e); if (rc) return rc; }
-    k_foothold<1><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score, e->tmap);
+    if (variant == 1) k_foothold<1><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score, e->tmap, e->d_tmap);
+    else k_foothold<2><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score, e->tmap, e->d_tmap);
+  } else if (variant == 3) {
+    k_foothold<3><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score, e->tmap, e->d_tmap);
   } else if (variant == 0) {
-    k_foothold<0><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score, e->tmap);
+    k_foothold<0><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score, e->tmap, e->d_tmap);
   } else {
     DTC_FAIL(DTC_ERR_ARG, "dtc_foothold_step: unknown variant %d", variant);
   }

@@ -1,0 +1,32 @@
+// FP32 GEMM family for the MLP stack (forward / dgrad / wgrad) - interface.
+#pragma once
+#include "dtc_common.cuh"
+
+enum GemmEpi {
+  EPI_STORE = 0,      // C = acc
+  EPI_BIAS = 1,       // C = acc + bias[n]
+  EPI_BIAS_RELU = 2,  // C = relu(acc + bias[n])
+  EPI_BIAS_ELU = 3,   // C = elu(acc + bias[n])
+  EPI_DRELU = 4,      // C = acc * (act_src > 0)
+  EPI_DELU = 5,       // C = acc * (act_src > 0 ? 1 : act_src + 1)      (d/dx elu(x) written with y = elu(x))
+};
+
+struct GemmArgs {
+  // C[m,n] = epi( sum_k A(m,k) * B(n,k) )
+  const float* A; int lda; bool a_kc;  // a_kc: A(m,k) = A[m*lda + k]   else A[k*lda + m]
+  const float* B; int ldb; bool b_kc;  // b_kc: B(n,k) = B[n*ldb + k]   else B[k*ldb + n]
+  float* C; int ldc;
+  int M, N, K;        // logical extents.  Storage contract: every leading dimension is a multiple of 4 floats and the
+                      // padding up to it holds zeros, so float4 accesses that straddle an extent read/write zeros.
+  const float* bias;  // [N] for EPI_BIAS*
+  const float* act_src; int ld_act;  // [M, ld_act] for EPI_D*
+  int epi;
+  bool accumulate;    // C += result (dgrad fan-in)
+  int splits;         // >1: split the reduction; partial tiles go to `ws` [splits][M][ldc] and are summed into C
+  float* ws;
+};
+
+// launches on `st`; returns 0 or a negative dtc_status with the message in dtc_last_error()
+int dtc_gemm_launch(const GemmArgs& a, cudaStream_t st);
+// column sums: out[n] = sum_m X[m*ld + n]  (bias gradients); ws >= 64*N floats
+int dtc_colsum_launch(const float* X, int ld, int M, int N, float* out, float* ws, cudaStream_t st);

@@ -58,4 +58,5 @@ def run(N=16384, iters=50, warmup=5, variants=(0, 1)):
 
 if __name__ == "__main__":
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
-    print(json.dumps({"N": N, **run(N)}))
+    variants = tuple(int(v) for v in sys.argv[2].split(",")) if len(sys.argv) > 2 else (0,)
+    print(json.dumps({"N": N, **run(N, variants=variants)}))
