@@ -55,21 +55,23 @@ class EnvNoise(C.Structure):
     _fields_ = [(n, vp) for n in ("resample_u", "push_u", "reset_u", "priv_u", "obs_u")]
 
 
-STORAGE_PTRS = ["observations", "next_observations", "privileged_observations", "observation_histories", "rewards",
-                "actions", "actions_log_prob", "values", "returns", "advantages", "mu", "sigma", "base_vel", "dones"]
+STORAGE_PTRS = ["hist", "priv_a", "xc", "next_obs", "actions", "mu", "sigma", "rewards", "values", "returns",
+                "advantages", "logp", "dones"]
 
 
 class Storage(C.Structure):
-    _fields_ = [(n, vp) for n in STORAGE_PTRS] + [(n, C.c_int32) for n in ("T", "N", "obs_ld", "priv_ld", "hist_ld", "bv_ld")]
+    _fields_ = [(n, vp) for n in STORAGE_PTRS] + [("T", C.c_int32), ("N", C.c_int32)]
 
 
 class PPOHParams(C.Structure):
     _fields_ = [("clip_param", C.c_float), ("value_loss_coef", C.c_float), ("entropy_coef", C.c_float),
-                ("max_grad_norm", C.c_float), ("desired_kl", C.c_float), ("adaptive_lr", C.c_int32)]
+                ("max_grad_norm", C.c_float), ("desired_kl", C.c_float), ("adaptive_lr", C.c_int32),
+                ("use_clipped_value_loss", C.c_int32), ("reserved", C.c_int32)]
 
 
 class ParamInfo(C.Structure):
-    _fields_ = [("name", C.c_char * 48), ("offset", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32), ("ld", C.c_int32)]
+    _fields_ = [("name", C.c_char * 48), ("offset", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32), ("ld", C.c_int32),
+                ("nseg", C.c_int32), ("seg_src", C.c_int32 * 4), ("seg_dst", C.c_int32 * 4), ("seg_len", C.c_int32 * 4)]
 
 
 class DtcError(RuntimeError):
@@ -96,10 +98,7 @@ def lib():
     L.dtc_env_reward_reset.argtypes = [vp, C.c_int64, C.c_uint64, C.c_float, C.POINTER(EnvNoise), vp]
     L.dtc_env_observe.argtypes = [vp, C.c_int64, C.c_uint64, C.POINTER(EnvNoise), vp]
     if not hasattr(L, "dtc_learner_create"):
-        if os.environ.get("DTC_ALLOW_PARTIAL") != "1":
-            raise DtcError("libdtc_b200.so was built without the learner kernels - rebuild")
-        _lib = L
-        return L
+        raise DtcError("libdtc_b200.so was built without the learner kernels - rebuild")
     L.dtc_param_total_floats.restype = C.c_int64
     L.dtc_learner_workspace_bytes.restype = C.c_int64
     L.dtc_learner_workspace_bytes.argtypes = [C.c_int32]
@@ -110,23 +109,25 @@ def lib():
     L.dtc_learner_create.argtypes = [C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.POINTER(vp)]
     L.dtc_learner_destroy.argtypes = [vp]
     L.dtc_learner_destroy.restype = None
-    i32, u64 = C.c_int32, C.c_uint64
-    L.dtc_policy_act.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, u64, u64, vp, vp, vp, vp, vp, vp]
+    i32, u64, SP = C.c_int32, C.c_uint64, C.POINTER(Storage)
+    L.dtc_policy_act.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, u64, u64, SP, i32, vp, vp, vp, vp, vp, vp]
     L.dtc_policy_evaluate.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp, vp]
-    L.dtc_store_transition.argtypes = [C.POINTER(Storage), i32, vp, i32, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp,
-                                       vp, i32, C.c_float, vp]
-    L.dtc_gae.argtypes = [C.POINTER(Storage), vp, C.c_float, C.c_float, vp, C.c_int, vp]
-    L.dtc_gae_normalize.argtypes = [C.POINTER(Storage), vp, vp]
-    L.dtc_gather_minibatch.argtypes = [C.POINTER(Storage), C.POINTER(Storage), vp, C.c_int64, vp]
-    step_args = [vp, C.POINTER(Storage), C.c_int64, i32, vp, u64, u64, C.POINTER(PPOHParams), C.c_int, C.c_float, vp]
+    L.dtc_policy_act_teacher.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp, vp]
+    L.dtc_store_transition.argtypes = [SP, i32, vp, vp, vp, vp, i32, C.c_float, vp]
+    L.dtc_gae.argtypes = [SP, vp, C.c_float, C.c_float, vp, C.c_int, vp]
+    L.dtc_gae_normalize.argtypes = [SP, vp, vp]
+    L.dtc_gather_minibatch.argtypes = [SP, SP, vp, C.c_int64, vp]
+    step_args = [vp, SP, C.c_int64, i32, vp, u64, u64, C.POINTER(PPOHParams), C.c_int, vp]
     L.dtc_vae_step.argtypes = step_args
     L.dtc_ppo_step.argtypes = step_args
-    L.dtc_optimizer_apply.argtypes = [vp, C.c_int, C.POINTER(PPOHParams), vp]
+    L.dtc_optimizer_apply.argtypes = [vp, C.c_int, C.POINTER(PPOHParams), C.c_float, i32, vp]
     L.dtc_learner_set_lr.argtypes = [vp, C.c_double, vp]
     L.dtc_learner_reset_stats.argtypes = [vp, vp]
     L.dtc_learner_set_adam_steps.argtypes = [vp, C.c_int64, C.c_int64]
+    L.dtc_learner_get_adam_steps.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.dtc_learner_debug_buffer.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.dtc_linear_forward.argtypes = [i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp]
+    L.dtc_gemm_debug.argtypes = [i32, i32, i32, vp, i32, i32, vp, i32, i32, vp, i32, i32, vp, vp]
     for which, st in enumerate((EnvConfig, EnvBuffers, EnvNoise, Storage, PPOHParams, ParamInfo)):
         got = L.dtc_struct_size(which)
         if got != C.sizeof(st):

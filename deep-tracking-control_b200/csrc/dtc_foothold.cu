@@ -101,7 +101,7 @@ k_foothold(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, float* __r
 
   // ---------------------------------------------------------------- phase 1
   double sum = 0.0, sumsq = 0.0, csum = 0.0;
-  float pa = 0.f, pb = 0.f;
+  double pa = 0.0, pb = 0.0;  // 693-term plane-fit dot products: fp64 keeps them at the correctly rounded fp32 value
   float* mh_out = b.measured_heights + (size_t)n * NP;
   const float* P0 = cfg->plane_op;
   const float* P1 = cfg->plane_op + NP;
@@ -132,8 +132,8 @@ k_foothold(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, float* __r
     sum += (double)gc;
     sumsq += (double)gc * (double)gc;
     if (p >= 10 * GYN && p < (GXN - 10) * GYN) csum += (double)__fsub_rn(root_z, fmaxf(mh, 0.f));
-    pa = fmaf(__ldg(P0 + p), mh, pa);
-    pb = fmaf(__ldg(P1 + p), mh, pb);
+    pa += (double)__ldg(P0 + p) * (double)mh;
+    pb += (double)__ldg(P1 + p) * (double)mh;
   }
   sum = warp_sum(sum);
   sumsq = warp_sum(sumsq);
@@ -147,8 +147,8 @@ k_foothold(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, float* __r
   const float edge = clampf(__fsqrt_rn((float)var_d), 0.0f, 0.3f);
   if (lane == 0) {
     b.center_clear_mean[n] = (float)(csum / (double)((GXN - 20) * GYN));
-    b.plane_ab[n * 2] = pa;
-    b.plane_ab[n * 2 + 1] = pb;
+    b.plane_ab[n * 2] = (float)pa;
+    b.plane_ab[n * 2 + 1] = (float)pb;
   }
   __syncwarp();
 

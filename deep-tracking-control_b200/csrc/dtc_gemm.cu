@@ -1,0 +1,325 @@
+// FP32 SIMT GEMM family for the MLP stack: C[m,n] = epi(sum_k A(m,k) * B(n,k)) with either operand k-contiguous or
+// k-strided, so one kernel template serves
+//   forward   Y  = act(X W^T + b)        A = X  (k contiguous)   B = W  (k contiguous)
+//   dgrad     dX = (dY W) * act'(X)      A = dY (k contiguous)   B = W  (k strided)
+//   wgrad     dW = dY^T X                A = dY (k strided)      B = X  (k strided), reduction over the batch, split-K
+// (rsl_rl/modules/actor_critic_decoder.py nn.Linear stacks and their autograd).
+// Exact fp32 FMA accumulation keeps the 1e-5 parity budget that TF32 tensor-core math would not.
+// 128 x BN x 16 tiles, 256 threads, 8 x BN/16 register micro-tile, double-buffered shared memory with register prefetch.
+#include "dtc_gemm.cuh"
+
+#define GBK 16
+#define GTHREADS 256
+
+__device__ __forceinline__ float4 ld4_guard(const float* __restrict__ p, bool row_ok, int nvalid) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!row_ok || nvalid <= 0) return v;
+  if (nvalid >= 4) return __ldg(reinterpret_cast<const float4*>(p));
+  v.x = __ldg(p);
+  if (nvalid > 1) v.y = __ldg(p + 1);
+  if (nvalid > 2) v.z = __ldg(p + 2);
+  return v;
+}
+
+__device__ __forceinline__ float epi_apply(float v, int epi, float bias, float src) {
+  switch (epi) {
+    case EPI_BIAS: return v + bias;
+    case EPI_BIAS_RELU: v += bias; return v > 0.f ? v : 0.f;
+    case EPI_BIAS_ELU: v += bias; return v > 0.f ? v : expm1f(v);
+    case EPI_DRELU: return src > 0.f ? v : 0.f;
+    case EPI_DELU: return src > 0.f ? v : v * (src + 1.0f);
+    default: return v;
+  }
+}
+
+template <int BM, int BN, bool AKC, bool BKC>
+__global__ void __launch_bounds__(GTHREADS, 2) k_gemm(const GemmArgs g) {
+  constexpr int TM = BM / 16, TN = BN / 16;
+  constexpr int LDAS = BM + 4, LDBS = BN + 4;
+  constexpr int NA4 = BM * GBK / 4, NB4 = BN * GBK / 4;
+  constexpr int LA = (NA4 + GTHREADS - 1) / GTHREADS, LB = (NB4 + GTHREADS - 1) / GTHREADS;
+  __shared__ __align__(16) float As[2][GBK][LDAS];
+  __shared__ __align__(16) float Bs[2][GBK][LDBS];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * g.k_per_split;
+  const int kend = min(g.K, kbeg + g.k_per_split);
+  const float* __restrict__ A = g.A;
+  const float* __restrict__ B = g.B;
+
+  float4 ra[LA], rb[LB];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      int f = tid + i * GTHREADS;
+      if (NA4 % GTHREADS == 0 || f < NA4) {
+        if (AKC) {
+          int m = f >> 2, gk = k0 + (f & 3) * 4, gm = m0 + m;
+          ra[i] = ld4_guard(A + (size_t)gm * g.lda + gk, gm < g.M, kend - gk);
+        } else {
+          int mq = f % (BM / 4), gk = k0 + f / (BM / 4), gm = m0 + mq * 4;
+          ra[i] = ld4_guard(A + (size_t)gk * g.lda + gm, gk < kend, g.M - gm);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      int f = tid + i * GTHREADS;
+      if (NB4 % GTHREADS == 0 || f < NB4) {
+        if (BKC) {
+          int n = f >> 2, gk = k0 + (f & 3) * 4, gn = n0 + n;
+          rb[i] = ld4_guard(B + (size_t)gn * g.ldb + gk, gn < g.N, kend - gk);
+        } else {
+          int nq = f % (BN / 4), gk = k0 + f / (BN / 4), gn = n0 + nq * 4;
+          rb[i] = ld4_guard(B + (size_t)gk * g.ldb + gn, gk < kend, g.N - gn);
+        }
+      }
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      int f = tid + i * GTHREADS;
+      if (NA4 % GTHREADS == 0 || f < NA4) {
+        if (AKC) {
+          int m = f >> 2, k = (f & 3) * 4;
+          As[buf][k + 0][m] = ra[i].x; As[buf][k + 1][m] = ra[i].y; As[buf][k + 2][m] = ra[i].z; As[buf][k + 3][m] = ra[i].w;
+        } else {
+          int mq = f % (BM / 4), k = f / (BM / 4);
+          *reinterpret_cast<float4*>(&As[buf][k][mq * 4]) = ra[i];
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      int f = tid + i * GTHREADS;
+      if (NB4 % GTHREADS == 0 || f < NB4) {
+        if (BKC) {
+          int n = f >> 2, k = (f & 3) * 4;
+          Bs[buf][k + 0][n] = rb[i].x; Bs[buf][k + 1][n] = rb[i].y; Bs[buf][k + 2][n] = rb[i].z; Bs[buf][k + 3][n] = rb[i].w;
+        } else {
+          int nq = f % (BN / 4), k = f / (BN / 4);
+          *reinterpret_cast<float4*>(&Bs[buf][k][nq * 4]) = rb[i];
+        }
+      }
+    }
+  };
+  auto mrow = [&](int i) { return TM == 8 ? ((i >> 2) * (BM / 2) + ty * 4 + (i & 3)) : ty * TM + i; };
+  auto ncol = [&](int j) { return TN == 8 ? ((j >> 2) * (BN / 2) + tx * 4 + (j & 3)) : tx * TN + j; };
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int nk = kend > kbeg ? (kend - kbeg + GBK - 1) / GBK : 0;
+  if (nk > 0) {
+    load_tiles(kbeg);
+    store_tiles(0);
+  }
+  __syncthreads();
+  for (int t = 0; t < nk; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < nk) load_tiles(kbeg + (t + 1) * GBK);
+#pragma unroll
+    for (int kk = 0; kk < GBK; ++kk) {
+      float a[TM], b[TN];
+      if constexpr (TM == 8) {
+        float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+        float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][BM / 2 + ty * 4]);
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4 % TM] = a1.x; a[5 % TM] = a1.y; a[6 % TM] = a1.z; a[7 % TM] = a1.w;
+      } else if constexpr (TM == 4) {
+        float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+        a[0] = a0.x; a[1 % TM] = a0.y; a[2 % TM] = a0.z; a[3 % TM] = a0.w;
+      } else {
+        float2 a0 = *reinterpret_cast<const float2*>(&As[buf][kk][ty * 2]);
+        a[0] = a0.x; a[1 % TM] = a0.y;
+      }
+      if constexpr (TN == 8) {
+        float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+        float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][BN / 2 + tx * 4]);
+        b[0] = b0.x; b[1 % TN] = b0.y; b[2 % TN] = b0.z; b[3 % TN] = b0.w; b[4 % TN] = b1.x; b[5 % TN] = b1.y; b[6 % TN] = b1.z; b[7 % TN] = b1.w;
+      } else if constexpr (TN == 4) {
+        float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+        b[0] = b0.x; b[1 % TN] = b0.y; b[2 % TN] = b0.z; b[3 % TN] = b0.w;
+      } else if constexpr (TN == 2) {
+        float2 b0 = *reinterpret_cast<const float2*>(&Bs[buf][kk][tx * 2]);
+        b[0] = b0.x; b[1 % TN] = b0.y;
+      } else {
+        b[0] = Bs[buf][kk][tx];
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (t + 1 < nk) store_tiles(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---------------------------------------------------------------- epilogue
+  const bool partial = g.splits > 1;
+  const int n4 = (g.N + 3) & ~3;
+  float* __restrict__ out = partial ? g.ws + (size_t)blockIdx.z * g.M * n4 : g.C;
+  const int ldo = partial ? n4 : g.ldc;
+  const int epi = partial ? EPI_STORE : g.epi;
+  const bool accum = !partial && g.accumulate;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int gm = m0 + mrow(i);
+    if (gm >= g.M) continue;
+    float* orow = out + (size_t)gm * ldo;
+    const float* srow = (epi == EPI_DRELU || epi == EPI_DELU) ? g.act_src + (size_t)gm * g.ld_act : nullptr;
+#pragma unroll
+    for (int j0 = 0; j0 < TN; j0 += 4) {
+      const int gn = n0 + ncol(j0);
+      if (TN >= 4 && gn + 3 < g.N) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float bias = (epi >= EPI_BIAS && epi <= EPI_BIAS_ELU) ? __ldg(g.bias + gn + j) : 0.f;
+          float src = srow ? __ldg(srow + gn + j) : 0.f;
+          v[j] = epi_apply(acc[i][(j0 + j) % TN], epi, bias, src);
+        }
+        float4* dst = reinterpret_cast<float4*>(orow + gn);
+        if (accum) {
+          float4 o = *dst;
+          v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+        }
+        *dst = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < (TN < 4 ? TN : 4); ++j) {
+          const int gnj = n0 + ncol((j0 + j) % TN);
+          if (gnj < g.N) {
+            float bias = (epi >= EPI_BIAS && epi <= EPI_BIAS_ELU) ? __ldg(g.bias + gnj) : 0.f;
+            float src = srow ? __ldg(srow + gnj) : 0.f;
+            float v = epi_apply(acc[i][(j0 + j) % TN], epi, bias, src);
+            if (accum) v += orow[gnj];
+            orow[gnj] = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+// sums the split-K partials: C[m,n] (+)= sum_s ws[s][m][n]
+__global__ void k_splitk_reduce(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc, int splits,
+                                int accumulate) {
+  const int n4 = (N + 3) & ~3, q = n4 >> 2;
+  const int64_t total = (int64_t)M * q;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int m = (int)(e / q), c = (int)(e - (int64_t)m * q) * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < splits; ++z) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(ws + ((size_t)z * M + m) * n4 + c));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float* dst = C + (size_t)m * ldc + c;
+    float v[4] = {s.x, s.y, s.z, s.w};
+    for (int j = 0; j < 4; ++j)
+      if (c + j < N) dst[j] = accumulate ? dst[j] + v[j] : v[j];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_colsum1(const float* __restrict__ X, int ld, int M, int N, float* __restrict__ ws) {
+  __shared__ float sh[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  const int rows = (M + COLSUM_CHUNKS - 1) / COLSUM_CHUNKS;
+  const int r0 = blockIdx.y * rows, r1 = min(M, r0 + rows);
+  float s = 0.f;
+  if (n < N)
+    for (int r = r0 + ty; r < r1; r += 8) s += __ldg(X + (size_t)r * ld + n);
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][tx];
+    ws[(size_t)blockIdx.y * N + n] = t;
+  }
+}
+__global__ void k_colsum2(const float* __restrict__ ws, int N, float* __restrict__ out) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float t = 0.f;
+  for (int c = 0; c < COLSUM_CHUNKS; ++c) t += ws[(size_t)c * N + n];
+  out[n] = t;
+}
+
+int dtc_gemm_pick_splits(int M, int N, int K) {
+  if (K < 2048) return 1;
+  int bm = M > 64 ? 128 : (M > 32 ? 64 : 32), bn = N > 64 ? 128 : 64;
+  int tiles = ceil_div(M, bm) * ceil_div(N, bn);
+  int s = ceil_div(592, tiles);
+  int smax = K / 256;
+  if (s > smax) s = smax;
+  if (s > 128) s = 128;
+  return s < 1 ? 1 : s;
+}
+
+#define LAUNCH(BM_, BN_, AKC_, BKC_)                                                       \
+  do {                                                                                     \
+    dim3 grid(ceil_div(a.N, BN_), ceil_div(a.M, BM_), a.splits);                           \
+    k_gemm<BM_, BN_, AKC_, BKC_><<<grid, GTHREADS, 0, st>>>(a);                            \
+  } while (0)
+
+int dtc_gemm_launch(GemmArgs a, cudaStream_t st) {
+  if (a.M <= 0 || a.N <= 0) return DTC_OK;
+  if ((a.lda & 3) || (a.ldb & 3) || (a.ldc & 3)) DTC_FAIL(DTC_ERR_ARG, "gemm: leading dimensions must be multiples of 4");
+  if (((uintptr_t)a.A | (uintptr_t)a.B | (uintptr_t)a.C) & 15) DTC_FAIL(DTC_ERR_ARG, "gemm: operands must be 16-byte aligned");
+  if (a.splits < 1) a.splits = 1;
+  if (a.splits > 1 && (a.epi != EPI_STORE || !a.ws)) DTC_FAIL(DTC_ERR_ARG, "gemm: split-K needs EPI_STORE and a workspace");
+  a.k_per_split = ((ceil_div(a.K, a.splits) + GBK - 1) / GBK) * GBK;
+  if (a.k_per_split == 0) a.k_per_split = GBK;
+  if (a.a_kc && a.b_kc) {
+    if (a.N > 64) LAUNCH(128, 128, true, true);
+    else if (a.N > 32) LAUNCH(128, 64, true, true);
+    else if (a.N > 16) LAUNCH(128, 32, true, true);
+    else LAUNCH(128, 16, true, true);
+  } else if (a.a_kc && !a.b_kc) {
+    if (a.N > 64) LAUNCH(128, 128, true, false);
+    else if (a.N > 32) LAUNCH(128, 64, true, false);
+    else if (a.N > 16) LAUNCH(128, 32, true, false);
+    else LAUNCH(128, 16, true, false);
+  } else if (!a.a_kc && !a.b_kc) {
+    if (a.M > 64) { if (a.N > 64) LAUNCH(128, 128, false, false); else LAUNCH(128, 64, false, false); }
+    else if (a.M > 32) { if (a.N > 64) LAUNCH(64, 128, false, false); else LAUNCH(64, 64, false, false); }
+    else { if (a.N > 64) LAUNCH(32, 128, false, false); else LAUNCH(32, 64, false, false); }
+  } else {
+    DTC_FAIL(DTC_ERR_ARG, "gemm: unsupported operand layout");
+  }
+  DTC_CHECK_LAUNCH("k_gemm");
+  if (a.splits > 1) {
+    int64_t total = (int64_t)a.M * ((a.N + 3) / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_splitk_reduce<<<blocks, 256, 0, st>>>(a.ws, a.C, a.M, a.N, a.ldc, a.splits, a.accumulate ? 1 : 0);
+    DTC_CHECK_LAUNCH("k_splitk_reduce");
+  }
+  return DTC_OK;
+}
+
+int dtc_colsum_launch(const float* X, int ld, int M, int N, float* out, float* ws, cudaStream_t st) {
+  dim3 grid(ceil_div(N, 32), COLSUM_CHUNKS);
+  k_colsum1<<<grid, 256, 0, st>>>(X, ld, M, N, ws);
+  DTC_CHECK_LAUNCH("k_colsum1");
+  k_colsum2<<<ceil_div(N, 256), 256, 0, st>>>(ws, N, out);
+  DTC_CHECK_LAUNCH("k_colsum2");
+  return DTC_OK;
+}
+
+extern "C" int dtc_linear_forward(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* W, int32_t ldw,
+                                  const float* bias, int32_t act, float* C, int32_t ldc, void* stream) {
+  GemmArgs g{};
+  g.A = A; g.lda = lda; g.a_kc = true;
+  g.B = W; g.ldb = ldw; g.b_kc = true;
+  g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+  g.bias = bias;
+  g.epi = bias ? (act == 1 ? EPI_BIAS_RELU : act == 2 ? EPI_BIAS_ELU : EPI_BIAS) : EPI_STORE;
+  g.splits = 1;
+  return dtc_gemm_launch(g, (cudaStream_t)stream);
+}

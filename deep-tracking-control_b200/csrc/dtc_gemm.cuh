@@ -16,17 +16,21 @@ struct GemmArgs {
   const float* A; int lda; bool a_kc;  // a_kc: A(m,k) = A[m*lda + k]   else A[k*lda + m]
   const float* B; int ldb; bool b_kc;  // b_kc: B(n,k) = B[n*ldb + k]   else B[k*ldb + n]
   float* C; int ldc;
-  int M, N, K;        // logical extents.  Storage contract: every leading dimension is a multiple of 4 floats and the
-                      // padding up to it holds zeros, so float4 accesses that straddle an extent read/write zeros.
+  int M, N, K;        // logical extents.  Storage contract: every base pointer is 16-byte aligned and every leading
+                      // dimension is a multiple of 4 floats; tails inside a float4 are masked by the loaders.
   const float* bias;  // [N] for EPI_BIAS*
   const float* act_src; int ld_act;  // [M, ld_act] for EPI_D*
   int epi;
   bool accumulate;    // C += result (dgrad fan-in)
   int splits;         // >1: split the reduction; partial tiles go to `ws` [splits][M][ldc] and are summed into C
   float* ws;
+  int k_per_split;    // filled by the launcher
 };
 
 // launches on `st`; returns 0 or a negative dtc_status with the message in dtc_last_error()
-int dtc_gemm_launch(const GemmArgs& a, cudaStream_t st);
-// column sums: out[n] = sum_m X[m*ld + n]  (bias gradients); ws >= 64*N floats
+int dtc_gemm_launch(GemmArgs a, cudaStream_t st);
+// splits the launcher would pick for a reduction of length K producing an MxN output (workspace sizing)
+int dtc_gemm_pick_splits(int M, int N, int K);
+// column sums: out[n] = sum_m X[m*ld + n]  (bias gradients); ws >= COLSUM_CHUNKS*N floats
+#define COLSUM_CHUNKS 64
 int dtc_colsum_launch(const float* X, int ld, int M, int N, float* out, float* ws, cudaStream_t st);

@@ -1,0 +1,198 @@
+"""`PPO` with the reference's surface (rsl_rl/rsl_rl/algorithms/ppo.py:42-357) over the fused learner kernels.
+
+act()            -> dtc_policy_act: encoder + actor + critic + sampling + log-prob, written straight into the
+                    rollout storage (the act-time half of add_transitions)
+process_env_step -> dtc_store_transition (timeout bootstrap + env-time half of add_transitions)
+compute_returns  -> dtc_policy_evaluate + dtc_gae
+update()         -> one gather for all minibatches, then per minibatch dtc_vae_step + dtc_ppo_step (forward,
+                    hand-written backward, clip_grad_norm_, Adam, adaptive-KL learning rate - all on the device; the
+                    host never waits for a value inside the loop)
+
+Data parallel: when torch.distributed is initialised with world_size > 1 each optimizer step stops
+after backward, the flat gradient range (plus the KL sum riding behind it) is all-reduced over NCCL, and
+dtc_optimizer_apply finishes with grad_scale = 1/world.  The advantage moments are all-reduced once per iteration.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from ... import _lib as B
+from ..storage import RolloutStorage
+
+
+class _DeviceAdamHandle:
+    """`alg.optimizer` of the reference, reduced to what the runner's save/load touches."""
+
+    def __init__(self, alg, which):
+        self._alg, self._which = alg, which
+
+    def state_dict(self):
+        ac = self._alg.actor_critic
+        a, b = C.c_int64(), C.c_int64()
+        if ac._h is not None:
+            B.lib().dtc_learner_get_adam_steps(ac._h, C.byref(a), C.byref(b))
+        m, v = ac._adam[0 if self._which == "main" else 2], ac._adam[1 if self._which == "main" else 3]
+        return {"layout": "dtc_b200.flat", "step": b.value if self._which == "main" else a.value,
+                "exp_avg": m.clone(), "exp_avg_sq": v.clone(), "lr": self._alg.learning_rate}
+
+    def load_state_dict(self, sd):
+        if sd.get("layout") != "dtc_b200.flat":
+            raise ValueError("optimizer state was not written by dtc_b200 (per-parameter torch.optim state is not convertible "
+                             "without the parameter order; load the model weights only)")
+        ac = self._alg.actor_critic
+        m, v = ac._adam[0 if self._which == "main" else 2], ac._adam[1 if self._which == "main" else 3]
+        m.copy_(sd["exp_avg"])
+        v.copy_(sd["exp_avg_sq"])
+        self._alg._pending_steps[self._which] = int(sd["step"])
+        if self._which == "main":
+            self._alg.learning_rate = float(sd["lr"])
+
+
+class PPO:
+    def __init__(self, actor_critic, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998, lam=0.95,
+                 value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True,
+                 schedule="fixed", desired_kl=0.01, device="cpu"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise B.DtcError("PPO runs on a CUDA device only (no CPU fallback)")
+        self.desired_kl, self.schedule = desired_kl, schedule
+        self.actor_critic = actor_critic
+        if actor_critic.device is None:
+            actor_critic.to(self.device)
+        self.storage = None
+        self.optimizer = _DeviceAdamHandle(self, "main")
+        self.vae_optimizer = _DeviceAdamHandle(self, "vae")
+        self._pending_steps = {}
+        self.transition = RolloutStorage.Transition()
+        self.clip_param = clip_param
+        self.num_learning_epochs, self.num_mini_batches = num_learning_epochs, num_mini_batches
+        self.value_loss_coef, self.entropy_coef = value_loss_coef, entropy_coef
+        self.gamma, self.lam, self.max_grad_norm = gamma, lam, max_grad_norm
+        self.use_clipped_value_loss = use_clipped_value_loss
+        self._lr_host = float(learning_rate)
+        self._lr_dirty = True
+        self._inject = None  # tests: dict(perm=LongTensor, eps=[per optimizer step [M,16] tensors, vae/ppo alternating])
+        self._update_calls = 0
+        self.group = None  # torch.distributed process group for data parallel training (None = default group)
+
+    # ------------------------------------------------------------------ learning rate lives on the device
+    @property
+    def learning_rate(self):
+        ac = self.actor_critic
+        if not self._lr_dirty and ac._h is not None:
+            self._lr_host = float(ac.stats()[8].item())
+        return self._lr_host
+
+    @learning_rate.setter
+    def learning_rate(self, v):
+        self._lr_host, self._lr_dirty = float(v), True
+
+    def _push_lr(self, h):
+        if self._lr_dirty:
+            B.check(B.lib().dtc_learner_set_lr(h, self._lr_host, B.stream_ptr(self.device)), "dtc_learner_set_lr")
+            self._lr_dirty = False
+
+    def _hparams(self):
+        hp = B.PPOHParams()
+        hp.clip_param, hp.value_loss_coef, hp.entropy_coef = self.clip_param, self.value_loss_coef, self.entropy_coef
+        hp.max_grad_norm = self.max_grad_norm
+        hp.desired_kl = self.desired_kl if self.desired_kl is not None else 0.0
+        hp.adaptive_lr = 1 if (self.desired_kl is not None and self.schedule == "adaptive") else 0
+        hp.use_clipped_value_loss = 1 if self.use_clipped_value_loss else 0
+        return hp
+
+    # ------------------------------------------------------------------ reference methods
+    def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, privileged_obs_shape, obs_history_shape, action_shape):
+        self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, privileged_obs_shape, obs_history_shape,
+                                      action_shape, self.device)
+        rows = (num_envs * num_transitions_per_env) // self.num_mini_batches
+        self.actor_critic._learner(max(rows, num_envs))
+
+    def test_mode(self):
+        self.actor_critic.eval()
+
+    def train_mode(self):
+        self.actor_critic.train()
+
+    def act(self, obs, privileged_obs, obs_history, base_vel, rew_buf=None):
+        st = self.storage
+        if st.step >= st.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        self.actor_critic._forward_act(obs, obs_history, privileged_obs, base_vel, storage=st._c, step=st.step, need_copies=False)
+        self.transition.actions = st.actions[st.step]
+        self.transition.values = st.values[st.step]
+        return self.transition.actions
+
+    def process_env_step(self, rewards, dones, next_obs, infos):
+        st = self.storage
+        to = infos["time_outs"] if "time_outs" in infos else None
+        if to is not None:
+            to = to.to(torch.uint8) if to.dtype != torch.uint8 else to
+        d = dones if dones.dtype == torch.uint8 else dones.to(torch.uint8)
+        B.check(B.lib().dtc_store_transition(C.byref(st._c), st.step, B.ptr(rewards), B.ptr(d), B.ptr(to), B.ptr(next_obs),
+                                             next_obs.stride(0), self.gamma, B.stream_ptr(self.device)), "dtc_store_transition")
+        st.step += 1
+        self.transition.clear()
+        self.actor_critic.reset(dones)
+
+    def compute_returns(self, last_critic_obs, last_critic_privileged_obs, base_vel):
+        last_values = self.actor_critic.evaluate(last_critic_obs, last_critic_privileged_obs, base_vel)
+        self.storage.compute_returns(last_values, self.gamma, self.lam, group=self.group)
+
+    def _world(self):
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self.group)
+        return 1
+
+    def update(self):
+        ac, st, lib = self.actor_critic, self.storage, B.lib()
+        T, N = st.num_transitions_per_env, st.num_envs
+        mbs = (T * N) // self.num_mini_batches
+        h = ac._learner(max(mbs, N))
+        if self._pending_steps:
+            a, b = C.c_int64(), C.c_int64()
+            lib.dtc_learner_get_adam_steps(h, C.byref(a), C.byref(b))
+            lib.dtc_learner_set_adam_steps(h, self._pending_steps.get("vae", a.value), self._pending_steps.get("main", b.value))
+            self._pending_steps = {}
+        self._push_lr(h)
+        stream = B.stream_ptr(self.device)
+        B.check(lib.dtc_learner_reset_stats(h, stream), "dtc_learner_reset_stats")
+        inj = self._inject or {}
+        self._inject = None
+        if "perm" in inj:
+            st._inject_perm = inj["perm"]
+        perm = st.draw_permutation(self.num_mini_batches * mbs)
+        batch = st.gather(perm)
+        eps_list = list(inj.get("eps", []))
+        hp = self._hparams()
+        world = self._world()
+        sync = 1 if world > 1 else 0
+        tab = ac._table
+        self._update_calls += 1
+        k = 0
+        for epoch in range(self.num_learning_epochs):
+            for i in range(self.num_mini_batches):
+                ctr = (self._update_calls << 16) + 2 * k
+                e1 = eps_list[2 * k] if eps_list else None
+                e2 = eps_list[2 * k + 1] if eps_list else None
+                k += 1
+                B.check(lib.dtc_vae_step(h, C.byref(batch._c), i * mbs, mbs, B.ptr(e1), ac.seed + 7919, ctr, C.byref(hp), sync, stream),
+                        "dtc_vae_step")
+                if sync:
+                    b0, b1 = tab.ranges["vae"]
+                    dist.all_reduce(ac._grads[b0:b1], group=self.group)
+                    B.check(lib.dtc_optimizer_apply(h, 0, C.byref(hp), 1.0 / world, mbs * world, stream), "dtc_optimizer_apply")
+                B.check(lib.dtc_ppo_step(h, C.byref(batch._c), i * mbs, mbs, B.ptr(e2), ac.seed + 7919, ctr + 1, C.byref(hp), sync, stream),
+                        "dtc_ppo_step")
+                if sync:
+                    b0, b1 = tab.ranges["policy_sync"]
+                    dist.all_reduce(ac._grads[b0:b1], group=self.group)
+                    B.check(lib.dtc_optimizer_apply(h, 1, C.byref(hp), 1.0 / world, mbs * world, stream), "dtc_optimizer_apply")
+        s = ac.stats().tolist()  # the one device->host read of update()
+        n = self.num_learning_epochs * self.num_mini_batches
+        self._lr_host = s[8]
+        self.last_stats = dict(value=s[0] / n, surrogate=s[1] / n, recons=s[2] / n, vel=s[3] / n, kld=s[4] / n, height=s[5] / n,
+                               entropy=s[6] / n, kl_mean=s[7], learning_rate=s[8], grad_norm_vae=s[9], grad_norm_policy=s[10])
+        st.clear()
+        return s[0] / n, s[1] / n, 0.0, 0, s[2] / n, s[3] / n, s[4] / n

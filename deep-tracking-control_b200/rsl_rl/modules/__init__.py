@@ -1,0 +1,1 @@
+from .actor_critic_decoder import ActorCriticDecoder, AC_Args, reference_init_state_dict  # noqa: F401

@@ -158,13 +158,35 @@ int dtc_env_observe(dtc_env* e, int64_t common_step_counter, uint64_t seed, cons
 
 /* ------------------------------------------------------------------ learner half */
 
-/* Parameter table: flat float32 buffer; weights stored [out, ld] with ld = round_up(in,4), zero padded. */
-typedef struct { char name[48]; int64_t offset; int32_t rows, cols, ld; } dtc_param_info;
+/* Parameter table.  All parameters of ActorCriticDecoder (rsl_rl/modules/actor_critic_decoder.py:91-369) live in ONE
+ * flat float32 buffer.  A weight is stored [rows, ld] (ld = in_features rounded up to 4, pad columns zero) with its
+ * input columns grouped into 16-byte aligned segments so that concatenated first-layer inputs need no copy:
+ * reference column seg_src[i]+j <-> internal column seg_dst[i]+j, j < seg_len[i].  Biases / std: rows = 1. */
+typedef struct {
+  char name[48];
+  int64_t offset;
+  int32_t rows, cols, ld;
+  int32_t nseg, seg_src[4], seg_dst[4], seg_len[4];
+} dtc_param_info;
 int dtc_param_count(void);
 int dtc_param_get(int i, dtc_param_info* out);
 int64_t dtc_param_total_floats(void);
-/* [begin,end) float ranges touched by the VAE optimizer step / the policy optimizer step */
-int dtc_param_range(int which /*0 vae-step, 1 policy-step, 2 all vae params, 3 all*/, int64_t* begin, int64_t* end);
+/* [begin,end) float ranges: 0 = VAE optimizer step (ppo.py:249-254), 1 = policy optimizer step (ppo.py:332-335),
+ * 2 = policy step range plus the piggy-back scalars that ride in the same gradient all-reduce (slot 0: sum of KL),
+ * 3 = everything */
+int dtc_param_range(int which, int64_t* begin, int64_t* end);
+
+/* Packed rollout storage (RolloutStorage, rsl_rl/storage/rollout_storage.py:36-116): R = T*N rows, time-major.
+ * Rows are laid out GEMM-ready:  hist [R,268] = obs_history 265 + 3 zero;  priv_a [R,696] = priv[:, :693] + 3 zero;
+ * xc [R,752] = priv[:, 693:1389] | obs 53 | base_vel 3  (the critic input of actor_critic_decoder.py:540-551 up to a
+ * column permutation);  next_obs [R,56];  actions/mu/sigma [R,12];  rewards/values/returns/advantages/logp [R];
+ * dones [R] uint8. */
+typedef struct {
+  float *hist, *priv_a, *xc, *next_obs, *actions, *mu, *sigma;
+  float *rewards, *values, *returns, *advantages, *logp;
+  uint8_t* dones;
+  int32_t T, N;
+} dtc_storage;
 
 typedef struct dtc_learner dtc_learner;
 int64_t dtc_learner_workspace_bytes(int32_t max_rows);
@@ -174,62 +196,68 @@ int dtc_learner_create(int32_t max_rows, float* params, float* grads, float* ada
 void dtc_learner_destroy(dtc_learner* l);
 
 /* P6: PPO.act = ActorCriticDecoder.act + evaluate + log_prob (ppo.py:137-155; actor_critic_decoder.py:409-451,540-551).
- * eps_z [M,16] / eps_a [M,12] standard normal draws or NULL (Philox). Outputs actions/mean/sigma [M,12], values/logp [M]. */
+ * eps_z [M,16] / eps_a [M,12]: standard normal draws, or NULL for in-kernel Philox(seed, counter).
+ * If `s` is not NULL the packed inputs and the outputs are written straight into rows [step*N, step*N+M) of the
+ * storage (the act-time half of add_transitions, rollout_storage.py:99-116) and M must equal s->N.
+ * actions/values/logp/mean/sigma: optional extra outputs ([M,12] / [M]). */
 int dtc_policy_act(dtc_learner* l, int32_t M, const float* obs, int32_t obs_ld, const float* hist, int32_t hist_ld,
                    const float* priv, int32_t priv_ld, const float* base_vel, int32_t bv_ld,
                    const float* eps_z, const float* eps_a, uint64_t seed, uint64_t counter,
+                   const dtc_storage* s, int32_t step,
                    float* actions, float* values, float* logp, float* mean, float* sigma, void* stream);
 /* P4 alone (ppo.py:170-171) */
 int dtc_policy_evaluate(dtc_learner* l, int32_t M, const float* obs, int32_t obs_ld, const float* priv, int32_t priv_ld,
                         const float* base_vel, int32_t bv_ld, float* values, void* stream);
+/* deployment path act_teacher (actor_critic_decoder.py:504-538): mean actions [M,12] */
+int dtc_policy_act_teacher(dtc_learner* l, int32_t M, const float* obs, int32_t obs_ld, const float* hist, int32_t hist_ld,
+                           const float* priv, int32_t priv_ld, float* actions, void* stream);
 
-/* P7+P8: bootstrap-on-timeout and the 13 copies of RolloutStorage.add_transitions in one launch
- * (ppo.py:157-168; rollout_storage.py:99-116). */
-typedef struct {
-  float *observations, *next_observations, *privileged_observations, *observation_histories;
-  float *rewards, *actions, *actions_log_prob, *values, *returns, *advantages, *mu, *sigma, *base_vel;
-  uint8_t* dones;
-  int32_t T, N, obs_ld, priv_ld, hist_ld, bv_ld;
-} dtc_storage;
-int dtc_store_transition(const dtc_storage* s, int32_t step, const float* obs, int32_t obs_ld_in, const float* next_obs,
-                         const float* priv, int32_t priv_ld_in, const float* hist, int32_t hist_ld_in,
-                         const float* actions, const float* rewards, const uint8_t* dones, const uint8_t* time_outs,
-                         const float* values, const float* logp, const float* mean, const float* sigma,
-                         const float* base_vel, int32_t bv_ld_in, float gamma, void* stream);
+/* P7+P8, env-time half: rewards (+ gamma * values * time_outs, ppo.py:157-168), dones, next_obs into row block `step`. */
+int dtc_store_transition(const dtc_storage* s, int32_t step, const float* rewards, const uint8_t* dones,
+                         const uint8_t* time_outs, const float* next_obs, int32_t next_obs_ld, float gamma, void* stream);
 
-/* P9: GAE reverse scan + advantage normalisation (rollout_storage.py:138-152).
- * scratch: >= 4096 doubles.  If stats_only_local != 0 the {sum, sumsq, count} triple is left in scratch[0..2]
- * for a cross-rank all-reduce and dtc_gae_normalize finishes the job. */
+/* P9: GAE reverse scan + advantage normalisation (rollout_storage.py:138-152).  scratch: >= 4 doubles.
+ * With defer_normalize != 0 the {sum, sumsq, count} triple is left in scratch[0..2] (for a cross-rank all-reduce)
+ * and dtc_gae_normalize finishes the job. */
 int dtc_gae(const dtc_storage* s, const float* last_values, float gamma, float lam, double* scratch, int defer_normalize, void* stream);
 int dtc_gae_normalize(const dtc_storage* s, const double* stats3, void* stream);
 
-/* P10: minibatch row gather by permutation (rollout_storage.py:165-214); dst is a second dtc_storage with T*N rows. */
+/* P10: minibatch row gather by permutation (rollout_storage.py:165-214): dst row r = src row perm[r]. */
 int dtc_gather_minibatch(const dtc_storage* src, const dtc_storage* dst, const int64_t* perm, int64_t rows, void* stream);
 
 /* P11 / P12: one VAE optimizer step / one policy optimizer step on rows [row0,row0+M) of a (gathered) storage
- * (ppo.py:197-254 / :265-338), forward + hand-written backward + clip_grad_norm_ + Adam.
- * eps: [M,16] normal draws or NULL.  Loss sums accumulate into the learner's device-side statistics.
- * If sync_grads != 0 the call stops after backward (gradients + grad-norm partials ready) so the caller can
- * all-reduce `grads[range]`, then calls dtc_optimizer_apply. */
-typedef struct { float clip_param, value_loss_coef, entropy_coef, max_grad_norm, desired_kl; int32_t adaptive_lr; } dtc_ppo_hparams;
+ * (ppo.py:197-254 / :265-338): forward + hand-written backward + clip_grad_norm_ + Adam.
+ * eps: [M,16] normal draws or NULL (Philox).  Loss sums accumulate into the learner's device-side statistics.
+ * If sync_grads != 0 the call stops after backward so the caller can all-reduce grads[dtc_param_range(0 or 2)] and
+ * then call dtc_optimizer_apply with grad_scale = 1/world. */
+typedef struct {
+  float clip_param, value_loss_coef, entropy_coef, max_grad_norm, desired_kl;
+  int32_t adaptive_lr, use_clipped_value_loss, reserved;
+} dtc_ppo_hparams;
 int dtc_vae_step(dtc_learner* l, const dtc_storage* batch, int64_t row0, int32_t M, const float* eps, uint64_t seed,
-                 uint64_t counter, const dtc_ppo_hparams* hp, int sync_grads, float grad_scale, void* stream);
+                 uint64_t counter, const dtc_ppo_hparams* hp, int sync_grads, void* stream);
 int dtc_ppo_step(dtc_learner* l, const dtc_storage* batch, int64_t row0, int32_t M, const float* eps, uint64_t seed,
-                 uint64_t counter, const dtc_ppo_hparams* hp, int sync_grads, float grad_scale, void* stream);
-int dtc_optimizer_apply(dtc_learner* l, int which /*0 vae, 1 policy*/, const dtc_ppo_hparams* hp, void* stream);
+                 uint64_t counter, const dtc_ppo_hparams* hp, int sync_grads, void* stream);
+int dtc_optimizer_apply(dtc_learner* l, int which /*0 vae, 1 policy*/, const dtc_ppo_hparams* hp, float grad_scale,
+                        int32_t rows_global /* minibatch rows over all ranks (KL mean) */, void* stream);
 
 /* learner statistics (device doubles): [0] value_loss sum, [1] surrogate sum, [2] recons, [3] vel, [4] kld,
- * [5] height, [6] entropy, [7] last kl_mean, [8] learning_rate, [9] last grad norm (vae), [10] last grad norm (policy) */
+ * [5] height, [6] entropy sum, [7] last kl_mean, [8] learning_rate, [9] last grad norm (vae), [10] last grad norm
+ * (policy), [11] number of vae steps accumulated, [12] number of policy steps accumulated */
 double* dtc_learner_stats(dtc_learner* l);
 int dtc_learner_set_lr(dtc_learner* l, double lr, void* stream);
 int dtc_learner_reset_stats(dtc_learner* l, void* stream);
 int dtc_learner_set_adam_steps(dtc_learner* l, int64_t vae_steps, int64_t main_steps);
+int dtc_learner_get_adam_steps(dtc_learner* l, int64_t* vae_steps, int64_t* main_steps);
 /* debug access to named activation / gradient buffers of the last step (tests) */
 int dtc_learner_debug_buffer(dtc_learner* l, const char* name, float** ptr, int32_t* rows, int32_t* cols, int32_t* ld);
 
 /* plain GEMM entry (tests / microbench): C[M,N] = act(A[M,K] * W[N,K]^T + bias) */
 int dtc_linear_forward(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* W, int32_t ldw,
                        const float* bias, int32_t act /*0 none,1 relu,2 elu*/, float* C, int32_t ldc, void* stream);
+/* general form used by the learner: C = epi(A op B) with either operand k-contiguous (1) or k-strided (0); tests */
+int dtc_gemm_debug(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int32_t a_kc, const float* B, int32_t ldb,
+                   int32_t b_kc, float* C, int32_t ldc, int32_t splits, float* ws, void* stream);
 
 #ifdef __cplusplus
 }

@@ -62,15 +62,16 @@ def _compare_step(o, c, tag, sel=None):
     _close(c.motor_strengths, o.motor_strengths, tag + "motor_strengths")
     _close(c.height_noise_offset, o.height_noise_offset, tag + "height_noise_offset")
     _close(c.feet_air_time, o.feet_air_time, tag + "feet_air_time")
-    _close(c.pitch_est, o.pitch_est, tag + "pitch_est")
+    # pitch_est: 693-term fp32 dot product (LS plane fit) on the oracle side, metre-scale terms -> 5e-6 absolute
+    _close(c.pitch_est, o.pitch_est, tag + "pitch_est", atol=5e-6)
     _close(c.last_actions, o.last_actions, tag + "last_actions")
     _close(c.lin_vel_buffer, o.lin_vel_buffer, tag + "lin_vel_buffer")
     _close(c.cmd_buffer, o.cmd_buffer, tag + "cmd_buffer")
     _close(c.get_base_vel(), o.get_base_vel(), tag + "base_vel")
 
 
-@pytest.mark.parametrize("N,kind,variant", [(64, "stones", 0), (64, "flat", 0), (256, "curriculum", 1), (4096, "stones", 0),
-                                            (1000, "stones", 1)])
+@pytest.mark.parametrize("N,kind,variant", [(64, "stones", 0), (64, "flat", 0), (256, "curriculum", 3), (4096, "stones", 0),
+                                            (1000, "stones", 3)])
 def test_env_step_parity(N, kind, variant):
     from oracle import env_oracle as EO
     oenv, cenv, fg_cpu, fg_gpu = H.make_pair(N, kind, seed=3)
@@ -111,13 +112,15 @@ def test_debug_score_matches_bruteforce():
     oenv, cenv, fg_cpu, fg_gpu = H.make_pair(N, "stones", seed=5)
     g = torch.Generator().manual_seed(1)
     st = [sim_stub.synth_state(N, oenv.env_origins, g) for _ in range(2)]
+    st[1]["root_states"][5:25, 2] += 1.5  # everything under these robots is an exception point -> fall-back argmin
     H.reset_both(oenv, cenv, fg_cpu, fg_gpu, st[0])
     cenv._debug_score = torch.zeros(N, K.NUM_POINTS, 4, device=cenv.device)
     H.lockstep(oenv, cenv, fg_cpu, fg_gpu, st[1], torch.zeros(N, 12))
     score = cenv._debug_score.cpu()
     assert torch.equal(score.argmin(dim=1), cenv.optimal_foothold_indice.squeeze(1).cpu())
     sel = EO.foothold_select(st[1]["root_states"], oenv.measured_heights, oenv.pred_footholds, oenv.grid, K, debug=True)
-    _close(score, sel["score"], "score tensor", rtol=1e-5, atol=1e-6)
+    # the distance term subtracts world coordinates of 30-60 m: one ulp there is 3.8e-6
+    _close(score, sel["score"], "score tensor", rtol=1e-5, atol=4e-6)
     frac_fallback = float((score.min(dim=1)[0] >= 8).float().mean())
     assert 0.0 < frac_fallback < 0.5  # the tie / fall-back path is exercised (SURVEY: ~8 % of pairs)
 

@@ -1,0 +1,355 @@
+"""GPU parity tests of the learner half: the CUDA kernels (through the C ABI / Python mirror classes) against the CPU
+oracle (oracle/learner_oracle.py, autograd as the differentiation oracle) on identical parameters, data and random draws.
+
+Tolerance (north_star): 1e-5 relative fp32, applied as |a-b| <= 1e-5 * max(|ref|, scale) with `scale` the tensor's own
+magnitude (max |ref|): GEMM summation order differs between cuBLAS-free SIMT kernels and the CPU's oneDNN/MKL kernels."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import dtc_b200  # noqa: F401
+from dtc_b200 import _lib as B
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _close(a, b, name, rel=1e-5, floor=0.0):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    scale = max(float(b.abs().max()), floor, 1e-30)
+    err = (a - b).abs()
+    tol = rel * torch.maximum(b.abs(), torch.full_like(b, scale))
+    if not bool((err <= tol).all()):
+        i = int((err / tol).argmax())
+        raise AssertionError(f"{name}: |diff| {err.flatten()[i].item():.3e} > tol {tol.flatten()[i].item():.3e} at "
+                             f"{np.unravel_index(i, tuple(a.shape))} (ref {b.flatten()[i].item():.6e}, got {a.flatten()[i].item():.6e}, "
+                             f"scale {scale:.3e})")
+
+
+# ------------------------------------------------------------------ GEMM family
+@pytest.mark.parametrize("M,N,K", [(4096, 512, 693), (300, 35, 64), (1000, 12, 128), (777, 693, 512), (64, 1, 128), (130, 588, 512)])
+def test_gemm_forward_and_dgrad(M, N, K):
+    lib = B.lib()
+    g = torch.Generator().manual_seed(M + N + K)
+    r4 = lambda x: (x + 3) // 4 * 4
+    A = torch.zeros(M, r4(K)); A[:, :K] = torch.randn(M, K, generator=g)
+    W = torch.zeros(N, r4(K)); W[:, :K] = torch.randn(N, K, generator=g) * 0.1
+    bias = torch.randn(N, generator=g)
+    ref = A[:, :K].double() @ W[:, :K].double().T + bias.double()
+    Ad, Wd, bd = A.to(DEV), W.to(DEV), bias.to(DEV)
+    for act, f in ((0, lambda x: x), (1, torch.relu), (2, torch.nn.functional.elu)):
+        Cd = torch.full((M, r4(N)), 7.0, device=DEV)
+        B.check(lib.dtc_linear_forward(M, N, K, B.ptr(Ad), A.shape[1], B.ptr(Wd), W.shape[1], B.ptr(bd), act, B.ptr(Cd), Cd.shape[1],
+                                       B.stream_ptr()), "fwd")
+        _close(Cd[:, :N], f(ref), f"fwd act{act}")
+        assert bool((Cd[:, N:] == 7.0).all()), "pad columns must not be written"
+    # dgrad layout: C[M,K] = dY[M,N] @ W[N,K]  (A k-contiguous, B k-strided)
+    dY = torch.zeros(M, r4(N)); dY[:, :N] = torch.randn(M, N, generator=g)
+    dYd = dY.to(DEV)
+    Cd = torch.zeros(M, r4(K), device=DEV)
+    B.check(lib.dtc_gemm_debug(M, K, N, B.ptr(dYd), dY.shape[1], 1, B.ptr(Wd), W.shape[1], 0, B.ptr(Cd), Cd.shape[1], 1, None,
+                               B.stream_ptr()), "dgrad")
+    _close(Cd[:, :K], dY[:, :N].double() @ W[:, :K].double(), "dgrad")
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 693, 24576), (35, 64, 4096), (12, 128, 3000), (1, 128, 2500), (53, 128, 999), (693, 512, 6144)])
+def test_gemm_wgrad_splitk(M, N, K):
+    """dW[M=out, N=in] = dY[K, out]^T X[K, in]; both operands k-strided; split-K through the workspace."""
+    lib = B.lib()
+    g = torch.Generator().manual_seed(M * 3 + N + K)
+    r4 = lambda x: (x + 3) // 4 * 4
+    dY = torch.zeros(K, r4(M)); dY[:, :M] = torch.randn(K, M, generator=g)
+    X = torch.zeros(K, r4(N)); X[:, :N] = torch.randn(K, N, generator=g)
+    ref = dY[:, :M].double().T @ X[:, :N].double()
+    dYd, Xd = dY.to(DEV), X.to(DEV)
+    for splits in (1, 7, 25):
+        ws = torch.zeros(splits * M * r4(N), device=DEV)
+        Cd = torch.full((M, r4(N)), 3.0, device=DEV)
+        B.check(lib.dtc_gemm_debug(M, N, K, B.ptr(dYd), dY.shape[1], 0, B.ptr(Xd), X.shape[1], 0, B.ptr(Cd), Cd.shape[1],
+                                   splits, B.ptr(ws), B.stream_ptr()), "wgrad")
+        _close(Cd[:, :N], ref, f"wgrad splits={splits}")
+
+
+# ------------------------------------------------------------------ policy forward
+def _make_policies(seed):
+    from oracle import learner_oracle as LO
+    from dtc_b200.rsl_rl.modules import ActorCriticDecoder
+    rng = H.TapRng(seed)
+    torch.manual_seed(seed)
+    oac = LO.ActorCriticDecoder(53, 1389, 12, rng=rng)
+    # make every parameter matter: the reference initialises later layers with gain 0.01 and zero bias
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(seed + 1)
+        for k, p in oac.named_parameters():
+            if k != "std":
+                p.add_(torch.randn(p.shape, generator=g) * (0.05 if p.dim() == 2 else 0.02))
+            else:
+                p.copy_(0.5 + torch.rand(12, generator=g))
+    cac = ActorCriticDecoder(53, 1389, 12).to(DEV)
+    cac.load_state_dict(oac.state_dict())
+    return oac, cac, rng
+
+
+def _inputs(M, seed):
+    g = torch.Generator().manual_seed(seed)
+    obs = torch.randn(M, 53, generator=g)
+    hist = torch.randn(M, 265, generator=g)
+    priv = torch.randn(M, 1389, generator=g)
+    bv = torch.randn(M, 3, generator=g)
+    return obs, hist, priv, bv
+
+
+def test_state_dict_roundtrip():
+    oac, cac, _ = _make_policies(1)
+    sd = cac.state_dict()
+    for k, v in oac.state_dict().items():
+        assert torch.equal(sd[k].cpu(), v), k
+    assert list(sd.keys()) == list(oac.state_dict().keys())
+
+
+@pytest.mark.parametrize("M", [64, 1000, 4096])
+def test_act_parity(M):
+    oac, cac, rng = _make_policies(2)
+    obs, hist, priv, bv = _inputs(M, 5)
+    with torch.no_grad():
+        a_ref = oac.act(obs, hist, priv)
+        v_ref = oac.evaluate(obs, priv, bv)
+        lp_ref = oac.get_actions_log_prob(a_ref)
+        mu_ref, sg_ref = oac.action_mean, oac.action_std
+    log = rng.take()
+    cac._inject = dict(eps_z=log[0][1].to(DEV).contiguous(), eps_a=log[1][1].to(DEV).contiguous())
+    o = cac._forward_act(obs.to(DEV), hist.to(DEV), priv.to(DEV), bv.to(DEV))
+    _close(cac.debug_buffer("ML")[:, :19], oac.latent_mu, "latent_mu")
+    _close(cac.debug_buffer("ML")[:, 19:35], oac.latent_var, "latent_var (after outlier repair)")
+    _close(cac.debug_buffer("XA")[:, 568:584], oac.z, "z")
+    _close(o["mean"], mu_ref, "action mean")
+    _close(o["sigma"], sg_ref, "action std")
+    _close(o["actions"], a_ref, "actions")
+    _close(o["values"], v_ref.squeeze(1), "values")
+    _close(o["logp"], lp_ref, "log prob", floor=1.0)
+    _close(cac.evaluate(obs.to(DEV), priv.to(DEV), bv.to(DEV)), v_ref, "evaluate")
+    with torch.no_grad():
+        t_ref = oac.act_teacher(obs, hist, priv)
+    _close(cac.act_teacher(obs.to(DEV), hist.to(DEV), priv.to(DEV)), t_ref, "act_teacher")
+
+
+def test_philox_path_runs_and_is_standard_normal():
+    _, cac, _ = _make_policies(3)
+    obs, hist, priv, bv = _inputs(4096, 6)
+    o = {k: v.clone() for k, v in cac._forward_act(obs.to(DEV), hist.to(DEV), priv.to(DEV), bv.to(DEV)).items()}
+    eps = (o["actions"] - o["mean"]) / o["sigma"]
+    assert abs(float(eps.mean())) < 0.02 and abs(float(eps.std()) - 1.0) < 0.02
+    z = cac.debug_buffer("EPS")
+    assert abs(float(z.mean())) < 0.02 and abs(float(z.std()) - 1.0) < 0.02
+    o2 = cac._forward_act(obs.to(DEV), hist.to(DEV), priv.to(DEV), bv.to(DEV))
+    assert not torch.equal(o2["actions"], o["actions"]), "a new call must draw new noise"
+
+
+# ------------------------------------------------------------------ storage, GAE, update
+def _fill_storages(N, T, seed, oac, cac, rng):
+    """An oracle PPO and a CUDA PPO holding identical synthetic rollouts."""
+    from oracle import learner_oracle as LO
+    from dtc_b200.rsl_rl.algorithms import PPO
+    kw = dict(num_learning_epochs=2, num_mini_batches=4, clip_param=0.2, gamma=0.99, lam=0.95, value_loss_coef=1.0,
+              entropy_coef=0.003, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True, schedule="adaptive",
+              desired_kl=0.01)
+    oalg = LO.PPO(oac, rng=rng, **kw)
+    oalg.init_storage(N, T, [53], [1389], [265], [12])
+    calg = PPO(cac, device=DEV, **kw)
+    calg.init_storage(N, T, [53], [1389], [265], [12])
+    g = torch.Generator().manual_seed(seed)
+    for t in range(T):
+        obs, hist, priv, bv = _inputs(N, seed * 100 + t)
+        with torch.no_grad():
+            a = oalg.act(obs, priv, hist, bv)
+        log = rng.take()
+        cac._inject = dict(eps_z=log[0][1].to(DEV).contiguous(), eps_a=log[1][1].to(DEV).contiguous())
+        ca = calg.act(obs.to(DEV), priv.to(DEV), hist.to(DEV), bv.to(DEV))
+        _close(ca, a, f"rollout actions t={t}")
+        rew = torch.randn(N, generator=g)
+        dones = (torch.rand(N, generator=g) < 0.1)
+        touts = dones & (torch.rand(N, generator=g) < 0.5)
+        nobs = torch.randn(N, 53, generator=g)
+        oalg.process_env_step(rew, dones, nobs, {"time_outs": touts})
+        calg.process_env_step(rew.to(DEV), dones.to(DEV).to(torch.uint8), nobs.to(DEV), {"time_outs": touts.to(DEV)})
+    obs, hist, priv, bv = _inputs(N, seed * 100 + T)
+    with torch.no_grad():
+        oalg.compute_returns(obs, priv, bv)
+    calg.compute_returns(obs.to(DEV), priv.to(DEV), bv.to(DEV))
+    return oalg, calg
+
+
+def test_storage_and_gae_parity():
+    oac, cac, rng = _make_policies(4)
+    oalg, calg = _fill_storages(32, 24, 7, oac, cac, rng)
+    so, sc = oalg.storage, calg.storage
+    for name in ("observations", "next_observations", "privileged_observations", "observation_histories", "actions", "base_vel"):
+        _close(getattr(sc, name), getattr(so, name), name)
+    assert torch.equal(sc.dones.cpu(), so.dones)
+    _close(sc.rewards, so.rewards, "rewards (timeout bootstrap)")
+    _close(sc.values, so.values, "values")
+    _close(sc.actions_log_prob, so.actions_log_prob, "logp", floor=1.0)
+    _close(sc.mu, so.mu, "mu")
+    _close(sc.sigma, so.sigma, "sigma")
+    _close(sc.returns, so.returns, "returns")
+    _close(sc.advantages, so.advantages, "advantages", rel=2e-5)
+
+
+def _grads_as_state_dict(cac):
+    out = {}
+    for k, idx in cac._idx.items():
+        out[k] = cac._grads[idx].view(cac._table.shape[k]).clone()
+    return out
+
+
+@pytest.mark.parametrize("N", [16, 171])
+def test_update_parity(N):
+    """Full PPO.update(): per-minibatch gradients of the first VAE and policy steps, losses, learning rate and the
+    parameters after 2 epochs x 4 minibatches (16 Adam steps)."""
+    oac, cac, rng = _make_policies(5)
+    T = 24
+    oalg, calg = _fill_storages(N, T, 9, oac, cac, rng)
+    mbs = N * T // 4
+    lib = B.lib()
+    # --- the oracle's update with draw logging
+    oalg.debug = {}
+    p_before = {k: v.clone() for k, v in oac.state_dict().items()}
+    o_ret = oalg.update()
+    log = rng.take()
+    assert log[0][0] == "randperm"
+    perm = log[0][1]
+    draws = [v for tag, v in log[1:]]
+    assert len(draws) == 3 * 8
+    eps = []
+    for k in range(8):
+        eps += [draws[3 * k].to(DEV).contiguous(), draws[3 * k + 1].to(DEV).contiguous()]
+    # --- single steps with sync_grads=1 to look at raw gradients (parameters still at their initial values)
+    batch = calg.storage.gather(perm.to(DEV))
+    hp = calg._hparams()
+    h = cac._learner(mbs)
+    calg._push_lr(h)
+    B.check(lib.dtc_learner_reset_stats(h, B.stream_ptr()), "reset")
+    B.check(lib.dtc_vae_step(h, C.byref(batch._c), 0, mbs, B.ptr(eps[0]), 0, 0, C.byref(hp), 1, B.stream_ptr()), "vae_step")
+    got = _grads_as_state_dict(cac)
+    for k, g_ref in oalg.debug["vae_grads"][0].items():
+        _close(got["vae." + k], g_ref, "vae grad " + k, rel=2e-5)
+    s = cac.stats().tolist()
+    rec, vel, kld, hgt = oalg.debug["vae_losses"][0]
+    assert s[2] == pytest.approx(rec, rel=1e-5) and s[3] == pytest.approx(vel, rel=1e-5)
+    assert s[4] == pytest.approx(kld, rel=1e-5, abs=1e-7) and s[5] == pytest.approx(hgt, rel=1e-5)
+    # --- now the real update from the same starting point
+    cac.load_state_dict(p_before)
+    calg._inject = dict(perm=perm, eps=eps)
+    c_ret = calg.update()
+    vl, sl, ent, klm, lr = oalg.debug["ppo_losses"][-1]
+    assert calg.learning_rate == pytest.approx(oalg.learning_rate, rel=1e-9), "adaptive-KL schedule must take the same branches"
+    for a, b, name in zip(c_ret, o_ret, ("value", "surrogate", "adaptation", "decoder", "recons", "vel", "kld")):
+        assert a == pytest.approx(b, rel=2e-4, abs=1e-6), name
+    sd = cac.state_dict()
+    for k, v in oac.state_dict().items():
+        # Adam normalises every step to ~lr whatever the gradient's size, so an element whose gradient is ~0 turns a
+        # 1e-7 input difference into a step of up to lr (same effect as documented in tests/test_oracle_golden.py).
+        # Raw gradients are compared at 2e-5 above; here: the bulk must agree tightly and no element may be off by
+        # more than a fraction of one Adam step budget.
+        moved = (v - p_before[k]).abs().max().item()
+        diff = (sd[k].cpu() - v).abs()
+        if moved == 0:
+            assert diff.max().item() == 0, k
+            continue
+        assert diff.mean().item() <= 2e-3 * moved, (k, diff.mean().item(), moved)
+        assert (diff > 0.05 * moved).float().mean().item() < 0.02, k
+        assert diff.max().item() <= 0.5 * moved, (k, diff.max().item(), moved)
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_adam_and_clip_match_torch(which):
+    """dtc_optimizer_apply (global-norm clip + Adam + adaptive-KL learning rate) against torch.nn.utils.clip_grad_norm_ +
+    torch.optim.Adam fed the SAME gradients, 6 steps - isolates the optimizer from gradient round-off (see
+    test_update_parity for why end-to-end trajectories can only be compared statistically)."""
+    from dtc_b200.rsl_rl.modules import ActorCriticDecoder
+    from dtc_b200.rsl_rl.algorithms import PPO
+    torch.manual_seed(0)
+    cac = ActorCriticDecoder(53, 1389, 12).to(DEV)
+    calg = PPO(cac, learning_rate=1e-3, schedule="adaptive", desired_kl=0.01, device=DEV)
+    lib, st = B.lib(), B.stream_ptr()
+    h = cac._learner(64)
+    calg._push_lr(h)
+    hp = calg._hparams()
+    b0, b1 = cac._table.ranges["vae" if which == 0 else "policy"]
+    piggy = cac._table.ranges["policy_sync"][1] - 4
+    p_ref = torch.nn.Parameter(cac._flat[b0:b1].cpu().clone())
+    lr = 5e-4 if which == 0 else 1e-3
+    opt = torch.optim.Adam([p_ref], lr=lr)
+    g = torch.Generator().manual_seed(3)
+    rows = 1000
+    for step in range(6):
+        scale = [3e-4, 1e-2, 1e-6, 5e-3, 1e-3, 2e-2][step]  # norms below and above max_grad_norm = 1
+        grad = torch.randn(b1 - b0, generator=g) * scale
+        grad[::7] = 0.0
+        cac._grads[b0:b1] = grad.to(DEV)
+        kl_mean = [0.05, 0.001, 0.01, 0.0, 0.03, 0.004][step]
+        cac._grads[piggy] = kl_mean * rows
+        B.check(lib.dtc_optimizer_apply(h, which, C.byref(hp), 1.0, rows, st), "apply")
+        if which == 1:
+            if kl_mean > 0.02:
+                lr = max(1e-5, lr / 1.5)
+            elif kl_mean < 0.005 and kl_mean > 0.0:
+                lr = min(1e-2, lr * 1.5)
+            for grp in opt.param_groups:
+                grp["lr"] = lr
+        p_ref.grad = grad.clone()
+        torch.nn.utils.clip_grad_norm_([p_ref], 1.0)
+        opt.step()
+        got = cac._flat[b0:b1].cpu()
+        d = (got - p_ref.detach()).abs().max().item()
+        assert d <= 2e-7, (step, d)
+        if which == 1:
+            assert float(cac.stats()[8]) == pytest.approx(lr, rel=1e-12)
+    if which == 1:
+        assert calg.learning_rate == pytest.approx(lr, rel=1e-12)
+
+
+def test_policy_step_gradients():
+    """Raw gradients of one policy step (sync_grads=1) against autograd, incl. the outlier->median gradient routing."""
+    oac, cac, rng = _make_policies(6)
+    N, T = 64, 24
+    oalg, calg = _fill_storages(N, T, 11, oac, cac, rng)
+    mbs = N * T // 4
+    lib = B.lib()
+    from oracle import learner_oracle as LO
+    st = oalg.storage
+    perm = torch.randperm(N * T, generator=torch.Generator().manual_seed(1))
+    b = perm[:mbs]
+    f = {k: getattr(st, k).flatten(0, 1) for k in LO.RolloutStorage.FIELDS}
+    # oracle: the policy half of PPO.update on minibatch 0, by hand
+    oac.zero_grad()
+    oac.act(f["observations"][b], f["observation_histories"][b], f["privileged_observations"][b])
+    log = rng.take()
+    logp = oac.get_actions_log_prob(f["actions"][b])
+    value = oac.evaluate(f["observations"][b], f["privileged_observations"][b], f["base_vel"][b])
+    ratio = torch.exp(logp - f["actions_log_prob"][b].squeeze())
+    adv = f["advantages"][b].squeeze()
+    surr = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 0.8, 1.2)).mean()
+    tv, ret = f["values"][b], f["returns"][b]
+    vc = tv + (value - tv).clamp(-0.2, 0.2)
+    vloss = torch.max((value - ret).pow(2), (vc - ret).pow(2)).mean()
+    loss = surr + 1.0 * vloss - 0.003 * oac.entropy.mean()
+    loss.backward()
+    batch = calg.storage.gather(perm.to(DEV))
+    hp = calg._hparams()
+    h = cac._learner(mbs)
+    B.check(lib.dtc_ppo_step(h, C.byref(batch._c), 0, mbs, B.ptr(log[0][1].to(DEV).contiguous()), 0, 0, C.byref(hp), 1,
+                             B.stream_ptr()), "ppo_step")
+    got = _grads_as_state_dict(cac)
+    n_checked = 0
+    for k, p in oac.named_parameters():
+        if p.grad is not None:
+            _close(got[k], p.grad, "policy grad " + k, rel=3e-5)
+            n_checked += 1
+    assert n_checked == 31
+    n_out = int(cac.debug_buffer("OUTM").view(torch.uint8)[:, :16].sum())
+    assert n_out > 0, "the outlier path must be exercised"
