@@ -34,6 +34,11 @@ extern int64_t g_dtc_launches;
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// optional per-launch CUDA-event timing (bench.py's roofline leg): kind 0 = GEMM family (work = flops), 1 = foothold kernel
+extern int g_dtc_prof;
+void dtc_prof_begin(cudaStream_t st, int kind, double work);
+void dtc_prof_end(cudaStream_t st);
+
 // ------------------------------------------------------------------ warp reductions
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

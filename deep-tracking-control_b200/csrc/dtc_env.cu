@@ -594,6 +594,43 @@ extern "C" int dtc_env_observe(dtc_env* e, int64_t step, uint64_t seed, const dt
   return DTC_OK;
 }
 
+// ------------------------------------------------------------------ per-launch event timing
+#include <vector>
+int g_dtc_prof = 0;
+struct ProfRec { cudaEvent_t a, b; int kind; double work; };
+static std::vector<ProfRec> g_prof_recs;
+void dtc_prof_begin(cudaStream_t st, int kind, double work) {
+  if (!g_dtc_prof) return;
+  ProfRec r;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  r.kind = kind; r.work = work;
+  cudaEventRecord(r.a, st);
+  g_prof_recs.push_back(r);
+}
+void dtc_prof_end(cudaStream_t st) {
+  if (!g_dtc_prof || g_prof_recs.empty()) return;
+  cudaEventRecord(g_prof_recs.back().b, st);
+}
+extern "C" void dtc_profile_enable(int on) { g_dtc_prof = on; }
+extern "C" int dtc_profile_read(double* gemm_flops, double* gemm_ms, int64_t* gemm_launches, double* foothold_ms, int64_t* foothold_launches) {
+  double fl = 0, gms = 0, fms = 0;
+  int64_t ng = 0, nf = 0;
+  for (auto& r : g_prof_recs) {
+    float ms = 0.f;
+    cudaEventSynchronize(r.b);
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    if (r.kind == 0) { fl += r.work; gms += ms; ++ng; } else { fms += ms; ++nf; }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof_recs.clear();
+  if (gemm_flops) *gemm_flops = fl;
+  if (gemm_ms) *gemm_ms = gms;
+  if (gemm_launches) *gemm_launches = ng;
+  if (foothold_ms) *foothold_ms = fms;
+  if (foothold_launches) *foothold_launches = nf;
+  return DTC_OK;
+}
+
 extern "C" int dtc_struct_size(int which) {
   switch (which) {
     case 0: return (int)sizeof(dtc_env_config);

@@ -290,6 +290,7 @@ extern "C" int dtc_foothold_step(dtc_env* e, int variant, float* debug_score, vo
   dim3 grid(ceil_div(N, FH_WARPS)), block(FH_WARPS * 32);
   if (variant >= 1 && variant <= 3 && (e->cfg.map_cols * 2) % 16 != 0)
     DTC_FAIL(DTC_ERR_ARG, "TMA variants need 16-byte aligned heightmap rows");
+  dtc_prof_begin(st, 1, 0.0);
   if (variant == 1 || variant == 2) {
     if (!e->tmap_ready) { int rc = make_heightmap_tmap(e); if (rc) return rc; }
     if (variant == 1) k_foothold<1><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score, e->tmap, e->d_tmap);
@@ -302,5 +303,6 @@ extern "C" int dtc_foothold_step(dtc_env* e, int variant, float* debug_score, vo
     DTC_FAIL(DTC_ERR_ARG, "dtc_foothold_step: unknown variant %d", variant);
   }
   DTC_CHECK_LAUNCH("k_foothold");
+  dtc_prof_end(st);
   return DTC_OK;
 }

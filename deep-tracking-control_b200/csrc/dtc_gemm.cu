@@ -275,6 +275,7 @@ int dtc_gemm_launch(GemmArgs a, cudaStream_t st) {
   if (a.splits > 1 && (a.epi != EPI_STORE || !a.ws)) DTC_FAIL(DTC_ERR_ARG, "gemm: split-K needs EPI_STORE and a workspace");
   a.k_per_split = ((ceil_div(a.K, a.splits) + GBK - 1) / GBK) * GBK;
   if (a.k_per_split == 0) a.k_per_split = GBK;
+  dtc_prof_begin(st, 0, 2.0 * a.M * a.N * a.K);
   if (a.a_kc && a.b_kc) {
     if (a.N > 64) LAUNCH(128, 128, true, true);
     else if (a.N > 32) LAUNCH(128, 64, true, true);
@@ -300,6 +301,7 @@ int dtc_gemm_launch(GemmArgs a, cudaStream_t st) {
     k_splitk_reduce<<<blocks, 256, 0, st>>>(a.ws, a.C, a.M, a.N, a.ldc, a.splits, a.accumulate ? 1 : 0);
     DTC_CHECK_LAUNCH("k_splitk_reduce");
   }
+  dtc_prof_end(st);
   return DTC_OK;
 }
 

@@ -25,6 +25,9 @@ int64_t dtc_launch_count(void);
 /* sizeof() of the ABI structs, for binding self-checks: 0 env_config, 1 env_buffers, 2 env_noise, 3 storage,
  * 4 ppo_hparams, 5 param_info */
 int dtc_struct_size(int which);
+/* bench.py roofline leg: CUDA events around every GEMM-family and foothold launch while enabled */
+void dtc_profile_enable(int on);
+int dtc_profile_read(double* gemm_flops, double* gemm_ms, int64_t* gemm_launches, double* foothold_ms, int64_t* foothold_launches);
 
 /* ------------------------------------------------------------------ environment half */
 
