@@ -56,7 +56,7 @@ class EnvNoise(C.Structure):
 
 
 STORAGE_PTRS = ["hist", "priv_a", "xc", "next_obs", "actions", "mu", "sigma", "rewards", "values", "returns",
-                "advantages", "logp", "dones"]
+                "advantages", "logp", "dones", "hist_lo", "priv_a_lo", "xc_lo"]
 
 
 class Storage(C.Structure):
@@ -75,7 +75,7 @@ class ParamInfo(C.Structure):
 
 
 # every entry point include/dtc_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
-EXPORTED_SYMBOLS = ['dtc_env_bind', 'dtc_env_create', 'dtc_env_destroy', 'dtc_env_observe', 'dtc_env_pre_physics', 'dtc_env_reward_reset', 'dtc_env_state_prep', 'dtc_foothold_step', 'dtc_gae', 'dtc_gae_normalize', 'dtc_gather_minibatch', 'dtc_gemm_debug', 'dtc_last_error', 'dtc_launch_count', 'dtc_learner_create', 'dtc_learner_debug_buffer', 'dtc_learner_destroy', 'dtc_learner_get_adam_steps', 'dtc_learner_reset_stats', 'dtc_learner_set_adam_steps', 'dtc_learner_set_lr', 'dtc_learner_stats', 'dtc_learner_workspace_bytes', 'dtc_linear_forward', 'dtc_optimizer_apply', 'dtc_param_count', 'dtc_param_get', 'dtc_param_range', 'dtc_param_total_floats', 'dtc_policy_act', 'dtc_policy_act_teacher', 'dtc_policy_evaluate', 'dtc_ppo_step', 'dtc_profile_enable', 'dtc_profile_read', 'dtc_store_transition', 'dtc_struct_size', 'dtc_vae_step', 'dtc_version']
+EXPORTED_SYMBOLS = ['dtc_env_bind', 'dtc_env_create', 'dtc_env_destroy', 'dtc_env_observe', 'dtc_env_pre_physics', 'dtc_env_reward_reset', 'dtc_env_state_prep', 'dtc_foothold_step', 'dtc_gae', 'dtc_gae_normalize', 'dtc_gather_minibatch', 'dtc_gemm_debug', 'dtc_get_gemm_mode', 'dtc_last_error', 'dtc_launch_count', 'dtc_learner_create', 'dtc_learner_debug_buffer', 'dtc_learner_destroy', 'dtc_learner_get_adam_steps', 'dtc_learner_refresh_params', 'dtc_learner_reset_stats', 'dtc_learner_set_adam_steps', 'dtc_learner_set_lr', 'dtc_learner_stats', 'dtc_learner_workspace_bytes', 'dtc_linear_forward', 'dtc_optimizer_apply', 'dtc_param_count', 'dtc_param_get', 'dtc_param_range', 'dtc_param_total_floats', 'dtc_policy_act', 'dtc_policy_act_teacher', 'dtc_policy_evaluate', 'dtc_ppo_step', 'dtc_profile_enable', 'dtc_profile_read', 'dtc_set_gemm_mode', 'dtc_store_transition', 'dtc_struct_size', 'dtc_vae_step', 'dtc_version']
 
 
 class DtcError(RuntimeError):
@@ -116,6 +116,7 @@ def lib():
     L.dtc_learner_create.argtypes = [C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.POINTER(vp)]
     L.dtc_learner_destroy.argtypes = [vp]
     L.dtc_learner_destroy.restype = None
+    L.dtc_learner_refresh_params.argtypes = [vp, vp]
     i32, u64, SP = C.c_int32, C.c_uint64, C.POINTER(Storage)
     L.dtc_policy_act.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, u64, u64, SP, i32, vp, vp, vp, vp, vp, vp]
     L.dtc_policy_evaluate.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp, vp]
@@ -134,7 +135,9 @@ def lib():
     L.dtc_learner_get_adam_steps.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.dtc_learner_debug_buffer.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.dtc_linear_forward.argtypes = [i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp]
-    L.dtc_gemm_debug.argtypes = [i32, i32, i32, vp, i32, i32, vp, i32, i32, vp, i32, i32, vp, vp]
+    L.dtc_gemm_debug.argtypes = [i32, i32, i32, vp, vp, i32, i32, vp, vp, i32, i32, vp, vp, i32, i32, vp, i32, vp]
+    L.dtc_set_gemm_mode.argtypes = [C.c_int]
+    L.dtc_set_gemm_mode.restype = None
     for which, st in enumerate((EnvConfig, EnvBuffers, EnvNoise, Storage, PPOHParams, ParamInfo)):
         got = L.dtc_struct_size(which)
         if got != C.sizeof(st):

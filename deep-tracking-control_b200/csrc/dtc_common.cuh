@@ -39,6 +39,21 @@ extern int g_dtc_prof;
 void dtc_prof_begin(cudaStream_t st, int kind, double work);
 void dtc_prof_end(cudaStream_t st);
 
+#define RETURN_IF_ERR(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
+// 3xTF32 companion value: the tensor core truncates an fp32 operand x to TF32; x_lo = rn_tf32(x - trunc_tf32(x)) carries
+// the next 11 bits (dtc_gemm_tc.cu)
+__host__ __device__ __forceinline__ float tf32_lo(float x) {
+#ifdef __CUDA_ARCH__
+  const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  const float r = x - hi;
+  return __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
+#else
+  uint32_t b; memcpy(&b, &x, 4); b &= 0xFFFFE000u; float hi; memcpy(&hi, &b, 4);
+  float r = x - hi; memcpy(&b, &r, 4); b = (b + 0x1000u) & 0xFFFFE000u; memcpy(&r, &b, 4); return r;
+#endif
+}
+
 // ------------------------------------------------------------------ warp reductions
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -6,6 +6,8 @@
 // (rsl_rl/modules/actor_critic_decoder.py nn.Linear stacks and their autograd).
 // Exact fp32 FMA accumulation keeps the 1e-5 parity budget that TF32 tensor-core math would not.
 // 128 x BN x 16 tiles, 256 threads, 8 x BN/16 register micro-tile, double-buffered shared memory with register prefetch.
+#include <stdlib.h>
+
 #include "dtc_gemm.cuh"
 
 #define GBK 16
@@ -162,6 +164,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) k_gemm(const GemmArgs g) {
   const bool partial = g.splits > 1;
   const int n4 = (g.N + 3) & ~3;
   float* __restrict__ out = partial ? g.ws + (size_t)blockIdx.z * g.M * n4 : g.C;
+  float* __restrict__ out_lo = partial ? nullptr : g.C_lo;
   const int ldo = partial ? n4 : g.ldc;
   const int epi = partial ? EPI_STORE : g.epi;
   const bool accum = !partial && g.accumulate;
@@ -188,6 +191,8 @@ __global__ void __launch_bounds__(GTHREADS, 2) k_gemm(const GemmArgs g) {
           v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
         }
         *dst = make_float4(v[0], v[1], v[2], v[3]);
+        if (out_lo)
+          *reinterpret_cast<float4*>(out_lo + (size_t)gm * ldo + gn) = make_float4(tf32_lo(v[0]), tf32_lo(v[1]), tf32_lo(v[2]), tf32_lo(v[3]));
       } else {
 #pragma unroll
         for (int j = 0; j < (TN < 4 ? TN : 4); ++j) {
@@ -198,6 +203,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) k_gemm(const GemmArgs g) {
             float v = epi_apply(acc[i][(j0 + j) % TN], epi, bias, src);
             if (accum) v += orow[gnj];
             orow[gnj] = v;
+            if (out_lo) out_lo[(size_t)gm * ldo + gnj] = tf32_lo(v);
           }
         }
       }
@@ -206,8 +212,8 @@ __global__ void __launch_bounds__(GTHREADS, 2) k_gemm(const GemmArgs g) {
 }
 
 // sums the split-K partials: C[m,n] (+)= sum_s ws[s][m][n]
-__global__ void k_splitk_reduce(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc, int splits,
-                                int accumulate) {
+__global__ void k_splitk_reduce(const float* __restrict__ ws, float* __restrict__ C, float* __restrict__ C_lo, int M, int N, int ldc,
+                                int splits, int accumulate) {
   const int n4 = (N + 3) & ~3, q = n4 >> 2;
   const int64_t total = (int64_t)M * q;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -220,9 +226,32 @@ __global__ void k_splitk_reduce(const float* __restrict__ ws, float* __restrict_
     float* dst = C + (size_t)m * ldc + c;
     float v[4] = {s.x, s.y, s.z, s.w};
     for (int j = 0; j < 4; ++j)
-      if (c + j < N) dst[j] = accumulate ? dst[j] + v[j] : v[j];
+      if (c + j < N) {
+        float o = accumulate ? dst[j] + v[j] : v[j];
+        dst[j] = o;
+        if (C_lo) C_lo[(size_t)m * ldc + c + j] = tf32_lo(o);
+      }
   }
 }
+void k_splitk_reduce_launch(const float* ws, float* C, float* C_lo, int M, int N, int ldc, int splits, int accumulate, cudaStream_t st) {
+  int64_t total = (int64_t)M * ((N + 3) / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_splitk_reduce<<<blocks, 256, 0, st>>>(ws, C, C_lo, M, N, ldc, splits, accumulate);
+  g_dtc_launches++;
+}
+
+static int g_gemm_mode = -1;
+int dtc_gemm_mode() {
+  if (g_gemm_mode < 0) {
+    const char* e = getenv("DTC_GEMM");
+    g_gemm_mode = (e && !strcmp(e, "simt")) ? 0 : 1;
+  }
+  return g_gemm_mode;
+}
+void dtc_gemm_set_mode(int mode) { g_gemm_mode = mode ? 1 : 0; }
+extern "C" void dtc_set_gemm_mode(int mode) { dtc_gemm_set_mode(mode); }
+extern "C" int dtc_get_gemm_mode(void) { return dtc_gemm_mode(); }
 
 __global__ void __launch_bounds__(256) k_colsum1(const float* __restrict__ X, int ld, int M, int N, float* __restrict__ ws) {
   __shared__ float sh[8][33];
@@ -251,13 +280,15 @@ __global__ void k_colsum2(const float* __restrict__ ws, int N, float* __restrict
 }
 
 int dtc_gemm_pick_splits(int M, int N, int K) {
-  if (K < 2048) return 1;
+  const int tc_min = ceil_div(ceil_div(K, 32), 32);  // the tensor-core path keeps <= 32 k-blocks per TMEM accumulation
+  if (K < 2048) return tc_min;
   int bm = M > 64 ? 128 : (M > 32 ? 64 : 32), bn = N > 64 ? 128 : 64;
   int tiles = ceil_div(M, bm) * ceil_div(N, bn);
   int s = ceil_div(592, tiles);
   int smax = K / 256;
   if (s > smax) s = smax;
   if (s > 128) s = 128;
+  if (s < tc_min) s = tc_min;
   return s < 1 ? 1 : s;
 }
 
@@ -272,6 +303,7 @@ int dtc_gemm_launch(GemmArgs a, cudaStream_t st) {
   if ((a.lda & 3) || (a.ldb & 3) || (a.ldc & 3)) DTC_FAIL(DTC_ERR_ARG, "gemm: leading dimensions must be multiples of 4");
   if (((uintptr_t)a.A | (uintptr_t)a.B | (uintptr_t)a.C) & 15) DTC_FAIL(DTC_ERR_ARG, "gemm: operands must be 16-byte aligned");
   if (a.splits < 1) a.splits = 1;
+  if (dtc_gemm_mode() == 1 && dtc_gemm_tc_eligible(a)) return dtc_gemm_tc_launch(a, st);
   if (a.splits > 1 && (a.epi != EPI_STORE || !a.ws)) DTC_FAIL(DTC_ERR_ARG, "gemm: split-K needs EPI_STORE and a workspace");
   a.k_per_split = ((ceil_div(a.K, a.splits) + GBK - 1) / GBK) * GBK;
   if (a.k_per_split == 0) a.k_per_split = GBK;
@@ -295,11 +327,7 @@ int dtc_gemm_launch(GemmArgs a, cudaStream_t st) {
   }
   DTC_CHECK_LAUNCH("k_gemm");
   if (a.splits > 1) {
-    int64_t total = (int64_t)a.M * ((a.N + 3) / 4);
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    k_splitk_reduce<<<blocks, 256, 0, st>>>(a.ws, a.C, a.M, a.N, a.ldc, a.splits, a.accumulate ? 1 : 0);
-    DTC_CHECK_LAUNCH("k_splitk_reduce");
+    k_splitk_reduce_launch(a.ws, a.C, a.C_lo, a.M, a.N, a.ldc, a.splits, a.accumulate ? 1 : 0, st);
   }
   dtc_prof_end(st);
   return DTC_OK;
@@ -323,5 +351,9 @@ extern "C" int dtc_linear_forward(int32_t M, int32_t N, int32_t K, const float* 
   g.bias = bias;
   g.epi = bias ? (act == 1 ? EPI_BIAS_RELU : act == 2 ? EPI_BIAS_ELU : EPI_BIAS) : EPI_STORE;
   g.splits = 1;
-  return dtc_gemm_launch(g, (cudaStream_t)stream);
+  const int saved = dtc_gemm_mode();
+  dtc_gemm_set_mode(0);  // no companions supplied: plain fp32 path
+  int rc = dtc_gemm_launch(g, (cudaStream_t)stream);
+  dtc_gemm_set_mode(saved);
+  return rc;
 }

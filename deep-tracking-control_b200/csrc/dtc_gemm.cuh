@@ -25,8 +25,16 @@ struct GemmArgs {
   int splits;         // >1: split the reduction; partial tiles go to `ws` [splits][M][ldc] and are summed into C
   float* ws;
   int k_per_split;    // filled by the launcher
+  // 3xTF32 companions (dtc_gemm_tc.cu): x_lo = rn_tf32(x - trunc_tf32(x)).  A_lo / B_lo feed the tensor-core path (NULL = that
+  // correction term is skipped); C_lo, when set, receives the companion of the result from either path's epilogue.
+  const float* A_lo; const float* B_lo; float* C_lo;
 };
 
+// GEMM engine: 0 = FP32 SIMT everywhere, 1 = tcgen05 3xTF32 where the shape is tile-worthy (default; env DTC_GEMM=simt|tc)
+int dtc_gemm_mode();
+void dtc_gemm_set_mode(int mode);
+bool dtc_gemm_tc_eligible(const GemmArgs& a);
+int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st);
 // launches on `st`; returns 0 or a negative dtc_status with the message in dtc_last_error()
 int dtc_gemm_launch(GemmArgs a, cudaStream_t st);
 // splits the launcher would pick for a reduction of length K producing an MxN output (workspace sizing)

@@ -1,0 +1,360 @@
+// Tensor-core GEMM for the MLP stack on sm_100a: tcgen05.mma kind::tf32 with TMEM accumulators, operands staged by TMA
+// into 128-byte-swizzled shared memory, three-stage mbarrier pipeline, warp-specialised (TMA producer / MMA issuer /
+// TMEM allocator / 4 epilogue warps).
+//
+// fp32 accuracy (the 1e-5 parity bar) comes from error-compensated 3xTF32: the tensor core TRUNCATES fp32 operands to
+// TF32 (measured, tools/tc_probe.cu), so with  x_lo = rn_tf32(x - trunc_tf32(x))  kept next to every operand,
+//     A B^T  ~=  A.B + A_lo.B + A.B_lo          (three MMAs per k-step into the same TMEM accumulator)
+// leaves a relative error of ~2^-21 per product - the same order as fp32 summation-order noise.
+// The TMEM accumulator add rounds toward zero (measured: ~0.25 ulp systematic error per accumulation step), so the k-steps
+// are dealt round-robin onto TC_NACC main accumulators, the two small correction products go to their own accumulator,
+// and the four are summed in fp32 in the epilogue; reductions longer than TC_MAX_KB k-blocks are split and summed in fp32.
+//
+// Same contract as the SIMT family (dtc_gemm.cu): C[m,n] = epi(sum_k A(m,k) B(n,k)), each operand k-contiguous
+// ("K-major": TMA box 32k x 128 rows, SWIZZLE_128B) or k-strided ("MN-major": four boxes 32mn x 32k, SWIZZLE_128B with
+// 32-byte atoms - the only MN-major layout kind::tf32 accepts).  Out-of-range rows / k-tails are zero-filled by TMA.
+#include <cuda.h>
+
+#include <unordered_map>
+
+#include "dtc_gemm.cuh"
+
+#define TC_BM 128
+#define TC_BN 128
+#define TC_BK 32
+#define TC_STAGES 3
+#define TC_NACC 3        // main accumulators (columns [0, 3*128)); correction accumulator at column 3*128
+#define TC_TMEM_COLS 512
+#define TC_MAX_KB 32     // k-blocks (of 32) accumulated in TMEM before the fp32 split-K sum takes over
+#define TC_TILE_BYTES (128 * 32 * 4)
+#define TC_STAGE_BYTES (4 * TC_TILE_BYTES)
+#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024)
+
+struct TcParams {
+  int M, N, K;
+  int kb_per_split, nkb;
+  float* C; float* C_lo; int ldc;
+  const float* bias; const float* act_src; int ld_act; int epi; int accumulate;
+  float* ws;
+  int splits, has_alo, has_blo;
+};
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tTC_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni TC_WAIT_DONE;\n\tbra.uni TC_WAIT_LOOP;\n\tTC_WAIT_DONE:\n\t}" ::"r"(tc_smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tc_tma_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"((uint64_t)map), "r"(tc_smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | layout <<61
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)layout_type << 61);
+}
+template <int MAJ>
+__device__ __forceinline__ uint64_t tc_operand_desc(uint32_t tile, int k8) {
+  // K-major : rows of 128 B (32 k), 8-row swizzle atoms 1024 B apart; one MMA (K = 8) advances 32 B inside the row
+  // MN-major: 4 blocks (32 mn each, 4096 B apart) of 32 k-rows x 128 B, 4-row swizzle atoms 512 B apart; one MMA = 8 k-rows
+  return MAJ == 0 ? tc_desc(tile + k8 * 32, 16, 1024, 2) : tc_desc(tile + k8 * 1024, 4096, 512, 1);
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float tc_epi(float v, int epi, float bias, float src) {
+  switch (epi) {
+    case EPI_BIAS: return v + bias;
+    case EPI_BIAS_RELU: v += bias; return v > 0.f ? v : 0.f;
+    case EPI_BIAS_ELU: v += bias; return v > 0.f ? v : expm1f(v);
+    case EPI_DRELU: return src > 0.f ? v : 0.f;
+    case EPI_DELU: return src > 0.f ? v : v * (src + 1.0f);
+    default: return v;
+  }
+}
+
+template <int AMAJ, int BMAJ>
+__global__ void __launch_bounds__(256, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapB,
+          const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_acc;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t smem0 = (tc_smem_u32(tc_smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int kb1 = min(p.nkb, kb0 + p.kb_per_split);
+  const int nloc = kb1 - kb0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(&bar_full[s], 1); tc_mbar_init(&bar_empty[s], 1); }
+    tc_mbar_init(&bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_s)), "r"(TC_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    const uint32_t bytes = TC_TILE_BYTES * (2 + p.has_alo + p.has_blo);
+    for (int it = 0; it < nloc; ++it) {
+      const int s = it % TC_STAGES, kb = kb0 + it;
+      tc_mbar_wait(&bar_empty[s], ((it / TC_STAGES) & 1) ^ 1);
+      tc_mbar_expect_tx(&bar_full[s], bytes);
+      const uint32_t st = smem0 + s * TC_STAGE_BYTES;
+      if (AMAJ == 0) {
+        tc_tma_2d(st, &mapA, &bar_full[s], kb * TC_BK, m0);
+        if (p.has_alo) tc_tma_2d(st + TC_TILE_BYTES, &mapAlo, &bar_full[s], kb * TC_BK, m0);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          tc_tma_2d(st + j * 4096, &mapA, &bar_full[s], m0 + 32 * j, kb * TC_BK);
+          if (p.has_alo) tc_tma_2d(st + TC_TILE_BYTES + j * 4096, &mapAlo, &bar_full[s], m0 + 32 * j, kb * TC_BK);
+        }
+      }
+      if (BMAJ == 0) {
+        tc_tma_2d(st + 2 * TC_TILE_BYTES, &mapB, &bar_full[s], kb * TC_BK, n0);
+        if (p.has_blo) tc_tma_2d(st + 3 * TC_TILE_BYTES, &mapBlo, &bar_full[s], kb * TC_BK, n0);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          tc_tma_2d(st + 2 * TC_TILE_BYTES + j * 4096, &mapB, &bar_full[s], n0 + 32 * j, kb * TC_BK);
+          if (p.has_blo) tc_tma_2d(st + 3 * TC_TILE_BYTES + j * 4096, &mapBlo, &bar_full[s], n0 + 32 * j, kb * TC_BK);
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (one thread)
+    // instruction descriptor: D f32 | A,B tf32 | majors | N >> 3 | M >> 4   (cute::UMMA::InstrDescriptor)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)AMAJ << 15) | ((uint32_t)BMAJ << 16) |
+                           ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    for (int it = 0; it < nloc; ++it) {
+      const int s = it % TC_STAGES;
+      tc_mbar_wait(&bar_full[s], (it / TC_STAGES) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t st = smem0 + s * TC_STAGE_BYTES;
+#pragma unroll
+      for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+        const uint64_t a = tc_operand_desc<AMAJ>(st, k8), b = tc_operand_desc<BMAJ>(st + 2 * TC_TILE_BYTES, k8);
+        const int step = it * (TC_BK / 8) + k8;
+        tc_mma(tmem + (uint32_t)(step % TC_NACC) * TC_BN, a, b, idesc, step >= TC_NACC ? 1u : 0u);
+        if (p.has_alo) tc_mma(tmem + TC_NACC * TC_BN, tc_operand_desc<AMAJ>(st + TC_TILE_BYTES, k8), b, idesc, step ? 1u : 0u);
+        if (p.has_blo) tc_mma(tmem + TC_NACC * TC_BN, a, tc_operand_desc<BMAJ>(st + 3 * TC_TILE_BYTES, k8), idesc, (step || p.has_alo) ? 1u : 0u);
+      }
+      tc_commit(&bar_empty[s]);  // frees the stage once these MMAs have read it
+    }
+    tc_commit(&bar_acc);  // accumulator complete
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue: TMEM -> registers -> global
+    const int q = warp & 3;
+    if (nloc > 0) {
+      tc_mbar_wait(&bar_acc, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const bool partial = p.splits > 1;
+    const int n4 = (p.N + 3) & ~3;
+    float* const out = partial ? p.ws + (size_t)blockIdx.z * p.M * n4 : p.C;
+    float* const out_lo = (!partial && p.C_lo) ? p.C_lo : nullptr;
+    const int ldo = partial ? n4 : p.ldc;
+    const int epi = partial ? EPI_STORE : p.epi;
+    const bool has_bias = epi >= EPI_BIAS && epi <= EPI_BIAS_ELU, has_src = epi == EPI_DRELU || epi == EPI_DELU;
+    const bool accum = !partial && p.accumulate;
+    // The pipeline stages are idle once the accumulator barrier has fired: each epilogue warp stages its 32x32 chunk there
+    // (row stride 36 floats) so that every global access below is a coalesced 128-byte row segment.
+    float* const stg = reinterpret_cast<float*>(tc_smem_raw + (smem0 - tc_smem_u32(tc_smem_raw))) + q * (32 * 36);
+    const int nsteps = nloc * (TC_BK / 8);
+    const bool has_corr = nsteps > 0 && (p.has_alo || p.has_blo);
+    const int nacc = (nsteps < TC_NACC ? nsteps : TC_NACC) + (has_corr ? 1 : 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+      if (n0 + c0 >= p.N) break;  // warp-uniform
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+#pragma unroll 1
+      for (int a = 0; a < nacc; ++a) {
+        // main accumulators first, the correction accumulator (column block TC_NACC) last
+        const int blk = (a == nacc - 1 && has_corr) ? TC_NACC : a;
+        uint32_t u[32];
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * TC_BN + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+            "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+              "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
+              "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
+              "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(u[j]);
+      }
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4)
+        *reinterpret_cast<float4*>(stg + lane * 36 + j4 * 4) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+      __syncwarp();
+      const int c4 = (lane & 7) * 4, gn = n0 + c0 + c4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = (lane >> 3) + 4 * i, gm = m0 + q * 32 + r;
+        if (gm >= p.M || gn >= p.N) continue;
+        const float4 acc4 = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
+        float x[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
+        float* orow = out + (size_t)gm * ldo + gn;
+        if (gn + 3 < p.N) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = b4;
+          if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn));
+          if (has_src) s4 = __ldg(reinterpret_cast<const float4*>(p.act_src + (size_t)gm * p.ld_act + gn));
+          x[0] = tc_epi(x[0], epi, b4.x, s4.x); x[1] = tc_epi(x[1], epi, b4.y, s4.y);
+          x[2] = tc_epi(x[2], epi, b4.z, s4.z); x[3] = tc_epi(x[3], epi, b4.w, s4.w);
+          if (accum) {
+            const float4 o4 = *reinterpret_cast<const float4*>(orow);
+            x[0] += o4.x; x[1] += o4.y; x[2] += o4.z; x[3] += o4.w;
+          }
+          *reinterpret_cast<float4*>(orow) = make_float4(x[0], x[1], x[2], x[3]);
+          if (out_lo)
+            *reinterpret_cast<float4*>(out_lo + (size_t)gm * ldo + gn) = make_float4(tf32_lo(x[0]), tf32_lo(x[1]), tf32_lo(x[2]), tf32_lo(x[3]));
+        } else {
+          for (int j = 0; j < 4 && gn + j < p.N; ++j) {
+            const float bias = has_bias ? __ldg(p.bias + gn + j) : 0.f;
+            const float src = has_src ? __ldg(p.act_src + (size_t)gm * p.ld_act + gn + j) : 0.f;
+            float y = tc_epi(x[j], epi, bias, src);
+            if (accum) y += orow[j];
+            orow[j] = y;
+            if (out_lo) out_lo[(size_t)gm * ldo + gn + j] = tf32_lo(y);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS));
+}
+
+// ------------------------------------------------------------------ host side: tensor-map cache + launcher
+typedef CUresult (*PFN_tc_encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tc_encode g_encode = nullptr;
+
+struct MapKey {
+  const void* p; int rows, k, ld, maj;
+  bool operator==(const MapKey& o) const { return p == o.p && rows == o.rows && k == o.k && ld == o.ld && maj == o.maj; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = (size_t)k.p * 1000003u;
+    h ^= ((size_t)k.rows << 1) ^ ((size_t)k.k << 21) ^ ((size_t)k.ld << 41) ^ (size_t)k.maj;
+    return h;
+  }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// operand X(r, k): maj 0 -> X = base[r*ld + k] (box 32 k x 128 r); maj 1 -> X = base[k*ld + r] (box 32 r x 32 k)
+static int tc_get_map(const float* base, int rows, int k, int ld, int maj, CUtensorMap* out) {
+  MapKey key{base, rows, k, ld, maj};
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return DTC_OK; }
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    DTC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) DTC_FAIL(DTC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    g_encode = (PFN_tc_encode)fn;
+  }
+  cuuint64_t dims[2], strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2], es[2] = {1, 1};
+  CUtensorMapSwizzle swz;
+  if (maj == 0) { dims[0] = k; dims[1] = rows; box[0] = TC_BK; box[1] = 128; swz = CU_TENSOR_MAP_SWIZZLE_128B; }
+  else { dims[0] = rows; dims[1] = k; box[0] = 32; box[1] = TC_BK; swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; }
+  CUtensorMap m;
+  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) DTC_FAIL(DTC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for [%d x %d] ld %d major %d", (int)r, rows, k, ld, maj);
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps.emplace(key, m);
+  *out = m;
+  return DTC_OK;
+}
+
+bool dtc_gemm_tc_eligible(const GemmArgs& a) {
+  if (a.M < 64 || a.N < 100 || a.K < 8) return false;
+  if (!a.A_lo || !a.B_lo) return false;  // fp32-grade results need both companions; otherwise the FP32 SIMT path runs
+  if (a.a_kc != true && a.b_kc == true) return false;  // (MN-major A, K-major B) is not used by the learner
+  return true;
+}
+
+template <int AMAJ, int BMAJ>
+static int tc_launch_t(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB, const CUtensorMap& mBlo, const TcParams& p,
+                       dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DTC_CUDA(cudaFuncSetAttribute(k_gemm_tc<AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  k_gemm_tc<AMAJ, BMAJ><<<grid, 256, TC_SMEM_BYTES, st>>>(mA, mAlo, mB, mBlo, p);
+  return DTC_OK;
+}
+
+void k_splitk_reduce_launch(const float* ws, float* C, float* C_lo, int M, int N, int ldc, int splits, int accumulate, cudaStream_t st);
+
+int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
+  TcParams p{};
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.nkb = ceil_div(a.K, TC_BK);
+  int splits = a.splits < 1 ? 1 : a.splits;
+  if (a.ws && a.epi == EPI_STORE && splits < ceil_div(p.nkb, TC_MAX_KB)) splits = ceil_div(p.nkb, TC_MAX_KB);
+  if (splits > p.nkb) splits = p.nkb;
+  p.kb_per_split = ceil_div(p.nkb, splits);
+  splits = ceil_div(p.nkb, p.kb_per_split);
+  p.splits = splits;
+  if (splits > 1 && (a.epi != EPI_STORE || !a.ws)) DTC_FAIL(DTC_ERR_ARG, "gemm_tc: split-K needs EPI_STORE and a workspace");
+  p.C = a.C; p.C_lo = a.C_lo; p.ldc = a.ldc;
+  p.bias = a.bias; p.act_src = a.act_src; p.ld_act = a.ld_act; p.epi = a.epi; p.accumulate = a.accumulate ? 1 : 0;
+  p.ws = a.ws;
+  p.has_alo = a.A_lo ? 1 : 0; p.has_blo = a.B_lo ? 1 : 0;
+  const int amaj = a.a_kc ? 0 : 1, bmaj = a.b_kc ? 0 : 1;
+  CUtensorMap mA, mAlo, mB, mBlo;
+  RETURN_IF_ERR(tc_get_map(a.A, a.M, a.K, a.lda, amaj, &mA));
+  RETURN_IF_ERR(tc_get_map(a.B, a.N, a.K, a.ldb, bmaj, &mB));
+  if (a.A_lo) RETURN_IF_ERR(tc_get_map(a.A_lo, a.M, a.K, a.lda, amaj, &mAlo)); else mAlo = mA;
+  if (a.B_lo) RETURN_IF_ERR(tc_get_map(a.B_lo, a.N, a.K, a.ldb, bmaj, &mBlo)); else mBlo = mB;
+  dim3 grid(ceil_div(a.N, TC_BN), ceil_div(a.M, TC_BM), splits);
+  dtc_prof_begin(st, 0, 2.0 * a.M * a.N * a.K);
+  int rc;
+  if (amaj == 0 && bmaj == 0) rc = tc_launch_t<0, 0>(mA, mAlo, mB, mBlo, p, grid, st);
+  else if (amaj == 0 && bmaj == 1) rc = tc_launch_t<0, 1>(mA, mAlo, mB, mBlo, p, grid, st);
+  else if (amaj == 1 && bmaj == 1) rc = tc_launch_t<1, 1>(mA, mAlo, mB, mBlo, p, grid, st);
+  else DTC_FAIL(DTC_ERR_ARG, "gemm_tc: unsupported operand layout");
+  if (rc) return rc;
+  DTC_CHECK_LAUNCH("k_gemm_tc");
+  if (splits > 1) k_splitk_reduce_launch(a.ws, a.C, a.C_lo, a.M, a.N, a.ldc, splits, a.accumulate ? 1 : 0, st);
+  dtc_prof_end(st);
+  return DTC_OK;
+}

@@ -176,9 +176,24 @@ struct dtc_learner {
   double* stats;
   float* skws;  // split-K partials
   float* csws;  // column-sum partials
+  // 3xTF32 companions (dtc_gemm_tc.cu): every activation / gradient buffer has a twin at +lo_shift floats, the parameters
+  // have params_lo, the packed batch rows have the *_lo arrays of dtc_storage (registered per call in ext[])
+  float* ws_val_begin; float* ws_val_end; ptrdiff_t lo_shift;
+  float* params_lo;
+  struct { const float* base; size_t n; const float* lo; } ext[3];
   int64_t vae_steps, main_steps;
   int last_M;
 };
+
+static const float* lo_of(const dtc_learner* l, const float* p) {
+  if (!p) return nullptr;
+  if (p >= l->ws_val_begin && p < l->ws_val_end) return p + l->lo_shift;
+  if (p >= l->params && p < l->params + g_total) return l->params_lo + (p - l->params);
+  for (int i = 0; i < 3; ++i)
+    if (l->ext[i].base && p >= l->ext[i].base && p < l->ext[i].base + l->ext[i].n) return l->ext[i].lo ? l->ext[i].lo + (p - l->ext[i].base) : nullptr;
+  return nullptr;
+}
+static float* lo_of(const dtc_learner* l, float* p) { return const_cast<float*>(lo_of(l, (const float*)p)); }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -193,11 +208,17 @@ static size_t splitk_ws_floats(int R) {
   return mx;
 }
 
-extern "C" int64_t dtc_learner_workspace_bytes(int32_t max_rows) {
-  size_t R = max_rows, tot = 0;
+static size_t ws_value_bytes(size_t R) {
+  size_t tot = 0;
 #define X(name, ld) tot += align256(R * (ld) * sizeof(float));
   WS_BUFFERS(X)
 #undef X
+  return tot;
+}
+extern "C" int64_t dtc_learner_workspace_bytes(int32_t max_rows) {
+  build_table();
+  size_t R = max_rows, tot = 0;
+  tot += 2 * ws_value_bytes(R) + align256((size_t)g_total * sizeof(float));
   tot += align256(sizeof(LvStat)) + align256(ST_COUNT * sizeof(double));
   tot += align256(splitk_ws_floats(max_rows) * sizeof(float));
   tot += align256((size_t)COLSUM_CHUNKS * 768 * sizeof(float));
@@ -217,9 +238,15 @@ extern "C" int dtc_learner_create(int32_t max_rows, float* params, float* grads,
   l->m_main = adam_main_m; l->v_main = adam_main_v; l->m_vae = adam_vae_m; l->v_vae = adam_vae_v;
   char* p = (char*)workspace;
   size_t R = max_rows;
+  l->ws_val_begin = (float*)p;
 #define X(name, ld) l->name = (float*)p; p += align256(R * (ld) * sizeof(float));
   WS_BUFFERS(X)
 #undef X
+  l->ws_val_end = (float*)p;
+  l->lo_shift = (ptrdiff_t)(ws_value_bytes(R) / sizeof(float));
+  p += ws_value_bytes(R);
+  l->params_lo = (float*)p; p += align256((size_t)g_total * sizeof(float));
+  memset(l->ext, 0, sizeof(l->ext));
   l->lvstat = (LvStat*)p; p += align256(sizeof(LvStat));
   l->stats = (double*)p; p += align256(ST_COUNT * sizeof(double));
   l->skws = (float*)p; p += align256(splitk_ws_floats(max_rows) * sizeof(float));
@@ -227,10 +254,28 @@ extern "C" int dtc_learner_create(int32_t max_rows, float* params, float* grads,
   l->vae_steps = l->main_steps = 0;
   l->last_M = 0;
   DTC_CUDA(cudaMemset(l->stats, 0, ST_COUNT * sizeof(double)));
+  DTC_CUDA(cudaMemset(l->ws_val_begin, 0, 2 * ws_value_bytes(R)));
   *out = l;
-  return DTC_OK;
+  return dtc_learner_refresh_params(l, nullptr);
 }
 extern "C" void dtc_learner_destroy(dtc_learner* l) { delete l; }
+
+__global__ void __launch_bounds__(256) k_split_lo(const float* __restrict__ x, float* __restrict__ lo, int64_t n) {
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) lo[i] = tf32_lo(x[i]);
+}
+static int split_lo(const float* x, float* lo, int64_t n, cudaStream_t st) {
+  if (!lo || n <= 0) return DTC_OK;
+  int64_t b = (n + 255) / 256;
+  if (b > 148 * 8) b = 148 * 8;
+  k_split_lo<<<(int)b, 256, 0, st>>>(x, lo, n);
+  DTC_CHECK_LAUNCH("k_split_lo");
+  return DTC_OK;
+}
+// recomputes the TF32 companions of ALL parameters; call after writing the flat parameter buffer from outside
+extern "C" int dtc_learner_refresh_params(dtc_learner* l, void* stream) {
+  if (!l) DTC_FAIL(DTC_ERR_ARG, "null learner");
+  return split_lo(l->params, l->params_lo, g_total, (cudaStream_t)stream);
+}
 extern "C" double* dtc_learner_stats(dtc_learner* l) { return l ? l->stats : nullptr; }
 
 __global__ void k_set_double(double* p, double v) { *p = v; }
@@ -266,7 +311,7 @@ extern "C" int dtc_learner_debug_buffer(dtc_learner* l, const char* name, float*
 }
 
 // ------------------------------------------------------------------ GEMM helpers
-#define RET_IF(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+#define RET_IF(x) RETURN_IF_ERR(x)
 
 static int fwd(dtc_learner* l, int id, const float* A, int lda, float* C, int ldc, int act, int M, cudaStream_t st) {
   const Layer& L = g_layers[id];
@@ -274,6 +319,7 @@ static int fwd(dtc_learner* l, int id, const float* A, int lda, float* C, int ld
   g.A = A; g.lda = lda; g.a_kc = true;
   g.B = l->params + L.w; g.ldb = L.ld; g.b_kc = true;
   g.C = C; g.ldc = ldc; g.M = M; g.N = L.out; g.K = L.in;
+  g.A_lo = lo_of(l, A); g.B_lo = lo_of(l, g.B); g.C_lo = lo_of(l, C);
   g.bias = l->params + L.b;
   g.epi = act == 1 ? EPI_BIAS_RELU : act == 2 ? EPI_BIAS_ELU : EPI_BIAS;
   g.splits = 1;
@@ -285,6 +331,7 @@ static int wgrad(dtc_learner* l, int id, const float* dY, int ldy, const float* 
   GemmArgs g{};
   g.A = dY; g.lda = ldy; g.a_kc = false;
   g.B = X; g.ldb = ldx; g.b_kc = false;
+  g.A_lo = lo_of(l, dY); g.B_lo = lo_of(l, X);
   g.C = l->grads + L.w; g.ldc = L.ld; g.M = L.out; g.N = L.in; g.K = M;
   g.epi = EPI_STORE;
   g.splits = dtc_gemm_pick_splits(L.out, L.in, M);
@@ -299,6 +346,7 @@ static int dgrad(dtc_learner* l, int id, const float* dY, int ldy, float* dX, in
   GemmArgs g{};
   g.A = dY; g.lda = ldy; g.a_kc = true;
   g.B = l->params + L.w; g.ldb = L.ld; g.b_kc = false;
+  g.A_lo = lo_of(l, dY); g.B_lo = lo_of(l, g.B); g.C_lo = lo_of(l, dX);
   g.C = dX; g.ldc = lddx; g.M = M; g.N = ncols; g.K = L.out;
   g.act_src = act_src; g.ld_act = ld_act; g.epi = epi; g.accumulate = accumulate;
   g.splits = 1;
@@ -768,7 +816,7 @@ __global__ void k_step_scalars(double* stats, const float* piggy, int which, flo
   }
 }
 // clip_grad_norm_ + Adam (torch.optim.Adam single-tensor formulas) over a flat range
-__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, float* __restrict__ p_lo, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, int64_t n, const double* __restrict__ stats, int which,
                                               float grad_scale, float max_norm, double lr_fixed, double bc1, double bc2_sqrt) {
   const double norm = stats[which == 0 ? ST_GN_VAE : ST_GN_POL];
@@ -786,7 +834,9 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
     vi = __fadd_rn(__fmul_rn(vi, b2), __fmul_rn(__fmul_rn(w2, gi), gi));
     m[i] = mi; v[i] = vi;
     float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), bcs), 1e-8f);
-    p[i] = __fsub_rn(p[i], __fmul_rn(step_size, __fdiv_rn(mi, denom)));
+    const float pn = __fsub_rn(p[i], __fmul_rn(step_size, __fdiv_rn(mi, denom)));
+    p[i] = pn;
+    p_lo[i] = tf32_lo(pn);
     (void)b1;
   }
 }
@@ -909,7 +959,7 @@ static int encode(dtc_learner* l, int M, const float* hist, const float* priv_a,
   RET_IF(fwd(l, TE4, l->T2, 512, X, ldx, 0, M, st));
   k_latent_fwd<<<ceil_div(M, 8), 128, 0, st>>>(M, mode, l->ML, l->lvstat, eps, seed, counter, l->EPS, l->OUTM, xc, X);
   DTC_CHECK_LAUNCH("k_latent_fwd");
-  return DTC_OK;
+  return split_lo(X, lo_of(l, X), (int64_t)M * ldx, st);  // z / mu / obs columns were written outside a GEMM epilogue
 }
 
 // backward of encode(): dX holds d l_t | d z | d mu[:3] (layout of X); fills the gradients of CE0, CE2, LAT, TE0..TE4
@@ -919,6 +969,7 @@ static int encode_bwd(dtc_learner* l, int M, const float* hist, const float* pri
   DTC_CHECK_LAUNCH("k_latent_bwd");
   k_lv_median_grad<<<grid1d((long long)M * 16, 256, 148 * 2), 256, 0, st>>>(M, l->ML, l->OUTM, l->dML, l->lvstat);
   DTC_CHECK_LAUNCH("k_lv_median_grad");
+  RET_IF(split_lo(l->dML, lo_of(l, l->dML), (int64_t)M * LD_ML, st));
   RET_IF(wgrad(l, LAT, l->dML, LD_ML, l->E, 64, M, st));
   RET_IF(dgrad(l, LAT, l->dML, LD_ML, l->dE, 64, 64, nullptr, 0, EPI_STORE, false, M, st));
   RET_IF(wgrad(l, CE2, l->dE, 64, l->H1, 128, M, st));
@@ -976,6 +1027,17 @@ extern "C" int dtc_policy_act(dtc_learner* l, int32_t M, const float* obs, int32
   k_pack_inputs<<<grid1d((long long)M * (LD_HIST + LD_PRIVA + LD_XC), 256), 256, 0, st>>>(M, obs, obs_ld, hist, hist_ld, priv, priv_ld,
                                                                                            base_vel, bv_ld, xh, xp, xc);
   DTC_CHECK_LAUNCH("k_pack_inputs");
+  if (s) {
+    const size_t b = (size_t)step * s->N;
+    l->ext[0] = {xh, (size_t)M * LD_HIST, s->hist_lo ? s->hist_lo + b * LD_HIST : nullptr};
+    l->ext[1] = {xp, (size_t)M * LD_PRIVA, s->priv_a_lo ? s->priv_a_lo + b * LD_PRIVA : nullptr};
+    l->ext[2] = {xc, (size_t)M * LD_XC, s->xc_lo ? s->xc_lo + b * LD_XC : nullptr};
+  } else {
+    memset(l->ext, 0, sizeof(l->ext));
+  }
+  RET_IF(split_lo(xh, lo_of(l, xh), (int64_t)M * LD_HIST, st));
+  RET_IF(split_lo(xp, lo_of(l, xp), (int64_t)M * LD_PRIVA, st));
+  RET_IF(split_lo(xc, lo_of(l, xc), (int64_t)M * LD_XC, st));
   RET_IF(encode(l, M, xh, xp, xc, 0, eps_z, seed, counter * 2, st));
   RET_IF(actor_fwd(l, M, st));
   RET_IF(critic_fwd(l, M, xc, st));
@@ -993,6 +1055,7 @@ extern "C" int dtc_policy_evaluate(dtc_learner* l, int32_t M, const float* obs, 
   k_pack_inputs<<<grid1d((long long)M * (LD_HIST + LD_PRIVA + LD_XC), 256), 256, 0, st>>>(M, obs, obs_ld, nullptr, 0, priv, priv_ld,
                                                                                            base_vel, bv_ld, nullptr, nullptr, l->XC);
   DTC_CHECK_LAUNCH("k_pack_inputs");
+  RET_IF(split_lo(l->XC, lo_of(l, l->XC), (int64_t)M * LD_XC, st));
   RET_IF(critic_fwd(l, M, l->XC, st));
   k_copy_col0<<<ceil_div(M, 256), 256, 0, st>>>(M, l->V, 4, values);
   DTC_CHECK_LAUNCH("k_copy_col0");
@@ -1033,6 +1096,8 @@ extern "C" int dtc_policy_act_teacher(dtc_learner* l, int32_t M, const float* ob
   k_pack_inputs<<<grid1d((long long)M * (LD_HIST + LD_PRIVA + LD_XC), 256), 256, 0, st>>>(M, obs, obs_ld, hist, hist_ld, priv, priv_ld,
                                                                                            obs, obs_ld, l->XH, l->XP, l->XC);
   DTC_CHECK_LAUNCH("k_pack_inputs");
+  RET_IF(split_lo(l->XH, lo_of(l, l->XH), (int64_t)M * LD_HIST, st));
+  RET_IF(split_lo(l->XP, lo_of(l, l->XP), (int64_t)M * LD_PRIVA, st));
   RET_IF(fwd(l, CE0, l->XH, LD_HIST, l->H1, 128, 1, M, st));
   RET_IF(fwd(l, CE2, l->H1, 128, l->E, 64, 0, M, st));
   RET_IF(fwd(l, LAT, l->E, 64, l->ML, LD_ML, 0, M, st));
@@ -1041,11 +1106,13 @@ extern "C" int dtc_policy_act_teacher(dtc_learner* l, int32_t M, const float* ob
   RET_IF(fwd(l, TE4, l->T2, 512, l->XA, LD_XA, 0, M, st));
   k_teacher_pack<<<grid1d((long long)M * LD_XM, 256), 256, 0, st>>>(M, l->XA, l->XH, l->XM);
   DTC_CHECK_LAUNCH("k_teacher_pack");
+  RET_IF(split_lo(l->XM, lo_of(l, l->XM), (int64_t)M * LD_XM, st));
   RET_IF(fwd(l, MM0, l->XM, LD_XM, l->C2, 256, 1, M, st));
   RET_IF(fwd(l, MM2, l->C2, 256, l->C3, 128, 1, M, st));
   RET_IF(fwd(l, MM4, l->C3, 128, l->C1, 512, 0, M, st));
   k_teacher_gate<<<grid1d((long long)M * LD_XA, 256), 256, 0, st>>>(M, l->C1, l->ML, l->XC, l->XA);
   DTC_CHECK_LAUNCH("k_teacher_gate");
+  RET_IF(split_lo(l->XA, lo_of(l, l->XA), (int64_t)M * LD_XA, st));
   RET_IF(actor_fwd(l, M, st));
   DTC_CUDA(cudaMemcpyAsync(actions, l->MEAN, (size_t)M * 12 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return DTC_OK;
@@ -1087,7 +1154,10 @@ extern "C" int dtc_gather_minibatch(const dtc_storage* src, const dtc_storage* d
   if (rows == 0) return DTC_OK;
   k_gather<<<grid1d(rows * 32, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(*src, *dst, perm, rows);
   DTC_CHECK_LAUNCH("k_gather");
-  return DTC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  RET_IF(split_lo(dst->hist, dst->hist_lo, rows * LD_HIST, st));
+  RET_IF(split_lo(dst->priv_a, dst->priv_a_lo, rows * LD_PRIVA, st));
+  return split_lo(dst->xc, dst->xc_lo, rows * LD_XC, st);
 }
 
 static int optimizer_apply(dtc_learner* l, int which, const dtc_ppo_hparams* hp, float grad_scale, int rows_global, cudaStream_t st) {
@@ -1104,7 +1174,7 @@ static int optimizer_apply(dtc_learner* l, int which, const dtc_ppo_hparams* hp,
   const double bc1 = 1.0 - pow(0.9, (double)steps), bc2 = 1.0 - pow(0.999, (double)steps);
   float* m = which == 0 ? l->m_vae : l->m_main;
   float* v = which == 0 ? l->v_vae : l->v_main;
-  k_adam<<<grid1d(n, 256, 148 * 8), 256, 0, st>>>(l->params + b, l->grads + b, m + b, v + b, n, l->stats, which, grad_scale,
+  k_adam<<<grid1d(n, 256, 148 * 8), 256, 0, st>>>(l->params + b, l->params_lo + b, l->grads + b, m + b, v + b, n, l->stats, which, grad_scale,
                                                  hp->max_grad_norm, 5.e-4, bc1, sqrt(bc2));
   DTC_CHECK_LAUNCH("k_adam");
   return DTC_OK;
@@ -1135,6 +1205,12 @@ extern "C" int dtc_vae_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
   const float* priv_a = batch->priv_a + row0 * LD_PRIVA;
   const float* xc = batch->xc + row0 * LD_XC;
   const float* next_obs = batch->next_obs + row0 * 56;
+  l->ext[0] = {hist, (size_t)M * LD_HIST, batch->hist_lo ? batch->hist_lo + row0 * LD_HIST : nullptr};
+  l->ext[1] = {priv_a, (size_t)M * LD_PRIVA, batch->priv_a_lo ? batch->priv_a_lo + row0 * LD_PRIVA : nullptr};
+  l->ext[2] = {xc, (size_t)M * LD_XC, batch->xc_lo ? batch->xc_lo + row0 * LD_XC : nullptr};
+  l->ext[0] = {hist, (size_t)M * LD_HIST, batch->hist_lo ? batch->hist_lo + row0 * LD_HIST : nullptr};
+  l->ext[1] = {priv_a, (size_t)M * LD_PRIVA, batch->priv_a_lo ? batch->priv_a_lo + row0 * LD_PRIVA : nullptr};
+  l->ext[2] = {xc, (size_t)M * LD_XC, batch->xc_lo ? batch->xc_lo + row0 * LD_XC : nullptr};
   const float inv_rows = 1.0f / (float)M;
   // forward (ppo.py:197-223)
   RET_IF(encode(l, M, hist, priv_a, xc, 1, eps, seed, counter, st));
@@ -1149,6 +1225,8 @@ extern "C" int dtc_vae_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
   DTC_CHECK_LAUNCH("k_vae_loss_rows");
   k_vae_loss_height<<<grid1d((long long)M * 696, 256), 256, 0, st>>>(M, 1.0f / ((float)M * 693.0f), l->HR, xc, l->dHR, l->stats);
   DTC_CHECK_LAUNCH("k_vae_loss_height");
+  RET_IF(split_lo(l->dREC, lo_of(l, l->dREC), (int64_t)M * 56, st));
+  RET_IF(split_lo(l->dHR, lo_of(l, l->dHR), (int64_t)M * 696, st));
   // backward: cenet decoder
   RET_IF(wgrad(l, CD4, l->dREC, 56, l->D2, 128, M, st));
   RET_IF(dgrad(l, CD4, l->dREC, 56, l->dD2, 128, 128, l->D2, 128, EPI_DRELU, false, M, st));
@@ -1177,6 +1255,9 @@ extern "C" int dtc_ppo_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
   const float* hist = batch->hist + row0 * LD_HIST;
   const float* priv_a = batch->priv_a + row0 * LD_PRIVA;
   const float* xc = batch->xc + row0 * LD_XC;
+  l->ext[0] = {hist, (size_t)M * LD_HIST, batch->hist_lo ? batch->hist_lo + row0 * LD_HIST : nullptr};
+  l->ext[1] = {priv_a, (size_t)M * LD_PRIVA, batch->priv_a_lo ? batch->priv_a_lo + row0 * LD_PRIVA : nullptr};
+  l->ext[2] = {xc, (size_t)M * LD_XC, batch->xc_lo ? batch->xc_lo + row0 * LD_XC : nullptr};
   const float inv_rows = 1.0f / (float)M;
   // forward (ppo.py:265-292)
   RET_IF(encode(l, M, hist, priv_a, xc, 0, eps, seed, counter, st));
@@ -1190,6 +1271,8 @@ extern "C" int dtc_ppo_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
   DTC_CHECK_LAUNCH("k_ppo_loss");
   k_publish_kl<<<1, 1, 0, st>>>(l->stats, l->grads + g_off_piggy);
   DTC_CHECK_LAUNCH("k_publish_kl");
+  RET_IF(split_lo(l->dMEAN, lo_of(l, l->dMEAN), (int64_t)M * 12, st));
+  RET_IF(split_lo(l->dV, lo_of(l, l->dV), (int64_t)M * 4, st));
   // backward: actor
   RET_IF(wgrad(l, AB6, l->dMEAN, 12, l->A3, 128, M, st));
   RET_IF(dgrad(l, AB6, l->dMEAN, 12, l->dA3, 128, 128, l->A3, 128, EPI_DELU, false, M, st));
@@ -1212,12 +1295,17 @@ extern "C" int dtc_ppo_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
   return optimizer_apply(l, 1, hp, 1.0f, M, st);
 }
 
-extern "C" int dtc_gemm_debug(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int32_t a_kc, const float* B, int32_t ldb,
-                              int32_t b_kc, float* C, int32_t ldc, int32_t splits, float* ws, void* stream) {
+extern "C" int dtc_gemm_debug(int32_t M, int32_t N, int32_t K, const float* A, const float* A_lo, int32_t lda, int32_t a_kc, const float* B,
+                              const float* B_lo, int32_t ldb, int32_t b_kc, float* C, float* C_lo, int32_t ldc, int32_t splits, float* ws,
+                              int32_t mode, void* stream) {
   GemmArgs g{};
-  g.A = A; g.lda = lda; g.a_kc = a_kc != 0;
-  g.B = B; g.ldb = ldb; g.b_kc = b_kc != 0;
-  g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+  g.A = A; g.A_lo = A_lo; g.lda = lda; g.a_kc = a_kc != 0;
+  g.B = B; g.B_lo = B_lo; g.ldb = ldb; g.b_kc = b_kc != 0;
+  g.C = C; g.C_lo = C_lo; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
   g.epi = EPI_STORE; g.splits = splits; g.ws = ws;
-  return dtc_gemm_launch(g, (cudaStream_t)stream);
+  const int saved = dtc_gemm_mode();
+  dtc_gemm_set_mode(mode);
+  int rc = dtc_gemm_launch(g, (cudaStream_t)stream);
+  dtc_gemm_set_mode(saved);
+  return rc;
 }

@@ -203,7 +203,13 @@ class ActorCriticDecoder:
                 if tuple(v.shape) != self._table.shape[k]:
                     raise ValueError(f"{k}: shape {tuple(v.shape)} != {self._table.shape[k]}")
                 self._flat[self._idx[k]] = v.reshape(-1)
+        self._params_written()
         return self
+
+    def _params_written(self):
+        """The flat buffer was written from outside the kernels: refresh the 3xTF32 companions of the parameters."""
+        if self._h is not None:
+            B.check(B.lib().dtc_learner_refresh_params(self._h, B.stream_ptr(self.device)), "dtc_learner_refresh_params")
 
     @property
     def std(self):

@@ -49,6 +49,8 @@ class RolloutStorage:
         self.num_transitions_per_env, self.num_envs = T, N
         f = lambda *s: torch.zeros(*s, device=self.device, dtype=torch.float32)
         self.hist, self.priv_a, self.xc, self.next_obs_p = f(T, N, 268), f(T, N, 696), f(T, N, 752), f(T, N, 56)
+        # 3xTF32 companions of the GEMM-input arrays (csrc/dtc_gemm_tc.cu), maintained by the kernels
+        self._hist_lo, self._priv_a_lo, self._xc_lo = f(T, N, 268), f(T, N, 696), f(T, N, 752)
         self.actions, self.mu, self.sigma = f(T, N, 12), f(T, N, 12), f(T, N, 12)
         self.rewards, self.values, self.returns = f(T, N, 1), f(T, N, 1), f(T, N, 1)
         self.advantages, self.actions_log_prob = f(T, N, 1), f(T, N, 1)
@@ -66,7 +68,8 @@ class RolloutStorage:
         for name, t in (("hist", self.hist), ("priv_a", self.priv_a), ("xc", self.xc), ("next_obs", self.next_obs_p),
                         ("actions", self.actions), ("mu", self.mu), ("sigma", self.sigma), ("rewards", self.rewards),
                         ("values", self.values), ("returns", self.returns), ("advantages", self.advantages),
-                        ("logp", self.actions_log_prob), ("dones", self.dones)):
+                        ("logp", self.actions_log_prob), ("dones", self.dones), ("hist_lo", self._hist_lo),
+                        ("priv_a_lo", self._priv_a_lo), ("xc_lo", self._xc_lo)):
             assert t.is_contiguous()
             setattr(s, name, t.data_ptr())
         s.T, s.N = self.num_transitions_per_env, self.num_envs
@@ -105,6 +108,9 @@ class RolloutStorage:
         self.xc[s, :, :696].copy_(t.privileged_observations[:, 693:])
         self.xc[s, :, 696:749].copy_(t.observations)
         self.xc[s, :, 749:752].copy_(t.base_vel)
+        for x, lo in ((self.hist, self._hist_lo), (self.priv_a, self._priv_a_lo), (self.xc, self._xc_lo)):
+            r = x[s] - (x[s].view(torch.int32) & -8192).view(torch.float32)            # x - trunc_tf32(x)
+            lo[s] = ((r.view(torch.int32) + 0x1000) & -8192).view(torch.float32)     # rounded to TF32
         self.next_obs_p[s, :, :53].copy_(t.next_observations)
         self.actions[s].copy_(t.actions)
         self.rewards[s].copy_(t.rewards.view(-1, 1))

@@ -188,6 +188,9 @@ typedef struct {
   float *hist, *priv_a, *xc, *next_obs, *actions, *mu, *sigma;
   float *rewards, *values, *returns, *advantages, *logp;
   uint8_t* dones;
+  /* optional 3xTF32 companions of the three GEMM-input arrays (x - trunc_tf32(x), same shapes); NULL = those GEMMs run on
+   * the FP32 SIMT path.  Written by dtc_policy_act / dtc_gather_minibatch. */
+  float *hist_lo, *priv_a_lo, *xc_lo;
   int32_t T, N;
 } dtc_storage;
 
@@ -197,6 +200,8 @@ int dtc_learner_create(int32_t max_rows, float* params, float* grads, float* ada
                        float* adam_vae_m, float* adam_vae_v, void* workspace, int64_t workspace_bytes,
                        dtc_learner** out);
 void dtc_learner_destroy(dtc_learner* l);
+/* call after writing the flat parameter buffer from outside (load_state_dict): refreshes the 3xTF32 companions */
+int dtc_learner_refresh_params(dtc_learner* l, void* stream);
 
 /* P6: PPO.act = ActorCriticDecoder.act + evaluate + log_prob (ppo.py:137-155; actor_critic_decoder.py:409-451,540-551).
  * eps_z [M,16] / eps_a [M,12]: standard normal draws, or NULL for in-kernel Philox(seed, counter).
@@ -258,9 +263,14 @@ int dtc_learner_debug_buffer(dtc_learner* l, const char* name, float** ptr, int3
 /* plain GEMM entry (tests / microbench): C[M,N] = act(A[M,K] * W[N,K]^T + bias) */
 int dtc_linear_forward(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* W, int32_t ldw,
                        const float* bias, int32_t act /*0 none,1 relu,2 elu*/, float* C, int32_t ldc, void* stream);
-/* general form used by the learner: C = epi(A op B) with either operand k-contiguous (1) or k-strided (0); tests */
-int dtc_gemm_debug(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int32_t a_kc, const float* B, int32_t ldb,
-                   int32_t b_kc, float* C, int32_t ldc, int32_t splits, float* ws, void* stream);
+/* general form used by the learner: C = A op B with either operand k-contiguous (1) or k-strided (0); tests and
+ * microbenchmarks.  mode 0 = FP32 SIMT, 1 = tcgen05 3xTF32 (A_lo / B_lo = companions x - trunc_tf32(x), may be NULL). */
+int dtc_gemm_debug(int32_t M, int32_t N, int32_t K, const float* A, const float* A_lo, int32_t lda, int32_t a_kc, const float* B,
+                   const float* B_lo, int32_t ldb, int32_t b_kc, float* C, float* C_lo, int32_t ldc, int32_t splits, float* ws,
+                   int32_t mode, void* stream);
+/* GEMM engine of the learner: 0 = FP32 SIMT, 1 = tcgen05 3xTF32 for tile-worthy shapes (default; env DTC_GEMM=simt|tc) */
+void dtc_set_gemm_mode(int mode);
+int dtc_get_gemm_mode(void);
 
 #ifdef __cplusplus
 }

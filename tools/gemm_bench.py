@@ -25,12 +25,18 @@ def main():
         t = bench(lambda: lib.dtc_linear_forward(M, N, K, B.ptr(A), A.shape[1], B.ptr(W), W.shape[1], B.ptr(b), 1, B.ptr(Cc), Cc.shape[1], st))
         out[f"fwd_{N}x{K}"] = round(2 * M * N * K / t / 1e12, 2)
         dY = torch.randn(M, r4(N), device="cuda"); dX = torch.empty(M, r4(K), device="cuda")
-        t = bench(lambda: lib.dtc_gemm_debug(M, K, N, B.ptr(dY), dY.shape[1], 1, B.ptr(W), W.shape[1], 0, B.ptr(dX), dX.shape[1], 1, None, st))
-        out[f"dgrad_{N}x{K}"] = round(2 * M * N * K / t / 1e12, 2)
-        splits = 25
-        ws = torch.empty(splits * N * r4(K), device="cuda"); dW = torch.empty(N, r4(K), device="cuda")
-        t = bench(lambda: lib.dtc_gemm_debug(N, K, M, B.ptr(dY), dY.shape[1], 0, B.ptr(A), A.shape[1], 0, B.ptr(dW), dW.shape[1], splits, B.ptr(ws), st))
-        out[f"wgrad_{N}x{K}"] = round(2 * M * N * K / t / 1e12, 2)
+        lo = lambda x: x - (x.view(torch.int32) & -8192).view(torch.float32)
+        Al, Wl, dYl = lo(A), lo(W), lo(dY)
+        Cl = torch.empty_like(Cc)
+        for mode, tag in ((0, "simt"), (1, "tc")):
+            t = bench(lambda: lib.dtc_gemm_debug(M, N, K, B.ptr(A), B.ptr(Al), A.shape[1], 1, B.ptr(W), B.ptr(Wl), W.shape[1], 1, B.ptr(Cc), B.ptr(Cl), Cc.shape[1], 1, None, mode, st))
+            out[f"{tag}_fwd_{N}x{K}"] = round(2 * M * N * K / t / 1e12, 2)
+            t = bench(lambda: lib.dtc_gemm_debug(M, K, N, B.ptr(dY), B.ptr(dYl), dY.shape[1], 1, B.ptr(W), B.ptr(Wl), W.shape[1], 0, B.ptr(dX), None, dX.shape[1], 1, None, mode, st))
+            out[f"{tag}_dgrad_{N}x{K}"] = round(2 * M * N * K / t / 1e12, 2)
+            splits = 25 if mode == 0 else max(1, 148 // (((N + 127) // 128) * ((K + 127) // 128)))
+            ws = torch.empty(splits * N * r4(K), device="cuda"); dW = torch.empty(N, r4(K), device="cuda")
+            t = bench(lambda: lib.dtc_gemm_debug(N, K, M, B.ptr(dY), B.ptr(dYl), dY.shape[1], 0, B.ptr(A), B.ptr(Al), A.shape[1], 0, B.ptr(dW), None, dW.shape[1], splits, B.ptr(ws), mode, st))
+            out[f"{tag}_wgrad_{N}x{K}"] = round(2 * M * N * K / t / 1e12, 2)
         t = bench(lambda: torch.mm(A, W.t()))
         out[f"torch_mm_{N}x{K}"] = round(2 * M * N * r4(K) / t / 1e12, 2)
     print(json.dumps({"M": M, "tflops": out}))
