@@ -15,10 +15,10 @@ dtc_optimizer_apply finishes with grad_scale = 1/world.  The advantage moments a
 import ctypes as C
 
 import torch
-import torch.distributed as dist
 
 from ... import _lib as B
 from ..storage import RolloutStorage
+from ..utils import dp
 
 
 class _DeviceAdamHandle:
@@ -141,9 +141,7 @@ class PPO:
         self.storage.compute_returns(last_values, self.gamma, self.lam, group=self.group)
 
     def _world(self):
-        if dist.is_available() and dist.is_initialized():
-            return dist.get_world_size(self.group)
-        return 1
+        return dp.world_size(self.group)
 
     def update(self):
         ac, st, lib = self.actor_critic, self.storage, B.lib()
@@ -181,13 +179,13 @@ class PPO:
                         "dtc_vae_step")
                 if sync:
                     b0, b1 = tab.ranges["vae"]
-                    dist.all_reduce(ac._grads[b0:b1], group=self.group)
+                    dp.allreduce_sum_(ac._grads[b0:b1], self.group)
                     B.check(lib.dtc_optimizer_apply(h, 0, C.byref(hp), 1.0 / world, mbs * world, stream), "dtc_optimizer_apply")
                 B.check(lib.dtc_ppo_step(h, C.byref(batch._c), i * mbs, mbs, B.ptr(e2), ac.seed + 7919, ctr + 1, C.byref(hp), sync, stream),
                         "dtc_ppo_step")
                 if sync:
                     b0, b1 = tab.ranges["policy_sync"]
-                    dist.all_reduce(ac._grads[b0:b1], group=self.group)
+                    dp.allreduce_sum_(ac._grads[b0:b1], self.group)
                     B.check(lib.dtc_optimizer_apply(h, 1, C.byref(hp), 1.0 / world, mbs * world, stream), "dtc_optimizer_apply")
         s = ac.stats().tolist()  # the one device->host read of update()
         n = self.num_learning_epochs * self.num_mini_batches

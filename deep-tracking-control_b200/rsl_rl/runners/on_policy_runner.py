@@ -25,6 +25,7 @@ class OnPolicyRunner:
         self.env = HistoryWrapper(env)
         num_critic_obs = self.env.num_privileged_obs if self.env.num_privileged_obs is not None else self.env.num_obs
         actor_critic = ActorCriticDecoder(self.env.num_obs, num_critic_obs, self.env.num_actions, **self.policy_cfg).to(self.device)
+        actor_critic.seed = int(getattr(env, "seed", 0))  # per-rank noise stream under data parallelism
         self.alg = PPO(actor_critic, device=self.device, **self.alg_cfg)
         self.num_steps_per_env = self.cfg["num_steps_per_env"]
         self.save_interval = self.cfg["save_interval"]

@@ -129,11 +129,11 @@ class RolloutStorage:
         lv = last_values.reshape(-1).contiguous().float()
         B.require_cuda(lv, "last_values")
         st = B.stream_ptr(self.device)
-        dp = group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                   and torch.distributed.get_world_size() > 1)
-        B.check(B.lib().dtc_gae(C.byref(self._c), B.ptr(lv), gamma, lam, B.ptr(self._scratch), 1 if dp else 0, st), "dtc_gae")
-        if dp:
-            torch.distributed.all_reduce(self._scratch[:3], group=group)
+        from ..utils import dp
+        multi = dp.world_size(group) > 1
+        B.check(B.lib().dtc_gae(C.byref(self._c), B.ptr(lv), gamma, lam, B.ptr(self._scratch), 1 if multi else 0, st), "dtc_gae")
+        if multi:
+            dp.combine_moments_(self._scratch[:3], group)
             B.check(B.lib().dtc_gae_normalize(C.byref(self._c), B.ptr(self._scratch), st), "dtc_gae_normalize")
 
     def get_statistics(self):
