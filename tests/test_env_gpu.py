@@ -70,8 +70,8 @@ def _compare_step(o, c, tag, sel=None):
     _close(c.get_base_vel(), o.get_base_vel(), tag + "base_vel")
 
 
-@pytest.mark.parametrize("N,kind,variant", [(64, "stones", 0), (64, "flat", 0), (256, "curriculum", 3), (4096, "stones", 0),
-                                            (1000, "stones", 3)])
+@pytest.mark.parametrize("N,kind,variant", [(64, "stones", 0), (64, "flat", 4), (256, "curriculum", 3), (4096, "stones", 4),
+                                            (1000, "stones", 3), (256, "curriculum", 4), (1000, "stones", 4), (64, "stones", 4)])
 def test_env_step_parity(N, kind, variant):
     from oracle import env_oracle as EO
     oenv, cenv, fg_cpu, fg_gpu = H.make_pair(N, kind, seed=3)
@@ -104,12 +104,14 @@ def test_env_step_parity(N, kind, variant):
         _compare_step(oenv, cenv, f"N{N} {kind} v{variant} step{t} ", sel)
 
 
-def test_debug_score_matches_bruteforce():
+@pytest.mark.parametrize("variant", [0, 4])
+def test_debug_score_matches_bruteforce(variant):
     """The windowed argmin equals the reference's brute-force 693x4 scan: dump the full score tensor from the kernel
     and check argmin(score) == optimal_idx, plus the tensor itself against the oracle."""
     from oracle import env_oracle as EO
     N = 512
     oenv, cenv, fg_cpu, fg_gpu = H.make_pair(N, "stones", seed=5)
+    cenv.foothold_variant = variant
     g = torch.Generator().manual_seed(1)
     st = [sim_stub.synth_state(N, oenv.env_origins, g) for _ in range(2)]
     st[1]["root_states"][5:25, 2] += 1.5  # everything under these robots is an exception point -> fall-back argmin
