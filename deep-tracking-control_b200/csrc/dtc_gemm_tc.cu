@@ -6,9 +6,9 @@
 // TF32 (measured, tools/tc_probe.cu), so with  x_lo = rn_tf32(x - trunc_tf32(x))  kept next to every operand,
 //     A B^T  ~=  A.B + A_lo.B + A.B_lo          (three MMAs per k-step into the same TMEM accumulator)
 // leaves a relative error of ~2^-21 per product - the same order as fp32 summation-order noise.
-// The TMEM accumulator add rounds toward zero (measured: ~0.25 ulp systematic error per accumulation step), so the k-steps
-// are dealt round-robin onto TC_NACC main accumulators, the two small correction products go to their own accumulator,
-// and the four are summed in fp32 in the epilogue; reductions longer than TC_MAX_KB k-blocks are split and summed in fp32.
+// The TMEM accumulator add rounds toward zero (measured: ~0.25 ulp systematic error per accumulation step), so the two
+// small correction products go to their OWN accumulator (one truncating add per k-step on the main one instead of three),
+// the two are summed in fp32 in the epilogue, and reductions longer than TC_MAX_KB k-blocks are split and summed in fp32.
 //
 // Same contract as the SIMT family (dtc_gemm.cu): C[m,n] = epi(sum_k A(m,k) B(n,k)), each operand k-contiguous
 // ("K-major": TMA box 32k x 128 rows, SWIZZLE_128B) or k-strided ("MN-major": four boxes 32mn x 32k, SWIZZLE_128B with
@@ -23,12 +23,12 @@
 #define TC_BN 128
 #define TC_BK 32
 #define TC_STAGES 3
-#define TC_NACC 3        // main accumulators (columns [0, 3*128)); correction accumulator at column 3*128
 #define TC_TMEM_COLS 512
 #define TC_MAX_KB 32     // k-blocks (of 32) accumulated in TMEM before the fp32 split-K sum takes over
 #define TC_TILE_BYTES (128 * 32 * 4)
 #define TC_STAGE_BYTES (4 * TC_TILE_BYTES)
-#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024)
+#define TC_STG_BYTES (4 * 32 * 36 * 4)  // epilogue staging: 4 warps x 32 rows x 36 floats
+#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + TC_STG_BYTES + 1024)
 
 struct TcParams {
   int M, N, K;
@@ -90,23 +90,24 @@ __device__ __forceinline__ float tc_epi(float v, int epi, float bias, float src)
   }
 }
 
+// Persistent kernel: one CTA per SM walks the (split, m-tile, n-tile) list with stride gridDim.x.  TMEM holds two
+// accumulator sets (main | correction, 2 x 128 columns each), so the epilogue of tile j overlaps the MMAs of tile j+1; the TMA
+// producer runs ahead across tile boundaries.
 template <int AMAJ, int BMAJ>
 __global__ void __launch_bounds__(256, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapB,
           const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
   extern __shared__ uint8_t tc_smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_acc;
+  __shared__ __align__(8) uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   const uint32_t smem0 = (tc_smem_u32(tc_smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM;
-  const int kb0 = blockIdx.z * p.kb_per_split;
-  const int kb1 = min(p.nkb, kb0 + p.kb_per_split);
-  const int nloc = kb1 - kb0;
+  const int nt_n = (p.N + TC_BN - 1) / TC_BN, nt_m = (p.M + TC_BM - 1) / TC_BM;
+  const int ntiles = nt_n * nt_m * p.splits;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(&bar_full[s], 1); tc_mbar_init(&bar_empty[s], 1); }
-    tc_mbar_init(&bar_acc, 1);
+    for (int s = 0; s < 2; ++s) { tc_mbar_init(&bar_acc_full[s], 1); tc_mbar_init(&bar_acc_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -121,29 +122,34 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
     const uint32_t bytes = TC_TILE_BYTES * (2 + p.has_alo + p.has_blo);
-    for (int it = 0; it < nloc; ++it) {
-      const int s = it % TC_STAGES, kb = kb0 + it;
-      tc_mbar_wait(&bar_empty[s], ((it / TC_STAGES) & 1) ^ 1);
-      tc_mbar_expect_tx(&bar_full[s], bytes);
-      const uint32_t st = smem0 + s * TC_STAGE_BYTES;
-      if (AMAJ == 0) {
-        tc_tma_2d(st, &mapA, &bar_full[s], kb * TC_BK, m0);
-        if (p.has_alo) tc_tma_2d(st + TC_TILE_BYTES, &mapAlo, &bar_full[s], kb * TC_BK, m0);
-      } else {
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int n0 = (t % nt_n) * TC_BN, m0 = ((t / nt_n) % nt_m) * TC_BM, z = t / (nt_n * nt_m);
+      const int kb0 = z * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % TC_STAGES;
+        tc_mbar_wait(&bar_empty[s], ((it / TC_STAGES) & 1) ^ 1);
+        tc_mbar_expect_tx(&bar_full[s], bytes);
+        const uint32_t st = smem0 + s * TC_STAGE_BYTES;
+        if (AMAJ == 0) {
+          tc_tma_2d(st, &mapA, &bar_full[s], kb * TC_BK, m0);
+          if (p.has_alo) tc_tma_2d(st + TC_TILE_BYTES, &mapAlo, &bar_full[s], kb * TC_BK, m0);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          tc_tma_2d(st + j * 4096, &mapA, &bar_full[s], m0 + 32 * j, kb * TC_BK);
-          if (p.has_alo) tc_tma_2d(st + TC_TILE_BYTES + j * 4096, &mapAlo, &bar_full[s], m0 + 32 * j, kb * TC_BK);
+          for (int j = 0; j < 4; ++j) {
+            tc_tma_2d(st + j * 4096, &mapA, &bar_full[s], m0 + 32 * j, kb * TC_BK);
+            if (p.has_alo) tc_tma_2d(st + TC_TILE_BYTES + j * 4096, &mapAlo, &bar_full[s], m0 + 32 * j, kb * TC_BK);
+          }
         }
-      }
-      if (BMAJ == 0) {
-        tc_tma_2d(st + 2 * TC_TILE_BYTES, &mapB, &bar_full[s], kb * TC_BK, n0);
-        if (p.has_blo) tc_tma_2d(st + 3 * TC_TILE_BYTES, &mapBlo, &bar_full[s], kb * TC_BK, n0);
-      } else {
+        if (BMAJ == 0) {
+          tc_tma_2d(st + 2 * TC_TILE_BYTES, &mapB, &bar_full[s], kb * TC_BK, n0);
+          if (p.has_blo) tc_tma_2d(st + 3 * TC_TILE_BYTES, &mapBlo, &bar_full[s], kb * TC_BK, n0);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          tc_tma_2d(st + 2 * TC_TILE_BYTES + j * 4096, &mapB, &bar_full[s], n0 + 32 * j, kb * TC_BK);
-          if (p.has_blo) tc_tma_2d(st + 3 * TC_TILE_BYTES + j * 4096, &mapBlo, &bar_full[s], n0 + 32 * j, kb * TC_BK);
+          for (int j = 0; j < 4; ++j) {
+            tc_tma_2d(st + 2 * TC_TILE_BYTES + j * 4096, &mapB, &bar_full[s], n0 + 32 * j, kb * TC_BK);
+            if (p.has_blo) tc_tma_2d(st + 3 * TC_TILE_BYTES + j * 4096, &mapBlo, &bar_full[s], n0 + 32 * j, kb * TC_BK);
+          }
         }
       }
     }
@@ -152,104 +158,128 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     // instruction descriptor: D f32 | A,B tf32 | majors | N >> 3 | M >> 4   (cute::UMMA::InstrDescriptor)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)AMAJ << 15) | ((uint32_t)BMAJ << 16) |
                            ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    for (int it = 0; it < nloc; ++it) {
-      const int s = it % TC_STAGES;
-      tc_mbar_wait(&bar_full[s], (it / TC_STAGES) & 1);
+    int it = 0, j = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
+      const int z = t / (nt_n * nt_m);
+      const int kb0 = z * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
+      const int buf = j & 1;
+      tc_mbar_wait(&bar_acc_empty[buf], ((j >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator set
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t st = smem0 + s * TC_STAGE_BYTES;
+      const uint32_t d_main = tmem + (uint32_t)buf * (2 * TC_BN), d_corr = d_main + TC_BN;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % TC_STAGES;
+        tc_mbar_wait(&bar_full[s], (it / TC_STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = smem0 + s * TC_STAGE_BYTES;
 #pragma unroll
-      for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
-        const uint64_t a = tc_operand_desc<AMAJ>(st, k8), b = tc_operand_desc<BMAJ>(st + 2 * TC_TILE_BYTES, k8);
-        const int step = it * (TC_BK / 8) + k8;
-        tc_mma(tmem + (uint32_t)(step % TC_NACC) * TC_BN, a, b, idesc, step >= TC_NACC ? 1u : 0u);
-        if (p.has_alo) tc_mma(tmem + TC_NACC * TC_BN, tc_operand_desc<AMAJ>(st + TC_TILE_BYTES, k8), b, idesc, step ? 1u : 0u);
-        if (p.has_blo) tc_mma(tmem + TC_NACC * TC_BN, a, tc_operand_desc<BMAJ>(st + 3 * TC_TILE_BYTES, k8), idesc, (step || p.has_alo) ? 1u : 0u);
+        for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+          const uint64_t a = tc_operand_desc<AMAJ>(st, k8), b = tc_operand_desc<BMAJ>(st + 2 * TC_TILE_BYTES, k8);
+          const uint32_t first = (kb == kb0 && k8 == 0) ? 0u : 1u;
+          tc_mma(d_main, a, b, idesc, first);
+          if (p.has_alo) tc_mma(d_corr, tc_operand_desc<AMAJ>(st + TC_TILE_BYTES, k8), b, idesc, first);
+          if (p.has_blo) tc_mma(d_corr, a, tc_operand_desc<BMAJ>(st + 3 * TC_TILE_BYTES, k8), idesc, (first || p.has_alo) ? 1u : 0u);
+        }
+        tc_commit(&bar_empty[s]);  // frees the stage once these MMAs have read it
       }
-      tc_commit(&bar_empty[s]);  // frees the stage once these MMAs have read it
+      tc_commit(&bar_acc_full[buf]);  // accumulator set complete
     }
-    tc_commit(&bar_acc);  // accumulator complete
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue: TMEM -> registers -> global
+    // ------------------------------------------------------------ epilogue: TMEM -> registers -> smem -> global
     const int q = warp & 3;
-    if (nloc > 0) {
-      tc_mbar_wait(&bar_acc, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
     const bool partial = p.splits > 1;
     const int n4 = (p.N + 3) & ~3;
-    float* const out = partial ? p.ws + (size_t)blockIdx.z * p.M * n4 : p.C;
-    float* const out_lo = (!partial && p.C_lo) ? p.C_lo : nullptr;
     const int ldo = partial ? n4 : p.ldc;
     const int epi = partial ? EPI_STORE : p.epi;
     const bool has_bias = epi >= EPI_BIAS && epi <= EPI_BIAS_ELU, has_src = epi == EPI_DRELU || epi == EPI_DELU;
     const bool accum = !partial && p.accumulate;
-    // The pipeline stages are idle once the accumulator barrier has fired: each epilogue warp stages its 32x32 chunk there
-    // (row stride 36 floats) so that every global access below is a coalesced 128-byte row segment.
-    float* const stg = reinterpret_cast<float*>(tc_smem_raw + (smem0 - tc_smem_u32(tc_smem_raw))) + q * (32 * 36);
-    const int nsteps = nloc * (TC_BK / 8);
-    const bool has_corr = nsteps > 0 && (p.has_alo || p.has_blo);
-    const int nacc = (nsteps < TC_NACC ? nsteps : TC_NACC) + (has_corr ? 1 : 0);
+    const bool has_corr = p.has_alo || p.has_blo;
+    // each epilogue warp stages its 32x32 chunk (row stride 36 floats) behind the pipeline stages so that every global
+    // access below is a coalesced 128-byte row segment
+    float* const stg = reinterpret_cast<float*>(tc_smem_raw + (smem0 - tc_smem_u32(tc_smem_raw)) + TC_STAGES * TC_STAGE_BYTES) + q * (32 * 36);
+    int j = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
+      const int n0 = (t % nt_n) * TC_BN, m0 = ((t / nt_n) % nt_m) * TC_BM, z = t / (nt_n * nt_m);
+      const int buf = j & 1;
+      float* const out = partial ? p.ws + (size_t)z * p.M * n4 : p.C;
+      float* const out_lo = (!partial && p.C_lo) ? p.C_lo : nullptr;
+      tc_mbar_wait(&bar_acc_full[buf], (j >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      int nchunks = (p.N - n0 + 31) / 32;
+      nchunks = nchunks > TC_BN / 32 ? TC_BN / 32 : nchunks;
 #pragma unroll 1
-    for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-      if (n0 + c0 >= p.N) break;  // warp-uniform
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = 0.f;
-#pragma unroll 1
-      for (int a = 0; a < nacc; ++a) {
-        // main accumulators first, the correction accumulator (column block TC_NACC) last
-        const int blk = (a == nacc - 1 && has_corr) ? TC_NACC : a;
-        uint32_t u[32];
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * TC_BN + c0);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
-            "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
-              "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
-              "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
-              "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(u[j]);
-      }
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4)
-        *reinterpret_cast<float4*>(stg + lane * 36 + j4 * 4) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-      __syncwarp();
-      const int c4 = (lane & 7) * 4, gn = n0 + c0 + c4;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = (lane >> 3) + 4 * i, gm = m0 + q * 32 + r;
-        if (gm >= p.M || gn >= p.N) continue;
-        const float4 acc4 = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
-        float x[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
-        float* orow = out + (size_t)gm * ldo + gn;
-        if (gn + 3 < p.N) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = b4;
-          if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn));
-          if (has_src) s4 = __ldg(reinterpret_cast<const float4*>(p.act_src + (size_t)gm * p.ld_act + gn));
-          x[0] = tc_epi(x[0], epi, b4.x, s4.x); x[1] = tc_epi(x[1], epi, b4.y, s4.y);
-          x[2] = tc_epi(x[2], epi, b4.z, s4.z); x[3] = tc_epi(x[3], epi, b4.w, s4.w);
-          if (accum) {
-            const float4 o4 = *reinterpret_cast<const float4*>(orow);
-            x[0] += o4.x; x[1] += o4.y; x[2] += o4.z; x[3] += o4.w;
+      for (int ch = 0; ch < TC_BN / 32; ++ch) {
+        const int c0 = ch * 32;
+        float v[32];
+        if (ch < nchunks) {
+          uint32_t u[32], w[32];
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * TC_BN + c0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+              "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+                "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
+                "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
+                "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+              : "r"(taddr));
+          if (has_corr) {
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+                "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]), "=r"(w[9]),
+                  "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]), "=r"(w[16]), "=r"(w[17]), "=r"(w[18]),
+                  "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]), "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]),
+                  "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
+                : "r"(taddr + TC_BN));
           }
-          *reinterpret_cast<float4*>(orow) = make_float4(x[0], x[1], x[2], x[3]);
-          if (out_lo)
-            *reinterpret_cast<float4*>(out_lo + (size_t)gm * ldo + gn) = make_float4(tf32_lo(x[0]), tf32_lo(x[1]), tf32_lo(x[2]), tf32_lo(x[3]));
-        } else {
-          for (int j = 0; j < 4 && gn + j < p.N; ++j) {
-            const float bias = has_bias ? __ldg(p.bias + gn + j) : 0.f;
-            const float src = has_src ? __ldg(p.act_src + (size_t)gm * p.ld_act + gn + j) : 0.f;
-            float y = tc_epi(x[j], epi, bias, src);
-            if (accum) y += orow[j];
-            orow[j] = y;
-            if (out_lo) out_lo[(size_t)gm * ldo + gn + j] = tf32_lo(y);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = has_corr ? __uint_as_float(u[i]) + __uint_as_float(w[i]) : __uint_as_float(u[i]);
+        }
+        if (ch == nchunks - 1) {
+          // all TMEM reads of this tile are done: hand the accumulator set back to the MMA issuer
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&bar_acc_empty[buf])) : "memory");
+        }
+        if (ch >= nchunks) continue;  // warp-uniform
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          *reinterpret_cast<float4*>(stg + lane * 36 + j4 * 4) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+        __syncwarp();
+        const int c4 = (lane & 7) * 4, gn = n0 + c0 + c4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = (lane >> 3) + 4 * i, gm = m0 + q * 32 + r;
+          if (gm >= p.M || gn >= p.N) continue;
+          const float4 acc4 = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
+          float x[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
+          float* orow = out + (size_t)gm * ldo + gn;
+          if (gn + 3 < p.N) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = b4;
+            if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn));
+            if (has_src) s4 = __ldg(reinterpret_cast<const float4*>(p.act_src + (size_t)gm * p.ld_act + gn));
+            x[0] = tc_epi(x[0], epi, b4.x, s4.x); x[1] = tc_epi(x[1], epi, b4.y, s4.y);
+            x[2] = tc_epi(x[2], epi, b4.z, s4.z); x[3] = tc_epi(x[3], epi, b4.w, s4.w);
+            if (accum) {
+              const float4 o4 = *reinterpret_cast<const float4*>(orow);
+              x[0] += o4.x; x[1] += o4.y; x[2] += o4.z; x[3] += o4.w;
+            }
+            *reinterpret_cast<float4*>(orow) = make_float4(x[0], x[1], x[2], x[3]);
+            if (out_lo)
+              *reinterpret_cast<float4*>(out_lo + (size_t)gm * ldo + gn) = make_float4(tf32_lo(x[0]), tf32_lo(x[1]), tf32_lo(x[2]), tf32_lo(x[3]));
+          } else {
+            for (int jj = 0; jj < 4 && gn + jj < p.N; ++jj) {
+              const float bias = has_bias ? __ldg(p.bias + gn + jj) : 0.f;
+              const float src = has_src ? __ldg(p.act_src + (size_t)gm * p.ld_act + gn + jj) : 0.f;
+              float y = tc_epi(x[jj], epi, bias, src);
+              if (accum) y += orow[jj];
+              orow[jj] = y;
+              if (out_lo) out_lo[(size_t)gm * ldo + gn + jj] = tf32_lo(y);
+            }
           }
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -345,7 +375,10 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   RETURN_IF_ERR(tc_get_map(a.B, a.N, a.K, a.ldb, bmaj, &mB));
   if (a.A_lo) RETURN_IF_ERR(tc_get_map(a.A_lo, a.M, a.K, a.lda, amaj, &mAlo)); else mAlo = mA;
   if (a.B_lo) RETURN_IF_ERR(tc_get_map(a.B_lo, a.N, a.K, a.ldb, bmaj, &mBlo)); else mBlo = mB;
-  dim3 grid(ceil_div(a.N, TC_BN), ceil_div(a.M, TC_BM), splits);
+  static int num_sms = 0;
+  if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+  const int ntiles = ceil_div(a.N, TC_BN) * ceil_div(a.M, TC_BM) * splits;
+  dim3 grid(ntiles < num_sms ? ntiles : num_sms);
   dtc_prof_begin(st, 0, 2.0 * a.M * a.N * a.K);
   int rc;
   if (amaj == 0 && bmaj == 0) rc = tc_launch_t<0, 0>(mA, mAlo, mB, mBlo, p, grid, st);

