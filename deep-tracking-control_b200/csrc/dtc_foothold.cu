@@ -546,6 +546,413 @@ k_foothold_v4(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, float* 
   }
 }
 
+// ================================================================== variant 5: persistent warps, single-tap min3 map
+// The scan is issue-bound (ncu: v4 spends 6.8 k warp instructions per environment, DRAM < 1 % busy), so v5 removes work:
+//   * min3 map: the heightmap is constant, so m[x][y] = min(H[x][y], H[x+1][y], H[x][y+1]) is tabulated once at bind time
+//     (dtc_env owns it) and every height sample is ONE tap instead of three;
+//   * persistent warps: a warp walks environments n, n + W, ... and keeps its 22 grid points' coordinates in registers; the
+//     NEXT environment's 44 x 56-cell patch (one cp.async.bulk.tensor.2d issued by one lane) is in flight while the current
+//     one is scored (two mbarriers per warp);
+//   * cells: q = (p + border) / h is affine in the grid coordinates; it is evaluated with two FMAs around the robot's own
+//     cell (computed once per environment in fp64) and converted with the 1.5*2^23 trick; only samples within 4e-4 cells of a
+//     cell boundary (where the reference's own fp32 rounding decides) are redone on the exact op-by-op path (~0.15 %);
+//   * the LS plane-fit operator rows are (to 1e-7) a_x * grid_x and a_y * grid_y on a symmetric grid - checked on the host,
+//     SEP = false keeps the tabulated rows in registers instead;
+//   * exception flags live in a per-lane bit mask, window arg-mins use redux.sync on (value bits, index).
+// Results are identical to variant 0 (tests/test_env_gpu.py::test_foothold_variants_agree).
+#define V5_WARPS 4
+#define V5_PW 56   // patch row pitch in cells
+#define V5_PH 42   // max patch rows
+#define V5_NK 22   // ceil(693 / 32) samples per lane
+
+#define V5_PATCH_ELEMS ((V5_PH * V5_PW + 63) / 64 * 64)
+struct __align__(128) V5Smem {
+  int16_t patch[2][V5_PATCH_ELEMS];
+  float gc[NP + 3];
+  float4 tx[GXN];  // gx, d0 = -(yz*t1), bx = yw*t1
+  float4 ty[GYN];  // gy, ay = yw*t0, d1 = yz*t0
+  uint64_t mbar[2];
+};
+
+struct V5Params {
+  double r0, r1;        // sums of the plane-fit operator rows (the shift by the first sample is added back through them)
+  float ax, ay;         // SEP: plane_op[0][p] = ax * grid_x[ix], plane_op[1][p] = ay * grid_y[iy]
+  float ext_x, ext_y;   // half extents of the sampling grid
+};
+
+struct V5Env {
+  float root_x, root_y, root_z, yz, yw;
+  float qx0, qy0;  // fractional cell position of the robot minus 0.5
+  uint32_t kbase;  // byte offset constant: (cell - patch origin - magic-number bits) folded for both axes (mod 2^32)
+  int fast;        // 1: patch staged and every sample is interior
+};
+
+__device__ __noinline__ float v5_exact_sample(const int16_t* __restrict__ min3, int rows, int cols, float gx, float gy, float yz, float yw,
+                                              float root_x, float root_y, float border, float hscale, float vscale) {
+  float rx, ry;
+  yaw_apply_exact(yz, yw, gx, gy, rx, ry);
+  const float wx = __fadd_rn(__fadd_rn(rx, root_x), border), wy = __fadd_rn(__fadd_rn(ry, root_y), border);
+  int px = (int)__fdiv_rn(wx, hscale), py = (int)__fdiv_rn(wy, hscale);  // .long(): truncation toward zero
+  px = min(max(px, 0), rows - 2);
+  py = min(max(py, 0), cols - 2);
+  return __fmul_rn((float)__ldg(min3 + (size_t)px * cols + py), vscale);
+}
+
+// loads environment n, stages its patch into `patch` and returns the per-environment constants.  The patch is the bounding box of
+// the rotated sampling grid: one cp.async.bulk per map row (16-byte aligned column origin), issued by lane 0 from uniform registers.
+// (A single cp.async.bulk.tensor.2d over an int16 / no-swizzle tensor map raised "illegal instruction" on this device for every
+// box shape tried - gpurun_out probe of round 1 - so the rows are copied individually.)
+__device__ __forceinline__ V5Env v5_prepare(const dtc_env_config* __restrict__ cfg, const dtc_env_buffers& b, const int16_t* __restrict__ min3,
+                                            int n, int lane, int16_t* patch, uint64_t* mbar, const V5Params& P) {
+  V5Env e;
+  const float* rs = b.root_states + (size_t)n * 13;
+  e.root_x = rs[0]; e.root_y = rs[1]; e.root_z = rs[2];
+  yaw_quat_exact(rs[5], rs[6], e.yz, e.yw);
+  const int rows = cfg->map_rows, cols = cfg->map_cols;
+  const double inv_h = 1.0 / (double)cfg->horizontal_scale;
+  const double cxd = ((double)e.root_x + (double)cfg->border_size) * inv_h, cyd = ((double)e.root_y + (double)cfg->border_size) * inv_h;
+  const double fx = floor(cxd), fy = floor(cyd);
+  const int cx = (int)fx, cy = (int)fy;
+  e.qx0 = (float)(cxd - fx - 0.5);
+  e.qy0 = (float)(cyd - fy - 0.5);
+  // bounding box of the rotated grid in cells, one cell of slack on every side
+  const float c = fabsf(1.0f - 2.0f * e.yz * e.yz), s = fabsf(2.0f * e.yz * e.yw);
+  const int cex = (int)ceilf((P.ext_x * c + P.ext_y * s) * (float)inv_h), cey = (int)ceilf((P.ext_x * s + P.ext_y * c) * (float)inv_h);
+  const int x0 = cx - cex - 1, nrows = 2 * cex + 3;
+  const int y0 = (cy - cey - 1) & ~7, ncols = (cy + cey + 1 - y0 + 8) & ~7;
+  // the 4e-4-cell margin of the fast path holds for coordinates below 128 m
+  e.fast = (cx - cex >= 0 && cx + cex <= rows - 2 && cy - cey >= 0 && cy + cey <= cols - 2 && x0 >= 0 && x0 + nrows <= rows && y0 >= 0 &&
+            y0 + ncols <= cols && nrows <= V5_PH && ncols <= V5_PW && fabsf(e.root_x) + cfg->border_size < 120.0f &&
+            fabsf(e.root_y) + cfg->border_size < 120.0f) ? 1 : 0;
+  e.kbase = ((uint32_t)(cx - x0) - 0x4B400000u) * (uint32_t)(V5_PW * 2) + ((uint32_t)(cy - y0) - 0x4B400000u) * 2u;
+  if (e.fast && lane == 0) {
+    const uint32_t mb = smem_u32(mbar), rowb = (uint32_t)ncols * 2u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)nrows * rowb) : "memory");
+    const int16_t* src = min3 + (size_t)x0 * cols + y0;
+    uint32_t dst = smem_u32(patch);
+#pragma unroll 4
+    for (int r = 0; r < nrows; ++r, src += cols, dst += V5_PW * 2)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(rowb),
+                   "r"(mb)
+                   : "memory");
+  }
+  return e;
+}
+
+__device__ __forceinline__ void v5_argmin(unsigned vbits, int idx, int& out_idx) {
+  // lexicographic (value, index) minimum of non-negative floats: two redux.sync
+  const unsigned m = __reduce_min_sync(0xffffffffu, vbits);
+  out_idx = (int)__reduce_min_sync(0xffffffffu, vbits == m ? (unsigned)idx : 0x7fffffffu);
+}
+
+template <bool SEP>
+__global__ void __launch_bounds__(V5_WARPS * 32, SEP ? 4 : 2)
+k_foothold_v5(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const int16_t* __restrict__ min3, const V5Params P) {
+  extern __shared__ __align__(128) uint8_t v5_smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  V5Smem& S = reinterpret_cast<V5Smem*>(v5_smem_raw)[warp];
+  const int N = cfg->num_envs;
+  const int stride = gridDim.x * V5_WARPS;
+  int n = blockIdx.x * V5_WARPS + warp;
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.mbar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.mbar[1])));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  if (n >= N) return;
+
+  const int rows = cfg->map_rows, cols = cfg->map_cols;
+  const float border = cfg->border_size, hscale = cfg->horizontal_scale, vscale = cfg->vertical_scale;
+  const float inv_h = 1.0f / hscale;
+  // ---- per-lane constants of the 22 samples p = 32 k + lane
+  float gxk[V5_NK], gyk[V5_NK], p0k[SEP ? 1 : V5_NK], p1k[SEP ? 1 : V5_NK];
+#pragma unroll
+  for (int k = 0; k < V5_NK; ++k) {
+    const int p = min(32 * k + lane, NP - 1);
+    const int ix = p / GYN, iy = p - ix * GYN;
+    gxk[k] = cfg->grid_x[ix];
+    gyk[k] = cfg->grid_y[iy];
+    if (!SEP) { p0k[k] = cfg->plane_op[p]; p1k[k] = cfg->plane_op[NP + p]; }
+  }
+  // window slots of the per-leg 7x7 search
+  int wi_k[2], wj_k[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) { const int slot = lane + 32 * k; wi_k[k] = slot / 7 - 3; wj_k[k] = slot - (slot / 7) * 7 - 3; }
+
+  int buf = 0;
+  uint32_t phase0 = 0u, phase1 = 0u;
+  V5Env E = v5_prepare(cfg, b, min3, n, lane, S.patch[0], &S.mbar[0], P);
+  for (; n < N; n += stride) {
+    const int nn = n + stride;
+    V5Env En = E;
+    // gc / tables / the other patch buffer were last read by this warp's previous iteration
+    __syncwarp();
+    if (nn < N) En = v5_prepare(cfg, b, min3, nn, lane, S.patch[buf ^ 1], &S.mbar[buf ^ 1], P);
+    const float root_x = E.root_x, root_y = E.root_y, root_z = E.root_z, yz = E.yz, yw = E.yw;
+    // ---- rotation tables (exact per-op values of yaw_apply_exact)
+    for (int i = lane; i < GXN + GYN; i += 32) {
+      if (i < GXN) {
+        const float gx = cfg->grid_x[i];
+        const float t1 = __fmul_rn(__fmul_rn(yz, gx), 2.0f);
+        S.tx[i] = make_float4(gx, -__fmul_rn(yz, t1), __fmul_rn(yw, t1), 0.f);
+      } else {
+        const float gy = cfg->grid_y[i - GXN];
+        const float t0 = __fmul_rn(-__fmul_rn(yz, gy), 2.0f);
+        S.ty[i - GXN] = make_float4(gy, __fmul_rn(yw, t0), __fmul_rn(yz, t0), 0.f);
+      }
+    }
+    const float ca = (1.0f - 2.0f * yz * yz) * inv_h, sa = (2.0f * yz * yw) * inv_h;
+
+    // ---------------------------------------------------------------- phase 1a: 693 single-tap samples
+    float mhk[V5_NK];
+    unsigned slowm = 0u;
+    if (E.fast) {
+      const uint32_t mb = smem_u32(&S.mbar[buf]);
+      const uint32_t ph = buf ? phase1 : phase0;
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(mb), "r"(ph) : "memory");
+      if (buf) phase1 ^= 1u; else phase0 ^= 1u;
+      const char* patch_b = reinterpret_cast<const char*>(S.patch[buf]);
+#pragma unroll
+      for (int k = 0; k < V5_NK; ++k) {
+        const float qx = fmaf(gxk[k], ca, fmaf(gyk[k], -sa, E.qx0));
+        const float qy = fmaf(gxk[k], sa, fmaf(gyk[k], ca, E.qy0));
+        const float tx = qx + 12582912.0f, ty = qy + 12582912.0f;
+        const float rx = qx - (tx - 12582912.0f), ry = qy - (ty - 12582912.0f);
+        if (fmaxf(fabsf(rx), fabsf(ry)) > 0.5f - 4.0e-4f) slowm |= 1u << k;
+        const uint32_t off = __float_as_uint(tx) * (uint32_t)(V5_PW * 2) + __float_as_uint(ty) * 2u + E.kbase;
+        mhk[k] = __fmul_rn((float)*reinterpret_cast<const int16_t*>(patch_b + off), vscale);
+      }
+    } else {
+      slowm = 0xffffffffu;
+#pragma unroll
+      for (int k = 0; k < V5_NK; ++k) mhk[k] = 0.f;
+    }
+    if (__any_sync(0xffffffffu, slowm != 0u)) {  // samples next to a cell boundary (or a robot at the map border): exact path
+#pragma unroll
+      for (int k = 0; k < V5_NK; ++k)
+        if ((slowm >> k) & 1u) mhk[k] = v5_exact_sample(min3, rows, cols, gxk[k], gyk[k], yz, yw, root_x, root_y, border, hscale, vscale);
+    }
+
+    // ---------------------------------------------------------------- phase 1b: stores, moments, plane fit
+    float* mh_out = b.measured_heights + (size_t)n * NP;
+    const float mh0 = __shfl_sync(0xffffffffu, mhk[0], 0);
+    const float c0 = fminf(fmaxf(__fsub_rn(mh0, root_z), -0.5f), 0.5f);
+    float s1 = 0.f, s2 = 0.f, cs = 0.f, pa = 0.f, pb = 0.f;
+    unsigned excm = 0u;
+#pragma unroll
+    for (int k = 0; k < V5_NK; ++k) {
+      const bool live = (k < V5_NK - 1) || (lane < NP - 32 * (V5_NK - 1));
+      if (live) {
+        const int p = 32 * k + lane;
+        const float mh = mhk[k];
+        mh_out[p] = mh;
+        const float graw = __fsub_rn(mh, root_z);
+        const float gc = fminf(fmaxf(graw, -0.5f), 0.5f);
+        S.gc[p] = gc;
+        if (fabsf(graw) > 1.0f) excm |= 1u << k;
+        const float d = gc - c0;
+        s1 += d;
+        s2 = fmaf(d, d, s2);
+        if (32 * k + 31 >= 10 * GYN && 32 * k < (GXN - 10) * GYN)
+          if (p >= 10 * GYN && p < (GXN - 10) * GYN) cs += __fsub_rn(root_z, fmaxf(mh, 0.f));
+        const float dm = mh - mh0;
+        pa = fmaf(SEP ? gxk[k] : p0k[k], dm, pa);
+        pb = fmaf(SEP ? gyk[k] : p1k[k], dm, pb);
+      }
+    }
+    const double S1 = warp_sum((double)s1), S2 = warp_sum((double)s2), CS = warp_sum((double)cs);
+    const double PA = warp_sum((double)pa) * (SEP ? (double)P.ax : 1.0) + (double)mh0 * P.r0;
+    const double PB = warp_sum((double)pb) * (SEP ? (double)P.ay : 1.0) + (double)mh0 * P.r1;
+    const double mean_d = (double)c0 + S1 / (double)NP;
+    double var_d = (S2 - S1 * S1 / (double)NP) / (double)(NP - 1);
+    var_d = var_d < 0.0 ? 0.0 : var_d;
+    const float mean = (float)mean_d;
+    const float edge = fminf(fmaxf(__fsqrt_rn((float)var_d), 0.0f), 0.3f);
+    if (lane == 0) {
+      b.center_clear_mean[n] = (float)(CS / (double)((GXN - 20) * GYN));
+      b.plane_ab[n * 2] = (float)PA;
+      b.plane_ab[n * 2 + 1] = (float)PB;
+    }
+    __syncwarp();
+
+    // ---------------------------------------------------------------- terrain score of one grid point (branch-free)
+    const float e02 = __fmul_rn(0.2f, edge);
+    const float inv_sp = __frcp_rn(0.05f);
+    const float* gcw = S.gc;
+    auto score = [&](int p, int ix, int iy) {  // s in [0, 0.1) or 10 (legged_robot_dtc.py:134-148)
+      const int pxm = ix > 0 ? p - GYN : p, pxp = ix < GXN - 1 ? p + GYN : p;
+      const int pym = iy > 0 ? p - 1 : p, pyp = iy < GYN - 1 ? p + 1 : p;
+      const float g = gcw[p];
+      float dx = div_by_const_rn(__fsub_rn(gcw[pxp], gcw[pxm]), 0.05f, inv_sp);
+      float dy = div_by_const_rn(__fsub_rn(gcw[pyp], gcw[pym]), 0.05f, inv_sp);
+      if (ix > 0 && ix < GXN - 1) dx = __fmul_rn(dx, 0.5f);
+      if (iy > 0 && iy < GYN - 1) dy = __fmul_rn(dy, 0.5f);
+      const float slope = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+      const float rough = fabsf(__fsub_rn(g, mean));
+      const float s = __fadd_rn(__fadd_rn(e02, slope), __fmul_rn(0.3f, rough));
+      return s < 0.1f ? s : 10.0f;
+    };
+
+    // ---------------------------------------------------------------- phase 3: Raibert nominal footholds (lane l = leg l)
+    float pfx = 0.f, pfy = 0.f, pfz = 0.f;
+    int ci = 0, cj = 0;
+    {
+      const int l = lane & 3;
+      const float cmd_x = b.commands[n * 4 + 0], cmd_y = b.commands[n * 4 + 1], cmd_yaw = b.commands[n * 4 + 2];
+      const float vx = b.base_lin_vel[n * 3 + 0], vy = b.base_lin_vel[n * 3 + 1], vz = b.base_lin_vel[n * 3 + 2];
+      const float cth = cosf(cmd_yaw), sth = sinf(cmd_yaw);
+      const float cpsi = 1.0f - 2.0f * yz * yz, spsi = 2.0f * yz * yw;
+      const float sym_x = __fadd_rn(__fmul_rn(0.01f, vx), __fmul_rn(0.03f, __fsub_rn(vx, cmd_x)));
+      const float sym_y = __fadd_rn(__fmul_rn(0.01f, vy), __fmul_rn(0.03f, __fsub_rn(vy, cmd_y)));
+      const float sym_z = __fadd_rn(__fmul_rn(0.01f, vz), __fmul_rn(0.03f, vz));
+      const float* th = b.rigid_body_state + (size_t)n * 17 * 13 + (2 + 4 * l) * 13;  // thigh bodies 2,6,10,14 (legged_robot_dtc.py:100)
+      const float hx = __fsub_rn(th[0], root_x), hy = __fsub_rn(th[1], root_y), hz = __fsub_rn(th[2], root_z);
+      const float rxh = __fadd_rn(__fmul_rn(cth, hx), __fmul_rn(-sth, hy));
+      const float ryh = __fadd_rn(__fmul_rn(sth, hx), __fmul_rn(cth, hy));
+      pfx = __fadd_rn(__fadd_rn(root_x, rxh), sym_x);
+      pfy = __fadd_rn(__fadd_rn(root_y, ryh), sym_y);
+      pfz = __fadd_rn(__fadd_rn(root_z, hz), sym_z);
+      const float relx = pfx - root_x, rely = pfy - root_y;
+      const float lxf = cpsi * relx + spsi * rely, lyf = -spsi * relx + cpsi * rely;
+      ci = (int)floorf((lxf + 0.8f) * 20.0f + 0.5f);
+      cj = (int)floorf((lyf + 0.5f) * 20.0f + 0.5f);
+    }
+    int my_idx = 0x7fffffff, my_nom = 0x7fffffff;  // results of leg `lane` (lanes 0..3)
+    bool need_fallback = false;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float lpfx = __shfl_sync(0xffffffffu, pfx, l), lpfy = __shfl_sync(0xffffffffu, pfy, l);
+      const int lci = __shfl_sync(0xffffffffu, ci, l), lcj = __shfl_sync(0xffffffffu, cj, l);
+      unsigned bs = 0x7f7fffffu, bd = 0x7f7fffffu;  // value bits; FLT_MAX = nothing found
+      int bsi = 0x7fffffff, bdi = 0x7fffffff;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int i = lci + wi_k[k], j = lcj + wj_k[k];
+        const bool valid = (k == 0 || lane < 49 - 32) && i >= 0 && i < GXN && j >= 0 && j < GYN;
+        const int ic = min(max(i, 0), GXN - 1), jc = min(max(j, 0), GYN - 1);
+        const int p = ic * GYN + jc;
+        const float4 a = S.tx[ic], c = S.ty[jc];
+        const float wx = __fadd_rn(__fadd_rn(__fadd_rn(a.x, c.y), a.y), root_x);
+        const float wy = __fadd_rn(__fadd_rn(__fadd_rn(c.x, a.z), c.z), root_y);
+        const float ddx = __fsub_rn(lpfx, wx), ddy = __fsub_rn(lpfy, wy);
+        const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
+        const unsigned em = __shfl_sync(0xffffffffu, excm, p & 31);
+        const bool in_r = valid && d < 0.16f;
+        const bool adm = in_r && !((em >> (p >> 5)) & 1u);
+        const float v = __fadd_rn(__fmul_rn(score(p, ic, jc), 0.2f), __fmul_rn(d, 0.8f));
+        const unsigned db = __float_as_uint(d), vb = __float_as_uint(v);
+        if (in_r && (db < bd || (db == bd && p < bdi))) { bd = db; bdi = p; }
+        if (adm && (vb < bs || (vb == bs && p < bsi))) { bs = vb; bsi = p; }
+      }
+      int ri, rn;
+      v5_argmin(bs, bsi, ri);
+      v5_argmin(bd, bdi, rn);
+      if (lane == l) { my_idx = ri; my_nom = rn; }
+      need_fallback |= (ri == 0x7fffffff);
+    }
+    int fbi = 0;
+    if (need_fallback) {  // warp-uniform: argmin_p (exc ? 10 : 0.2 s_p + 8), lowest index on ties
+      const float c8 = __fmul_rn(10.0f, 0.8f);
+      float fbv = 3.0e38f;
+      fbi = 0x7fffffff;
+#pragma unroll 1
+      for (int k = 0; k < V5_NK; ++k) {
+        const int p = 32 * k + lane;
+        if (p < NP) {
+          const int ix = p / GYN, iy = p - ix * GYN;
+          const float v = ((excm >> k) & 1u) ? 10.0f : __fadd_rn(__fmul_rn(score(p, ix, iy), 0.2f), c8);
+          if (v < fbv) { fbv = v; fbi = p; }
+        }
+      }
+      warp_argmin(fbv, fbi);
+    }
+    if (lane < 4) {
+      const int l = lane;
+      const int idx = my_idx != 0x7fffffff ? my_idx : fbi, nom = my_nom != 0x7fffffff ? my_nom : 0;
+      const int xi = idx % GYN, yi = idx / GYN;  // reference quirk: x list indexed by idx%21, y list by (idx//21)%21
+      const float4 a = S.tx[yi], c = S.ty[xi];
+      b.optimal_idx[n * 4 + l] = idx;
+      b.nominal_idx[n * 4 + l] = nom;
+      b.foothold_obs[n * 8 + l] = S.tx[xi].x;
+      b.foothold_obs[n * 8 + 4 + l] = S.ty[yi % GYN].x;
+      float* pf = b.pred_footholds + (size_t)n * 12 + l * 3;
+      pf[0] = pfx; pf[1] = pfy; pf[2] = pfz;
+      float* ow = b.optimal_footholds_world + (size_t)n * 12 + l * 3;
+      ow[0] = __fadd_rn(__fadd_rn(__fadd_rn(a.x, c.y), a.y), root_x);
+      ow[1] = __fadd_rn(__fadd_rn(__fadd_rn(c.x, a.z), c.z), root_y);
+      ow[2] = mh_out[idx];
+    }
+    E = En;
+    buf ^= 1;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_min3_map(const int16_t* __restrict__ H, int16_t* __restrict__ out, int rows, int cols) {
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t e = blockIdx.x * 256ll + threadIdx.x; e < total; e += gridDim.x * 256ll) {
+    const int x = (int)(e / cols), y = (int)(e - (int64_t)x * cols);
+    const int x1 = min(x + 1, rows - 1), y1 = min(y + 1, cols - 1);
+    const int a = H[e], bb = H[(int64_t)x1 * cols + y], c = H[(int64_t)x * cols + y1];
+    out[e] = (int16_t)min(min(a, bb), c);
+  }
+}
+
+// (re)builds the min3 map of variant 5 from the bound heightmap; synchronous, called from dtc_env_bind
+int dtc_env_build_min3(dtc_env* e) {
+  const size_t bytes = (size_t)e->cfg.map_rows * e->cfg.map_cols * sizeof(int16_t);
+  if (e->min3 && e->min3_bytes != bytes) { cudaFree(e->min3); e->min3 = nullptr; }
+  if (!e->min3) { DTC_CUDA(cudaMalloc(&e->min3, bytes)); e->min3_bytes = bytes; }
+  k_min3_map<<<148 * 4, 256>>>(e->buf.height_samples, e->min3, e->cfg.map_rows, e->cfg.map_cols);
+  DTC_CHECK_LAUNCH("k_min3_map");
+  DTC_CUDA(cudaDeviceSynchronize());
+  return DTC_OK;
+}
+
+// plane-fit operator rows as a_x * grid_x / a_y * grid_y (least squares in fp64) and whether that reproduces the table
+static V5Params v5_params(const dtc_env_config& c, bool* separable) {
+  V5Params P;
+  double r0 = 0, r1 = 0, nx = 0, dxx = 0, ny = 0, dyy = 0, mx = 0;
+  for (int p = 0; p < NP; ++p) {
+    const double gx = c.grid_x[p / GYN], gy = c.grid_y[p % GYN], a = c.plane_op[p], bb = c.plane_op[NP + p];
+    r0 += a; r1 += bb;
+    nx += a * gx; dxx += gx * gx; ny += bb * gy; dyy += gy * gy;
+    mx = fmax(mx, fmax(fabs(a), fabs(bb)));
+  }
+  const double ax = dxx > 0 ? nx / dxx : 0, ay = dyy > 0 ? ny / dyy : 0;
+  double res = 0;
+  for (int p = 0; p < NP; ++p) {
+    res = fmax(res, fabs(c.plane_op[p] - ax * c.grid_x[p / GYN]));
+    res = fmax(res, fabs(c.plane_op[NP + p] - ay * c.grid_y[p % GYN]));
+  }
+  *separable = mx > 0 && res <= 2e-6 * mx;
+  P.r0 = r0; P.r1 = r1; P.ax = (float)ax; P.ay = (float)ay;
+  P.ext_x = fmaxf(fabsf(c.grid_x[0]), fabsf(c.grid_x[GXN - 1]));
+  P.ext_y = fmaxf(fabsf(c.grid_y[0]), fabsf(c.grid_y[GYN - 1]));
+  return P;
+}
+
+template <bool SEP>
+static int launch_v5(dtc_env* e, const V5Params& P, cudaStream_t st) {
+  static int ctas_per_sm = 0, sms = 0;
+  const int smem = V5_WARPS * (int)sizeof(V5Smem);
+  if (!ctas_per_sm) {
+    int dev = 0;
+    DTC_CUDA(cudaGetDevice(&dev));
+    DTC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DTC_CUDA(cudaFuncSetAttribute(k_foothold_v5<SEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DTC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_foothold_v5<SEP>, V5_WARPS * 32, smem));
+    if (ctas_per_sm < 1) DTC_FAIL(DTC_ERR_CUDA, "k_foothold_v5 does not fit on this device");
+  }
+  const int N = e->cfg.num_envs;
+  const int ctas = min(ceil_div(N, V5_WARPS), sms * ctas_per_sm);
+  k_foothold_v5<SEP><<<ctas, V5_WARPS * 32, smem, st>>>(e->d_cfg, e->buf, e->min3, P);
+  return DTC_OK;
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -575,7 +982,7 @@ extern "C" int dtc_foothold_step(dtc_env* e, int variant, float* debug_score, vo
   cudaStream_t st = (cudaStream_t)stream;
   int N = e->cfg.num_envs;
   dim3 grid(ceil_div(N, FH_WARPS)), block(FH_WARPS * 32);
-  if (variant >= 1 && variant <= 4 && (e->cfg.map_cols * 2) % 16 != 0)
+  if (variant >= 1 && variant <= 5 && (e->cfg.map_cols * 2) % 16 != 0)
     DTC_FAIL(DTC_ERR_ARG, "TMA variants need 16-byte aligned heightmap rows");
   dtc_prof_begin(st, 1, 0.0);
   if (variant == 1 || variant == 2) {
@@ -586,7 +993,12 @@ extern "C" int dtc_foothold_step(dtc_env* e, int variant, float* debug_score, vo
     k_foothold<3><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score, e->tmap, e->d_tmap);
   } else if (variant == 4) {
     k_foothold_v4<<<ceil_div(N, V4_WARPS), V4_WARPS * 32, 0, st>>>(e->d_cfg, e->buf, debug_score);
-  } else if (variant == 0) {
+  } else if (variant == 5 && !debug_score) {
+    if (!e->min3) DTC_FAIL(DTC_ERR_STATE, "dtc_foothold_step: min3 map missing (dtc_env_bind builds it)");
+    bool sep = false;
+    const V5Params P = v5_params(e->cfg, &sep);
+    RETURN_IF_ERR(sep ? launch_v5<true>(e, P, st) : launch_v5<false>(e, P, st));
+  } else if (variant == 0 || variant == 5) {  // the brute-force debug dump of variant 5 is variant 0's
     k_foothold<0><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score, e->tmap, e->d_tmap);
   } else {
     DTC_FAIL(DTC_ERR_ARG, "dtc_foothold_step: unknown variant %d", variant);

@@ -233,11 +233,39 @@ __global__ void k_splitk_reduce(const float* __restrict__ ws, float* __restrict_
       }
   }
 }
+// same sum for small outputs (the 12..128-wide layers: a few hundred float4s, up to 128 partials each): one warp per float4, lanes
+// stride over the partials, so the reduction is latency-parallel instead of one serial chain per thread
+__global__ void __launch_bounds__(256) k_splitk_reduce_warp(const float* __restrict__ ws, float* __restrict__ C, float* __restrict__ C_lo,
+                                                            int M, int N, int ldc, int splits, int accumulate) {
+  const int n4 = (N + 3) & ~3, q = n4 >> 2;
+  const int64_t total = (int64_t)M * q;
+  const int lane = threadIdx.x & 31;
+  for (int64_t e = blockIdx.x * 8ll + (threadIdx.x >> 5); e < total; e += (int64_t)gridDim.x * 8) {
+    const int m = (int)(e / q), c = (int)(e - (int64_t)m * q) * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = lane; z < splits; z += 32) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(ws + ((size_t)z * M + m) * n4 + c));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    s.x = warp_sum(s.x); s.y = warp_sum(s.y); s.z = warp_sum(s.z); s.w = warp_sum(s.w);
+    if (lane < 4 && c + lane < N) {
+      const float v = lane == 0 ? s.x : lane == 1 ? s.y : lane == 2 ? s.z : s.w;
+      float* dst = C + (size_t)m * ldc + c + lane;
+      const float o = accumulate ? *dst + v : v;
+      *dst = o;
+      if (C_lo) C_lo[(size_t)m * ldc + c + lane] = tf32_lo(o);
+    }
+  }
+}
 void k_splitk_reduce_launch(const float* ws, float* C, float* C_lo, int M, int N, int ldc, int splits, int accumulate, cudaStream_t st) {
   int64_t total = (int64_t)M * ((N + 3) / 4);
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  k_splitk_reduce<<<blocks, 256, 0, st>>>(ws, C, C_lo, M, N, ldc, splits, accumulate);
+  if (total <= 148 * 8 * 8 && splits >= 8) {
+    k_splitk_reduce_warp<<<(int)((total + 7) / 8), 256, 0, st>>>(ws, C, C_lo, M, N, ldc, splits, accumulate);
+  } else {
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_splitk_reduce<<<blocks, 256, 0, st>>>(ws, C, C_lo, M, N, ldc, splits, accumulate);
+  }
   g_dtc_launches++;
 }
 

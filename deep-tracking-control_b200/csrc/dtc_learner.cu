@@ -38,6 +38,7 @@ struct Layer { const char* name; int out, in, in_ref, ld; int64_t w, b; };
 #define LD_ML 36     // ml = [mu 19 | logvar 16 | 1 zero]
 #define ML_LV 19
 #define NPIGGY 4
+#define DTC_NEV 32
 
 static Layer g_layers[NLAYERS];
 static std::vector<dtc_param_info> g_params;
@@ -183,6 +184,11 @@ struct dtc_learner {
   struct { const float* base; size_t n; const float* lo; } ext[3];
   int64_t vae_steps, main_steps;
   int last_M;
+  // intra-step concurrency: two non-blocking side streams forked from / joined into the caller's stream inside one call
+  bool side_ready;
+  cudaStream_t side[2];
+  cudaEvent_t ev[DTC_NEV];
+  int ev_next;
 };
 
 static const float* lo_of(const dtc_learner* l, const float* p) {
@@ -253,12 +259,60 @@ extern "C" int dtc_learner_create(int32_t max_rows, float* params, float* grads,
   l->csws = (float*)p;
   l->vae_steps = l->main_steps = 0;
   l->last_M = 0;
+  l->side_ready = false;
+  l->ev_next = 0;
   DTC_CUDA(cudaMemset(l->stats, 0, ST_COUNT * sizeof(double)));
   DTC_CUDA(cudaMemset(l->ws_val_begin, 0, 2 * ws_value_bytes(R)));
   *out = l;
   return dtc_learner_refresh_params(l, nullptr);
 }
-extern "C" void dtc_learner_destroy(dtc_learner* l) { delete l; }
+extern "C" void dtc_learner_destroy(dtc_learner* l) {
+  if (!l) return;
+  if (l->side_ready) {
+    for (int i = 0; i < 2; ++i) cudaStreamDestroy(l->side[i]);
+    for (int i = 0; i < DTC_NEV; ++i) cudaEventDestroy(l->ev[i]);
+  }
+  delete l;
+}
+
+// ------------------------------------------------------------------ intra-step concurrency
+// One optimizer step is ~100 launches on three independent chains: the CENet encoder/decoder (GEMMs 12..128 wide, a
+// handful of CTAs each), the weight gradients (a split-K GEMM + reduce + column sum per layer, needed only by the
+// optimizer), and the 512-wide activation-gradient chain that is the critical path.  The step forks the first two onto side
+// streams (events, no host synchronisation) so that they run in the shadow of the big tensor-core GEMMs and fill the tails of
+// their persistent grids; everything is joined back into the caller's stream before the call returns.
+static int g_overlap = 1;
+extern "C" void dtc_set_overlap(int on) { g_overlap = on ? 1 : 0; }
+extern "C" int dtc_get_overlap(void) { return g_overlap; }
+
+struct StepStreams { cudaStream_t main, w, c; };  // w: weight gradients + critic forward; c: CENet chains + critic backward
+
+// work queued on `to` after this call waits for everything queued on `from` so far
+static int chain(dtc_learner* l, cudaStream_t from, cudaStream_t to) {
+  if (from == to) return DTC_OK;
+  cudaEvent_t e = l->ev[l->ev_next];
+  l->ev_next = (l->ev_next + 1) % DTC_NEV;
+  DTC_CUDA(cudaEventRecord(e, from));
+  DTC_CUDA(cudaStreamWaitEvent(to, e, 0));
+  return DTC_OK;
+}
+static int streams_begin(dtc_learner* l, cudaStream_t st, StepStreams* S) {
+  S->main = S->w = S->c = st;
+  if (!g_overlap || g_dtc_prof) return DTC_OK;  // per-launch profiling wants every kernel alone on the device
+  if (!l->side_ready) {
+    for (int i = 0; i < 2; ++i) DTC_CUDA(cudaStreamCreateWithFlags(&l->side[i], cudaStreamNonBlocking));
+    for (int i = 0; i < DTC_NEV; ++i) DTC_CUDA(cudaEventCreateWithFlags(&l->ev[i], cudaEventDisableTiming));
+    l->side_ready = true;
+  }
+  S->w = l->side[0];
+  S->c = l->side[1];
+  RETURN_IF_ERR(chain(l, st, S->w));
+  return chain(l, st, S->c);
+}
+static int streams_end(dtc_learner* l, const StepStreams& S) {
+  RETURN_IF_ERR(chain(l, S.w, S.main));
+  return chain(l, S.c, S.main);
+}
 
 __global__ void __launch_bounds__(256) k_split_lo(const float* __restrict__ x, float* __restrict__ lo, int64_t n) {
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) lo[i] = tf32_lo(x[i]);
@@ -939,49 +993,57 @@ static int grid1d(long long n, int threads, int cap = 148 * 8) {
   return b < 1 ? 1 : (int)b;
 }
 
-// cenet encoder + latent heads + outlier statistics + terrain encoder + latent kernel; X receives l_t | z | mu[:3]
+// cenet encoder + latent heads + outlier statistics (stream c) | terrain encoder (main) -> latent kernel; X receives l_t | z | mu[:3]
 static int encode(dtc_learner* l, int M, const float* hist, const float* priv_a, const float* xc, int mode, const float* eps,
-                  uint64_t seed, uint64_t counter, cudaStream_t st) {
+                  uint64_t seed, uint64_t counter, const StepStreams& S) {
   float* X = mode == 0 ? l->XA : l->XD;
   const int ldx = mode == 0 ? LD_XA : LD_XD;
-  RET_IF(fwd(l, CE0, hist, LD_HIST, l->H1, 128, 1, M, st));
-  RET_IF(fwd(l, CE2, l->H1, 128, l->E, 64, 0, M, st));
-  RET_IF(fwd(l, LAT, l->E, 64, l->ML, LD_ML, 0, M, st));
-  DTC_CUDA(cudaMemsetAsync(l->lvstat, 0, sizeof(LvStat), st));
+  cudaStream_t st = S.main, sc = S.c;
+  RET_IF(fwd(l, CE0, hist, LD_HIST, l->H1, 128, 1, M, sc));
+  RET_IF(fwd(l, CE2, l->H1, 128, l->E, 64, 0, M, sc));
+  RET_IF(fwd(l, LAT, l->E, 64, l->ML, LD_ML, 0, M, sc));
+  DTC_CUDA(cudaMemsetAsync(l->lvstat, 0, sizeof(LvStat), sc));
   const int gb = grid1d((long long)M * 16, 256, 148 * 2);
-  k_lv_moments<<<gb, 256, 0, st>>>(l->ML, M, l->lvstat); DTC_CHECK_LAUNCH("k_lv_moments");
-  k_lv_hist<1><<<gb, 256, 0, st>>>(l->ML, M, l->lvstat); DTC_CHECK_LAUNCH("k_lv_hist1");
-  k_lv_hist<2><<<gb, 256, 0, st>>>(l->ML, M, l->lvstat); DTC_CHECK_LAUNCH("k_lv_hist2");
-  k_lv_hist<3><<<gb, 256, 0, st>>>(l->ML, M, l->lvstat); DTC_CHECK_LAUNCH("k_lv_hist3");
-  k_lv_final<<<1, 256, 0, st>>>(M, l->lvstat); DTC_CHECK_LAUNCH("k_lv_final");
+  k_lv_moments<<<gb, 256, 0, sc>>>(l->ML, M, l->lvstat); DTC_CHECK_LAUNCH("k_lv_moments");
+  k_lv_hist<1><<<gb, 256, 0, sc>>>(l->ML, M, l->lvstat); DTC_CHECK_LAUNCH("k_lv_hist1");
+  k_lv_hist<2><<<gb, 256, 0, sc>>>(l->ML, M, l->lvstat); DTC_CHECK_LAUNCH("k_lv_hist2");
+  k_lv_hist<3><<<gb, 256, 0, sc>>>(l->ML, M, l->lvstat); DTC_CHECK_LAUNCH("k_lv_hist3");
+  k_lv_final<<<1, 256, 0, sc>>>(M, l->lvstat); DTC_CHECK_LAUNCH("k_lv_final");
   RET_IF(fwd(l, TE0, priv_a, LD_PRIVA, l->T1, 512, 1, M, st));
   RET_IF(fwd(l, TE2, l->T1, 512, l->T2, 512, 1, M, st));
   RET_IF(fwd(l, TE4, l->T2, 512, X, ldx, 0, M, st));
+  RET_IF(chain(l, sc, st));
   k_latent_fwd<<<ceil_div(M, 8), 128, 0, st>>>(M, mode, l->ML, l->lvstat, eps, seed, counter, l->EPS, l->OUTM, xc, X);
   DTC_CHECK_LAUNCH("k_latent_fwd");
   return split_lo(X, lo_of(l, X), (int64_t)M * ldx, st);  // z / mu / obs columns were written outside a GEMM epilogue
 }
 
-// backward of encode(): dX holds d l_t | d z | d mu[:3] (layout of X); fills the gradients of CE0, CE2, LAT, TE0..TE4
-static int encode_bwd(dtc_learner* l, int M, const float* hist, const float* priv_a, int mode, int has_direct, cudaStream_t st) {
+// backward of encode(): dX holds d l_t | d z | d mu[:3] (layout of X); fills the gradients of CE0, CE2, LAT, TE0..TE4.
+// Everything dX / dML depend on must already be ordered before S.main.
+static int encode_bwd(dtc_learner* l, int M, const float* hist, const float* priv_a, int mode, int has_direct, const StepStreams& S) {
   const int ldx = mode == 0 ? LD_XA : LD_XD;
+  cudaStream_t st = S.main, sw = S.w, sc = S.c;
   k_latent_bwd<<<ceil_div(M, 8), 128, 0, st>>>(M, mode, has_direct, l->ML, l->EPS, l->OUTM, l->dX, l->dML, l->lvstat);
   DTC_CHECK_LAUNCH("k_latent_bwd");
   k_lv_median_grad<<<grid1d((long long)M * 16, 256, 148 * 2), 256, 0, st>>>(M, l->ML, l->OUTM, l->dML, l->lvstat);
   DTC_CHECK_LAUNCH("k_lv_median_grad");
   RET_IF(split_lo(l->dML, lo_of(l, l->dML), (int64_t)M * LD_ML, st));
-  RET_IF(wgrad(l, LAT, l->dML, LD_ML, l->E, 64, M, st));
-  RET_IF(dgrad(l, LAT, l->dML, LD_ML, l->dE, 64, 64, nullptr, 0, EPI_STORE, false, M, st));
-  RET_IF(wgrad(l, CE2, l->dE, 64, l->H1, 128, M, st));
-  RET_IF(dgrad(l, CE2, l->dE, 64, l->dH1, 128, 128, l->H1, 128, EPI_DRELU, false, M, st));
-  RET_IF(wgrad(l, CE0, l->dH1, 128, hist, LD_HIST, M, st));
-  const float* X = mode == 0 ? l->XA : l->XD;
-  (void)X;
-  RET_IF(wgrad(l, TE4, l->dX, ldx, l->T2, 512, M, st));
+  RET_IF(chain(l, st, sw));
+  RET_IF(chain(l, st, sc));
+  RET_IF(wgrad(l, TE4, l->dX, ldx, l->T2, 512, M, sw));
+  RET_IF(wgrad(l, LAT, l->dML, LD_ML, l->E, 64, M, sw));
+  RET_IF(dgrad(l, LAT, l->dML, LD_ML, l->dE, 64, 64, nullptr, 0, EPI_STORE, false, M, sc));
+  RET_IF(chain(l, sc, sw));
+  RET_IF(wgrad(l, CE2, l->dE, 64, l->H1, 128, M, sw));
   RET_IF(dgrad(l, TE4, l->dX, ldx, l->dT2, 512, 512, l->T2, 512, EPI_DRELU, false, M, st));
-  RET_IF(wgrad(l, TE2, l->dT2, 512, l->T1, 512, M, st));
+  RET_IF(chain(l, st, sw));
+  RET_IF(wgrad(l, TE2, l->dT2, 512, l->T1, 512, M, sw));
+  RET_IF(dgrad(l, CE2, l->dE, 64, l->dH1, 128, 128, l->H1, 128, EPI_DRELU, false, M, sc));
+  RET_IF(chain(l, sc, sw));
+  RET_IF(wgrad(l, CE0, l->dH1, 128, hist, LD_HIST, M, sw));
   RET_IF(dgrad(l, TE2, l->dT2, 512, l->dT1, 512, 512, l->T1, 512, EPI_DRELU, false, M, st));
-  RET_IF(wgrad(l, TE0, l->dT1, 512, priv_a, LD_PRIVA, M, st));
+  RET_IF(chain(l, st, sw));
+  RET_IF(wgrad(l, TE0, l->dT1, 512, priv_a, LD_PRIVA, M, sw));
   return DTC_OK;
 }
 
@@ -1038,9 +1100,12 @@ extern "C" int dtc_policy_act(dtc_learner* l, int32_t M, const float* obs, int32
   RET_IF(split_lo(xh, lo_of(l, xh), (int64_t)M * LD_HIST, st));
   RET_IF(split_lo(xp, lo_of(l, xp), (int64_t)M * LD_PRIVA, st));
   RET_IF(split_lo(xc, lo_of(l, xc), (int64_t)M * LD_XC, st));
-  RET_IF(encode(l, M, xh, xp, xc, 0, eps_z, seed, counter * 2, st));
+  StepStreams S;
+  RET_IF(streams_begin(l, st, &S));
+  RET_IF(critic_fwd(l, M, xc, S.w));
+  RET_IF(encode(l, M, xh, xp, xc, 0, eps_z, seed, counter * 2, S));
   RET_IF(actor_fwd(l, M, st));
-  RET_IF(critic_fwd(l, M, xc, st));
+  RET_IF(streams_end(l, S));
   k_act_head<<<ceil_div(M, 128), 128, 0, st>>>(M, l->MEAN, l->V, l->params + g_off_std, eps_a, seed, counter * 2 + 1, o_act, o_val,
                                               o_logp, o_mu, o_sig, actions, values, logp, mean, sigma);
   DTC_CHECK_LAUNCH("k_act_head");
@@ -1212,36 +1277,48 @@ extern "C" int dtc_vae_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
   l->ext[1] = {priv_a, (size_t)M * LD_PRIVA, batch->priv_a_lo ? batch->priv_a_lo + row0 * LD_PRIVA : nullptr};
   l->ext[2] = {xc, (size_t)M * LD_XC, batch->xc_lo ? batch->xc_lo + row0 * LD_XC : nullptr};
   const float inv_rows = 1.0f / (float)M;
-  // forward (ppo.py:197-223)
-  RET_IF(encode(l, M, hist, priv_a, xc, 1, eps, seed, counter, st));
-  RET_IF(fwd(l, CD0, l->XD, LD_XD, l->D1, 64, 1, M, st));
-  RET_IF(fwd(l, CD2, l->D1, 64, l->D2, 128, 1, M, st));
-  RET_IF(fwd(l, CD4, l->D2, 128, l->REC, 56, 0, M, st));
+  StepStreams S;
+  RET_IF(streams_begin(l, st, &S));
+  cudaStream_t sw = S.w, sc = S.c;
+  // forward (ppo.py:197-223): CENet decoder on stream c, terrain decoder on the caller's stream
+  RET_IF(encode(l, M, hist, priv_a, xc, 1, eps, seed, counter, S));
+  RET_IF(chain(l, st, sc));
+  RET_IF(fwd(l, CD0, l->XD, LD_XD, l->D1, 64, 1, M, sc));
+  RET_IF(fwd(l, CD2, l->D1, 64, l->D2, 128, 1, M, sc));
+  RET_IF(fwd(l, CD4, l->D2, 128, l->REC, 56, 0, M, sc));
   RET_IF(fwd(l, TD0, l->XD, LD_XD, l->U1, 512, 1, M, st));
   RET_IF(fwd(l, TD2, l->U1, 512, l->U2, 512, 1, M, st));
   RET_IF(fwd(l, TD4, l->U2, 512, l->HR, 696, 0, M, st));
   // losses and output gradients (ppo.py:213-247)
-  k_vae_loss_rows<<<ceil_div(M, 128), 128, 0, st>>>(M, inv_rows, l->REC, next_obs, l->ML, xc, l->dREC, l->dML, l->stats);
+  k_vae_loss_rows<<<ceil_div(M, 128), 128, 0, sc>>>(M, inv_rows, l->REC, next_obs, l->ML, xc, l->dREC, l->dML, l->stats);
   DTC_CHECK_LAUNCH("k_vae_loss_rows");
+  RET_IF(split_lo(l->dREC, lo_of(l, l->dREC), (int64_t)M * 56, sc));
   k_vae_loss_height<<<grid1d((long long)M * 696, 256), 256, 0, st>>>(M, 1.0f / ((float)M * 693.0f), l->HR, xc, l->dHR, l->stats);
   DTC_CHECK_LAUNCH("k_vae_loss_height");
-  RET_IF(split_lo(l->dREC, lo_of(l, l->dREC), (int64_t)M * 56, st));
   RET_IF(split_lo(l->dHR, lo_of(l, l->dHR), (int64_t)M * 696, st));
-  // backward: cenet decoder
-  RET_IF(wgrad(l, CD4, l->dREC, 56, l->D2, 128, M, st));
-  RET_IF(dgrad(l, CD4, l->dREC, 56, l->dD2, 128, 128, l->D2, 128, EPI_DRELU, false, M, st));
-  RET_IF(wgrad(l, CD2, l->dD2, 128, l->D1, 64, M, st));
-  RET_IF(dgrad(l, CD2, l->dD2, 128, l->dD1, 64, 64, l->D1, 64, EPI_DRELU, false, M, st));
-  RET_IF(wgrad(l, CD0, l->dD1, 64, l->XD, LD_XD, M, st));
-  RET_IF(dgrad(l, CD0, l->dD1, 64, l->dX, LD_XD, LD_XD, nullptr, 0, EPI_STORE, false, M, st));
-  // backward: terrain decoder, fan-in into d l_t
-  RET_IF(wgrad(l, TD4, l->dHR, 696, l->U2, 512, M, st));
+  // backward: cenet decoder (stream c), terrain decoder (caller's stream), weight gradients (stream w)
+  RET_IF(chain(l, sc, sw));
+  RET_IF(wgrad(l, CD4, l->dREC, 56, l->D2, 128, M, sw));
+  RET_IF(chain(l, st, sw));
+  RET_IF(wgrad(l, TD4, l->dHR, 696, l->U2, 512, M, sw));
+  RET_IF(dgrad(l, CD4, l->dREC, 56, l->dD2, 128, 128, l->D2, 128, EPI_DRELU, false, M, sc));
+  RET_IF(chain(l, sc, sw));
+  RET_IF(wgrad(l, CD2, l->dD2, 128, l->D1, 64, M, sw));
   RET_IF(dgrad(l, TD4, l->dHR, 696, l->dU2, 512, 512, l->U2, 512, EPI_DRELU, false, M, st));
-  RET_IF(wgrad(l, TD2, l->dU2, 512, l->U1, 512, M, st));
+  RET_IF(chain(l, st, sw));
+  RET_IF(wgrad(l, TD2, l->dU2, 512, l->U1, 512, M, sw));
+  RET_IF(dgrad(l, CD2, l->dD2, 128, l->dD1, 64, 64, l->D1, 64, EPI_DRELU, false, M, sc));
+  RET_IF(chain(l, sc, sw));
+  RET_IF(wgrad(l, CD0, l->dD1, 64, l->XD, LD_XD, M, sw));
   RET_IF(dgrad(l, TD2, l->dU2, 512, l->dU1, 512, 512, l->U1, 512, EPI_DRELU, false, M, st));
-  RET_IF(wgrad(l, TD0, l->dU1, 512, l->XD, LD_XD, M, st));
+  RET_IF(chain(l, st, sw));
+  RET_IF(wgrad(l, TD0, l->dU1, 512, l->XD, LD_XD, M, sw));
+  RET_IF(dgrad(l, CD0, l->dD1, 64, l->dX, LD_XD, LD_XD, nullptr, 0, EPI_STORE, false, M, sc));
+  // fan-in into d l_t: the terrain decoder's input gradient accumulates onto the CENet decoder's (dML comes from stream c too)
+  RET_IF(chain(l, sc, st));
   RET_IF(dgrad(l, TD0, l->dU1, 512, l->dX, LD_XD, 512, nullptr, 0, EPI_STORE, true, M, st));
-  RET_IF(encode_bwd(l, M, hist, priv_a, 1, 1, st));
+  RET_IF(encode_bwd(l, M, hist, priv_a, 1, 1, S));
+  RET_IF(streams_end(l, S));
   if (sync_grads) return DTC_OK;
   return optimizer_apply(l, 0, hp, 1.0f, M, st);
 }
@@ -1259,10 +1336,14 @@ extern "C" int dtc_ppo_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
   l->ext[1] = {priv_a, (size_t)M * LD_PRIVA, batch->priv_a_lo ? batch->priv_a_lo + row0 * LD_PRIVA : nullptr};
   l->ext[2] = {xc, (size_t)M * LD_XC, batch->xc_lo ? batch->xc_lo + row0 * LD_XC : nullptr};
   const float inv_rows = 1.0f / (float)M;
-  // forward (ppo.py:265-292)
-  RET_IF(encode(l, M, hist, priv_a, xc, 0, eps, seed, counter, st));
+  StepStreams S;
+  RET_IF(streams_begin(l, st, &S));
+  cudaStream_t sw = S.w, sc = S.c;
+  // forward (ppo.py:265-292): the critic does not depend on the encoders and runs on stream w
+  RET_IF(critic_fwd(l, M, xc, sw));
+  RET_IF(encode(l, M, hist, priv_a, xc, 0, eps, seed, counter, S));
   RET_IF(actor_fwd(l, M, st));
-  RET_IF(critic_fwd(l, M, xc, st));
+  RET_IF(chain(l, sw, st));
   DTC_CUDA(cudaMemsetAsync(l->grads + g_off_std, 0, (12 + NPIGGY) * sizeof(float), st));
   k_ppo_loss<<<ceil_div(M, 128), 128, 0, st>>>(M, inv_rows, l->MEAN, l->V, l->params + g_off_std, batch->actions + row0 * 12,
                                               batch->values + row0, batch->advantages + row0, batch->returns + row0,
@@ -1273,24 +1354,32 @@ extern "C" int dtc_ppo_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
   DTC_CHECK_LAUNCH("k_publish_kl");
   RET_IF(split_lo(l->dMEAN, lo_of(l, l->dMEAN), (int64_t)M * 12, st));
   RET_IF(split_lo(l->dV, lo_of(l, l->dV), (int64_t)M * 4, st));
-  // backward: actor
-  RET_IF(wgrad(l, AB6, l->dMEAN, 12, l->A3, 128, M, st));
+  // backward: actor chain on the caller's stream, critic chain on stream c, weight gradients on stream w
+  RET_IF(chain(l, st, sw));
+  RET_IF(chain(l, st, sc));
+  RET_IF(wgrad(l, AB6, l->dMEAN, 12, l->A3, 128, M, sw));
+  RET_IF(wgrad(l, CB6, l->dV, 4, l->C3, 128, M, sw));
   RET_IF(dgrad(l, AB6, l->dMEAN, 12, l->dA3, 128, 128, l->A3, 128, EPI_DELU, false, M, st));
-  RET_IF(wgrad(l, AB4, l->dA3, 128, l->A2, 256, M, st));
+  RET_IF(chain(l, st, sw));
+  RET_IF(wgrad(l, AB4, l->dA3, 128, l->A2, 256, M, sw));
+  RET_IF(dgrad(l, CB6, l->dV, 4, l->dC3, 128, 128, l->C3, 128, EPI_DELU, false, M, sc));
+  RET_IF(chain(l, sc, sw));
+  RET_IF(wgrad(l, CB4, l->dC3, 128, l->C2, 256, M, sw));
   RET_IF(dgrad(l, AB4, l->dA3, 128, l->dA2, 256, 256, l->A2, 256, EPI_DELU, false, M, st));
-  RET_IF(wgrad(l, AB2, l->dA2, 256, l->A1, 512, M, st));
+  RET_IF(chain(l, st, sw));
+  RET_IF(wgrad(l, AB2, l->dA2, 256, l->A1, 512, M, sw));
+  RET_IF(dgrad(l, CB4, l->dC3, 128, l->dC2, 256, 256, l->C2, 256, EPI_DELU, false, M, sc));
+  RET_IF(chain(l, sc, sw));
+  RET_IF(wgrad(l, CB2, l->dC2, 256, l->C1, 512, M, sw));
   RET_IF(dgrad(l, AB2, l->dA2, 256, l->dA1, 512, 512, l->A1, 512, EPI_DELU, false, M, st));
-  RET_IF(wgrad(l, AB0, l->dA1, 512, l->XA, LD_XA, M, st));
+  RET_IF(chain(l, st, sw));
+  RET_IF(wgrad(l, AB0, l->dA1, 512, l->XA, LD_XA, M, sw));
+  RET_IF(dgrad(l, CB2, l->dC2, 256, l->dC1, 512, 512, l->C1, 512, EPI_DELU, false, M, sc));
+  RET_IF(chain(l, sc, sw));
+  RET_IF(wgrad(l, CB0, l->dC1, 512, xc, LD_XC, M, sw));
   RET_IF(dgrad(l, AB0, l->dA1, 512, l->dX, LD_XA, LD_XA, nullptr, 0, EPI_STORE, false, M, st));
-  // backward: critic
-  RET_IF(wgrad(l, CB6, l->dV, 4, l->C3, 128, M, st));
-  RET_IF(dgrad(l, CB6, l->dV, 4, l->dC3, 128, 128, l->C3, 128, EPI_DELU, false, M, st));
-  RET_IF(wgrad(l, CB4, l->dC3, 128, l->C2, 256, M, st));
-  RET_IF(dgrad(l, CB4, l->dC3, 128, l->dC2, 256, 256, l->C2, 256, EPI_DELU, false, M, st));
-  RET_IF(wgrad(l, CB2, l->dC2, 256, l->C1, 512, M, st));
-  RET_IF(dgrad(l, CB2, l->dC2, 256, l->dC1, 512, 512, l->C1, 512, EPI_DELU, false, M, st));
-  RET_IF(wgrad(l, CB0, l->dC1, 512, xc, LD_XC, M, st));
-  RET_IF(encode_bwd(l, M, hist, priv_a, 0, 0, st));
+  RET_IF(encode_bwd(l, M, hist, priv_a, 0, 0, S));
+  RET_IF(streams_end(l, S));
   if (sync_grads) return DTC_OK;
   return optimizer_apply(l, 1, hp, 1.0f, M, st);
 }

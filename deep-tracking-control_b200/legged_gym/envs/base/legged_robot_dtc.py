@@ -26,7 +26,7 @@ class _Scales:
 
 class LeggedRobotDTC:
     def __init__(self, cfg, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True, *, gym,
-                 height_samples, terrain_origins, layout, seed=0, foothold_variant=4, robot_mass=12.0):
+                 height_samples, terrain_origins, layout, seed=0, foothold_variant=5, robot_mass=12.0):
         self.cfg = cfg
         self.device = torch.device(sim_device)
         if self.device.type != "cuda":

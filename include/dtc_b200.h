@@ -134,7 +134,12 @@ typedef struct {
 typedef struct dtc_env dtc_env;
 int dtc_env_create(const dtc_env_config* cfg, dtc_env** out);
 void dtc_env_destroy(dtc_env* e);
+/* binds the caller's buffers; also tabulates the foothold kernel's single-tap min3 map from buf->height_samples
+ * (library-owned, synchronous: the heightmap must already hold the terrain, as after LeggedRobot._create_heightfield,
+ * legged_robot.py:1201-1228) */
 int dtc_env_bind(dtc_env* e, const dtc_env_buffers* buf);
+/* call after writing height_samples in place (the reference never does after start-up) */
+int dtc_env_heightmap_updated(dtc_env* e);
 
 /* E1+E2: clip actions, 4x PD torque with the lag buffer (legged_robot.py:92-111,595-630).
  * lag_choice[4]: the host draws np.random.randint(1,5) per sub-step like the reference (:608). */
@@ -146,7 +151,8 @@ int dtc_env_state_prep(dtc_env* e, int64_t common_step_counter, uint64_t seed, c
 
 /* E5 + E7..E10: height sampling, Raibert footholds, terrain score, argmin, decode
  * (legged_robot.py:1279-1317; legged_robot_dtc.py:100-201).  THE foothold-scoring kernel.
- * variant 0 = L2 gathers, 1 = TMA-staged heightmap patch. debug_score may be NULL or [N,693,4]. */
+ * variant 0 = L2 gathers, 1..3 = TMA-staged patch (tensor box / descriptor in global / bulk rows), 4 = lazy window
+ * scoring, 5 = persistent warps + min3 map + prefetched tight patch (default).  debug_score may be NULL or [N,693,4]. */
 int dtc_foothold_step(dtc_env* e, int variant, float* debug_score, void* stream);
 
 /* E4(rest), E6, E11, E12, E13: push, foot clearance, contact filter, termination, 23 rewards, reset
@@ -271,6 +277,11 @@ int dtc_gemm_debug(int32_t M, int32_t N, int32_t K, const float* A, const float*
 /* GEMM engine of the learner: 0 = FP32 SIMT, 1 = tcgen05 3xTF32 for tile-worthy shapes (default; env DTC_GEMM=simt|tc) */
 void dtc_set_gemm_mode(int mode);
 int dtc_get_gemm_mode(void);
+/* Intra-step concurrency of dtc_policy_act / dtc_vae_step / dtc_ppo_step (default on): the CENet chains and the weight
+ * gradients are forked onto two library-owned non-blocking streams with events and joined back into the caller's stream
+ * before the call returns; results are identical either way.  Off while dtc_profile_enable(1) is active. */
+void dtc_set_overlap(int on);
+int dtc_get_overlap(void);
 
 #ifdef __cplusplus
 }

@@ -71,7 +71,9 @@ def _compare_step(o, c, tag, sel=None):
 
 
 @pytest.mark.parametrize("N,kind,variant", [(64, "stones", 0), (64, "flat", 4), (256, "curriculum", 3), (4096, "stones", 4),
-                                            (1000, "stones", 3), (256, "curriculum", 4), (1000, "stones", 4), (64, "stones", 4)])
+                                            (1000, "stones", 3), (256, "curriculum", 4), (1000, "stones", 4), (64, "stones", 4),
+                                            (64, "stones", 5), (256, "curriculum", 5), (4096, "stones", 5), (64, "flat", 5),
+                                            (1000, "curriculum", 5)])
 def test_env_step_parity(N, kind, variant):
     from oracle import env_oracle as EO
     oenv, cenv, fg_cpu, fg_gpu = H.make_pair(N, kind, seed=3)
@@ -104,7 +106,7 @@ def test_env_step_parity(N, kind, variant):
         _compare_step(oenv, cenv, f"N{N} {kind} v{variant} step{t} ", sel)
 
 
-@pytest.mark.parametrize("variant", [0, 4])
+@pytest.mark.parametrize("variant", [0, 4, 5])
 def test_debug_score_matches_bruteforce(variant):
     """The windowed argmin equals the reference's brute-force 693x4 scan: dump the full score tensor from the kernel
     and check argmin(score) == optimal_idx, plus the tensor itself against the oracle."""
@@ -125,6 +127,54 @@ def test_debug_score_matches_bruteforce(variant):
     _close(score, sel["score"], "score tensor", rtol=1e-5, atol=4e-6)
     frac_fallback = float((score.min(dim=1)[0] >= 8).float().mean())
     assert 0.0 < frac_fallback < 0.5  # the tie / fall-back path is exercised (SURVEY: ~8 % of pairs)
+
+
+@pytest.mark.parametrize("N,kind", [(16384, "stones"), (8192, "curriculum")])
+def test_foothold_variants_agree(N, kind):
+    """Every output of the default kernel (variant 5: min3 map, fast cell arithmetic with the exact path near cell boundaries,
+    persistent warps with a prefetched patch) against the brute-force variant 0 at BASELINE.json's microbench size, including
+    robots at / outside the map border and robots whose whole window is exception points.  Heights, Raibert footholds and
+    nominal indices must be bit-identical."""
+    import ctypes as C
+    from dtc_b200 import _lib as B
+    from dtc_b200.legged_gym.envs import LeggedRobotDTC, Lite3DTCCfg
+    dev = "cuda"
+    hs, tor = sim_stub.make_heightmap(kind, 0)
+    layout = sim_stub.initial_env_layout(N, tor, 1)
+    fg = sim_stub.FakeGym(N, device=dev)
+    cfg = Lite3DTCCfg()
+    cfg.env.num_envs = N
+    env = LeggedRobotDTC(cfg, sim_device=dev, gym=fg, height_samples=hs, terrain_origins=tor, layout=layout, seed=1)
+    g = torch.Generator(device=dev).manual_seed(2)
+    fg.load(sim_stub.synth_state(N, env.env_origins, g, device=dev))
+    env.reset()
+    names = ("measured_heights", "pred_footholds", "optimal_idx", "nominal_idx", "foothold_obs", "optimal_footholds_world",
+             "center_clear_mean", "plane_ab")
+    stp = B.stream_ptr()
+    for rep in range(3):
+        st = sim_stub.synth_state(N, env.env_origins, g, device=dev)
+        st["root_states"][0:8, 0:2] = torch.tensor([[-19.99, 5.0], [-25.0, 70.0], [67.9, 30.0], [10.0, -19.97], [10.0, 35.9],
+                                                     [-20.0, -20.0], [200.0, 5.0], [0.0249999, 0.05]], device=dev)
+        st["root_states"][8:40, 2] += 1.5   # all exception points -> fall-back argmin
+        fg.load(st)
+        out = {}
+        for v in (0, 5):
+            for nme in names:
+                env._keep[nme].zero_()
+            B.check(env.lib.dtc_foothold_step(env._h, v, C.c_void_p(0), stp), "foothold")
+            torch.cuda.synchronize()
+            out[v] = {nme: env._keep[nme].clone() for nme in names}
+        for nme in names:
+            a, b = out[0][nme], out[5][nme]
+            if nme in ("plane_ab", "center_clear_mean"):
+                # reductions: v0 sums in fp64, v5 in fp32 lane partials (same tolerance class as the oracle comparison)
+                assert torch.allclose(a, b, rtol=1e-5, atol=5e-6), f"{nme} rep{rep}: {(a - b).abs().max()}"
+            elif nme in ("optimal_idx", "foothold_obs", "optimal_footholds_world"):
+                # the edge term of the score depends on the variance reduction: isolated near-tie flips only
+                frac = (a != b).float().mean().item()
+                assert frac < 2e-4, f"{nme} rep{rep}: mismatch fraction {frac}"
+            else:
+                assert torch.equal(a, b), f"{nme} rep{rep}: {int((a != b).sum())} mismatches"
 
 
 def test_philox_noise_statistics():

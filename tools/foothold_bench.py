@@ -24,6 +24,14 @@ def run(N=16384, iters=50, warmup=5, variants=(0, 1)):
     g = torch.Generator(device=dev).manual_seed(2)
     fg.load(sim_stub.synth_state(N, env.env_origins, g, device=dev))
     env.reset()
+    # one full environment step on a fresh synthetic state, then restore that state: reset_idx rewrote the root states of the
+    # environments that terminated, and the kernel should see what it sees inside the training loop (root / thigh / command
+    # tensors of one consistent simulator state)
+    st0 = sim_stub.synth_state(N, env.env_origins, g, device=dev)
+    fg.queue.append(st0)
+    env.step(torch.zeros(N, 12, device=dev))
+    fg.load(st0)
+    torch.cuda.synchronize()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
         if os.path.exists("MEASURED_PEAKS.json") else 6650.0

@@ -33,7 +33,8 @@ def main():
             out[f"{tag}_fwd_{N}x{K}"] = round(2 * M * N * K / t / 1e12, 2)
             t = bench(lambda: lib.dtc_gemm_debug(M, K, N, B.ptr(dY), B.ptr(dYl), dY.shape[1], 1, B.ptr(W), B.ptr(Wl), W.shape[1], 0, B.ptr(dX), None, dX.shape[1], 1, None, mode, st))
             out[f"{tag}_dgrad_{N}x{K}"] = round(2 * M * N * K / t / 1e12, 2)
-            splits = 25 if mode == 0 else max(1, 148 // (((N + 127) // 128) * ((K + 127) // 128)))
+            tiles = ((N + 127) // 128) * ((K + 127) // 128)
+            splits = min(128, max(-(-592 // tiles), -(-M // 1024)))  # as dtc_gemm_pick_splits: >= ceil(M/32/32) for the TMEM accumulation limit
             ws = torch.empty(splits * N * r4(K), device="cuda"); dW = torch.empty(N, r4(K), device="cuda")
             t = bench(lambda: lib.dtc_gemm_debug(N, K, M, B.ptr(dY), B.ptr(dYl), dY.shape[1], 0, B.ptr(A), B.ptr(Al), A.shape[1], 0, B.ptr(dW), None, dW.shape[1], splits, B.ptr(ws), mode, st))
             out[f"{tag}_wgrad_{N}x{K}"] = round(2 * M * N * K / t / 1e12, 2)
