@@ -562,7 +562,8 @@ k_foothold_v4(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, float* 
 // Results are identical to variant 0 (tests/test_env_gpu.py::test_foothold_variants_agree).
 #define V5_WARPS 4
 #define V5_PW 56   // patch row pitch in cells
-#define V5_PH 42   // max patch rows
+#define V5_PH 42   // patch rows
+#define V5_PC 48   // patch columns copied (of the V5_PW pitch)
 #define V5_NK 22   // ceil(693 / 32) samples per lane
 
 #define V5_PATCH_ELEMS ((V5_PH * V5_PW + 63) / 64 * 64)
@@ -571,7 +572,6 @@ struct __align__(128) V5Smem {
   float gc[NP + 3];
   float4 tx[GXN];  // gx, d0 = -(yz*t1), bx = yw*t1
   float4 ty[GYN];  // gy, ay = yw*t0, d1 = yz*t0
-  uint64_t mbar[2];
 };
 
 struct V5Params {
@@ -598,12 +598,13 @@ __device__ __noinline__ float v5_exact_sample(const int16_t* __restrict__ min3, 
   return __fmul_rn((float)__ldg(min3 + (size_t)px * cols + py), vscale);
 }
 
-// loads environment n, stages its patch into `patch` and returns the per-environment constants.  The patch is the bounding box of
-// the rotated sampling grid: one cp.async.bulk per map row (16-byte aligned column origin), issued by lane 0 from uniform registers.
-// (A single cp.async.bulk.tensor.2d over an int16 / no-swizzle tensor map raised "illegal instruction" on this device for every
-// box shape tried - gpurun_out probe of round 1 - so the rows are copied individually.)
+// loads environment n, starts the copy of its patch into `patch` (one cp.async group per call) and returns the per-environment
+// constants.  The patch is a fixed 42 x 48-cell window around the bounding box of the rotated sampling grid (column origin rounded
+// down to 8 cells = 16 B); every lane moves eight 16-byte chunks with cp.async.cg (252 chunks, L2 -> shared memory, no registers).
+// Measured alternatives: one cp.async.bulk per row costs ~16 issue slots per row (uniform-register set-up), a single
+// cp.async.bulk.tensor.2d over an int16 / no-swizzle tensor map raised "illegal instruction" for every box shape tried.
 __device__ __forceinline__ V5Env v5_prepare(const dtc_env_config* __restrict__ cfg, const dtc_env_buffers& b, const int16_t* __restrict__ min3,
-                                            int n, int lane, int16_t* patch, uint64_t* mbar, const V5Params& P) {
+                                            int n, int lane, int16_t* patch, const V5Params& P) {
   V5Env e;
   const float* rs = b.root_states + (size_t)n * 13;
   e.root_x = rs[0]; e.root_y = rs[1]; e.root_z = rs[2];
@@ -618,24 +619,26 @@ __device__ __forceinline__ V5Env v5_prepare(const dtc_env_config* __restrict__ c
   // bounding box of the rotated grid in cells, one cell of slack on every side
   const float c = fabsf(1.0f - 2.0f * e.yz * e.yz), s = fabsf(2.0f * e.yz * e.yw);
   const int cex = (int)ceilf((P.ext_x * c + P.ext_y * s) * (float)inv_h), cey = (int)ceilf((P.ext_x * s + P.ext_y * c) * (float)inv_h);
-  const int x0 = cx - cex - 1, nrows = 2 * cex + 3;
-  const int y0 = (cy - cey - 1) & ~7, ncols = (cy + cey + 1 - y0 + 8) & ~7;
+  const int x0 = cx - cex - 1, y0 = (cy - cey - 1) & ~7;
   // the 4e-4-cell margin of the fast path holds for coordinates below 128 m
-  e.fast = (cx - cex >= 0 && cx + cex <= rows - 2 && cy - cey >= 0 && cy + cey <= cols - 2 && x0 >= 0 && x0 + nrows <= rows && y0 >= 0 &&
-            y0 + ncols <= cols && nrows <= V5_PH && ncols <= V5_PW && fabsf(e.root_x) + cfg->border_size < 120.0f &&
+  e.fast = (cx - cex >= 0 && cx + cex <= rows - 2 && cy - cey >= 0 && cy + cey <= cols - 2 && x0 >= 0 && x0 + V5_PH <= rows && y0 >= 0 &&
+            y0 + V5_PC <= cols && 2 * cex + 3 <= V5_PH && cy + cey + 1 - y0 < V5_PC && fabsf(e.root_x) + cfg->border_size < 120.0f &&
             fabsf(e.root_y) + cfg->border_size < 120.0f) ? 1 : 0;
   e.kbase = ((uint32_t)(cx - x0) - 0x4B400000u) * (uint32_t)(V5_PW * 2) + ((uint32_t)(cy - y0) - 0x4B400000u) * 2u;
-  if (e.fast && lane == 0) {
-    const uint32_t mb = smem_u32(mbar), rowb = (uint32_t)ncols * 2u;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)nrows * rowb) : "memory");
-    const int16_t* src = min3 + (size_t)x0 * cols + y0;
-    uint32_t dst = smem_u32(patch);
-#pragma unroll 4
-    for (int r = 0; r < nrows; ++r, src += cols, dst += V5_PW * 2)
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(rowb),
-                   "r"(mb)
-                   : "memory");
+  if (e.fast) {
+    const char* src0 = reinterpret_cast<const char*>(min3 + (size_t)x0 * cols + y0);
+    const uint32_t dst0 = smem_u32(patch);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ch = lane + 32 * i;                 // chunk id: row = ch / 6, 16-byte column chunk = ch % 6
+      const int r = (ch * 171) >> 10, q = ch - 6 * r;
+      if (ch < V5_PH * (V5_PC / 8))
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(r * (V5_PW * 2) + q * 16)),
+                     "l"(src0 + (size_t)r * (size_t)(cols * 2) + q * 16)
+                     : "memory");
+    }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
   return e;
 }
 
@@ -654,12 +657,6 @@ k_foothold_v5(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const i
   const int N = cfg->num_envs;
   const int stride = gridDim.x * V5_WARPS;
   int n = blockIdx.x * V5_WARPS + warp;
-  if (lane == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.mbar[0])));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.mbar[1])));
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncwarp();
   if (n >= N) return;
 
   const int rows = cfg->map_rows, cols = cfg->map_cols;
@@ -681,14 +678,14 @@ k_foothold_v5(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const i
   for (int k = 0; k < 2; ++k) { const int slot = lane + 32 * k; wi_k[k] = slot / 7 - 3; wj_k[k] = slot - (slot / 7) * 7 - 3; }
 
   int buf = 0;
-  uint32_t phase0 = 0u, phase1 = 0u;
-  V5Env E = v5_prepare(cfg, b, min3, n, lane, S.patch[0], &S.mbar[0], P);
+  V5Env E = v5_prepare(cfg, b, min3, n, lane, S.patch[0], P);
   for (; n < N; n += stride) {
     const int nn = n + stride;
     V5Env En = E;
     // gc / tables / the other patch buffer were last read by this warp's previous iteration
     __syncwarp();
-    if (nn < N) En = v5_prepare(cfg, b, min3, nn, lane, S.patch[buf ^ 1], &S.mbar[buf ^ 1], P);
+    if (nn < N) En = v5_prepare(cfg, b, min3, nn, lane, S.patch[buf ^ 1], P);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
     const float root_x = E.root_x, root_y = E.root_y, root_z = E.root_z, yz = E.yz, yw = E.yw;
     // ---- rotation tables (exact per-op values of yaw_apply_exact)
     for (int i = lane; i < GXN + GYN; i += 32) {
@@ -707,14 +704,9 @@ k_foothold_v5(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const i
     // ---------------------------------------------------------------- phase 1a: 693 single-tap samples
     float mhk[V5_NK];
     unsigned slowm = 0u;
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // this environment's patch (the group before the prefetch) has landed
+    __syncwarp();
     if (E.fast) {
-      const uint32_t mb = smem_u32(&S.mbar[buf]);
-      const uint32_t ph = buf ? phase1 : phase0;
-      uint32_t done = 0;
-      while (!done)
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done) : "r"(mb), "r"(ph) : "memory");
-      if (buf) phase1 ^= 1u; else phase0 ^= 1u;
       const char* patch_b = reinterpret_cast<const char*>(S.patch[buf]);
 #pragma unroll
       for (int k = 0; k < V5_NK; ++k) {
