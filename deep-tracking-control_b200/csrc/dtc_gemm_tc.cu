@@ -76,6 +76,38 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
       : "memory");
 }
+// one elected lane of a converged warp (CUTLASS elect_one_sync): unlike `lane == 0`, ptxas knows the guarded region has a single
+// active thread and issues UTMALDG / UTCHMMA / UTCBAR straight from uniform registers instead of wrapping each in an ELECT loop
+__device__ __forceinline__ bool tc_elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// descriptor halves: the low word carries the start address (and LBO), the high word is constant per operand layout, so the
+// per-k8 / per-stage descriptor update is one 32-bit add
+template <int MAJ> __device__ __forceinline__ uint32_t tc_desc_hi() {
+  return MAJ == 0 ? (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29)) : (uint32_t)((512u >> 4) | (1u << 14) | (1u << 29));
+}
+template <int MAJ> __device__ __forceinline__ uint32_t tc_desc_lo(uint32_t tile) {
+  return MAJ == 0 ? (((tile >> 4) & 0x3FFFu) | ((16u >> 4) << 16)) : (((tile >> 4) & 0x3FFFu) | ((4096u >> 4) << 16));
+}
+template <int MAJ> __device__ __forceinline__ constexpr uint32_t tc_desc_k8_step() { return MAJ == 0 ? (32u >> 4) : (1024u >> 4); }
+template <int CG>
+__device__ __forceinline__ void tc_mma_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                          uint32_t accumulate) {
+  if (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
@@ -119,7 +151,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
+   if (tc_elect_one()) {
     // ------------------------------------------------------------ TMA producer
     const uint32_t bytes = TC_TILE_BYTES * (2 + p.has_alo + p.has_blo);
     int it = 0;
@@ -153,7 +186,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+   }
+  } else if (warp == 1) {
+   if (tc_elect_one()) {
     // ------------------------------------------------------------ MMA issuer (one thread)
     // instruction descriptor: D f32 | A,B tf32 | majors | N >> 3 | M >> 4   (cute::UMMA::InstrDescriptor)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)AMAJ << 15) | ((uint32_t)BMAJ << 16) |
@@ -171,18 +206,22 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         tc_mbar_wait(&bar_full[s], (it / TC_STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = smem0 + s * TC_STAGE_BYTES;
+        const uint32_t a0 = tc_desc_lo<AMAJ>(st), al0 = tc_desc_lo<AMAJ>(st + TC_TILE_BYTES);
+        const uint32_t b0 = tc_desc_lo<BMAJ>(st + 2 * TC_TILE_BYTES), bl0 = tc_desc_lo<BMAJ>(st + 3 * TC_TILE_BYTES);
+        const uint32_t ahi = tc_desc_hi<AMAJ>(), bhi = tc_desc_hi<BMAJ>();
 #pragma unroll
         for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
-          const uint64_t a = tc_operand_desc<AMAJ>(st, k8), b = tc_operand_desc<BMAJ>(st + 2 * TC_TILE_BYTES, k8);
+          const uint32_t ka = k8 * tc_desc_k8_step<AMAJ>(), kb8 = k8 * tc_desc_k8_step<BMAJ>();
           const uint32_t first = (kb == kb0 && k8 == 0) ? 0u : 1u;
-          tc_mma(d_main, a, b, idesc, first);
-          if (p.has_alo) tc_mma(d_corr, tc_operand_desc<AMAJ>(st + TC_TILE_BYTES, k8), b, idesc, first);
-          if (p.has_blo) tc_mma(d_corr, a, tc_operand_desc<BMAJ>(st + 3 * TC_TILE_BYTES, k8), idesc, (first || p.has_alo) ? 1u : 0u);
+          tc_mma_lh<1>(d_main, a0 + ka, ahi, b0 + kb8, bhi, idesc, first);
+          if (p.has_alo) tc_mma_lh<1>(d_corr, al0 + ka, ahi, b0 + kb8, bhi, idesc, first);
+          if (p.has_blo) tc_mma_lh<1>(d_corr, a0 + ka, ahi, bl0 + kb8, bhi, idesc, (first || p.has_alo) ? 1u : 0u);
         }
         tc_commit(&bar_empty[s]);  // frees the stage once these MMAs have read it
       }
       tc_commit(&bar_acc_full[buf]);  // accumulator set complete
     }
+   }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue: TMEM -> registers -> smem -> global
     const int q = warp & 3;
@@ -287,6 +326,264 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS));
 }
 
+// ================================================================== CTA-pair variant (cta_group::2)
+// ncu on the kernel above: the tensor pipe is 57 % busy and the shared-memory pipe is the limiter - one 128x128x8 TF32 MMA
+// reads 8 KB of operands (64 wavefronts) in its 64 cycles, and the TMA writes of the four operand tiles (16 KB per k8-step of
+// three MMAs) take another 128 wavefronts, i.e. 320 wavefronts per 192 MMA cycles.  Two CTAs of one TPC working on a 256x128
+// tile halve the B traffic: each CTA stages its 128 rows of A / A_lo and HALF (64 rows) of B / B_lo, the leader's
+// tcgen05.mma.cta_group::2 (M = 256) reads each B half once for both tensor cores -> 240 wavefronts per 192 MMA cycles.
+//   * cluster (2,1,1); the pair walks (split, 256-row m-tile, n-tile) with stride gridDim.x / 2;
+//   * full[s]   lives in the leader: one arrival (its producer, expect_tx = the bytes of BOTH CTAs); the peer's TMA
+//               (cp.async.bulk.tensor...cta_group::2) completes its bytes on the leader's barrier;
+//   * empty[s], acc_full[b] live in both CTAs and are signalled by multicast tcgen05.commit from the leader;
+//   * acc_empty[b] lives in the leader: 8 arrivals (4 epilogue warps x 2 CTAs, the peer's through mapa);
+//   * each CTA drains its own 128 TMEM lanes with the same epilogue as above.
+#define TC2_STAGES 4
+#define TC2_A_BYTES TC_TILE_BYTES          // 128 rows x 32 k fp32
+#define TC2_B_BYTES (TC_TILE_BYTES / 2)    // 64 rows x 32 k fp32
+#define TC2_STAGE_BYTES (2 * TC2_A_BYTES + 2 * TC2_B_BYTES)
+#define TC2_SMEM_BYTES (TC2_STAGES * TC2_STAGE_BYTES + TC_STG_BYTES + 1024)
+
+__device__ __forceinline__ uint32_t tc_cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t tc_mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tc_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load of this CTA's tile whose bytes complete on `bar_cluster` (a shared::cluster address, possibly in the peer CTA)
+__device__ __forceinline__ void tc2_tma_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"((uint64_t)map), "r"(bar_cluster), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc2_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once all MMAs issued so far have completed) on the barrier at the same shared-memory offset in both CTAs of the pair
+__device__ __forceinline__ void tc2_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+template <int MAJ>
+__device__ __forceinline__ uint64_t tc2_b_desc(uint32_t tile, int k8) {  // 64-row B half: same atoms as tc_operand_desc, two MN blocks
+  return MAJ == 0 ? tc_desc(tile + k8 * 32, 16, 1024, 2) : tc_desc(tile + k8 * 1024, 4096, 512, 1);
+}
+
+template <int AMAJ, int BMAJ>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapB,
+           const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[TC2_STAGES], bar_empty[TC2_STAGES], bar_acc_full[2], bar_acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t smem0 = (tc_smem_u32(tc_smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc_cluster_ctarank();
+  const int nt_n = (p.N + TC_BN - 1) / TC_BN, nt_m = (p.M + 2 * TC_BM - 1) / (2 * TC_BM);
+  const int ntiles = nt_n * nt_m * p.splits;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC2_STAGES; ++s) { tc_mbar_init(&bar_full[s], 1); tc_mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc_mbar_init(&bar_acc_full[s], 1); tc_mbar_init(&bar_acc_empty[s], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_s)), "r"(TC_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  tc_cluster_sync();  // both CTAs' barriers are initialised before any remote arrival / multicast commit
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+   if (tc_elect_one()) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    const uint32_t bytes_cta = (uint32_t)(TC2_A_BYTES * (1 + p.has_alo) + TC2_B_BYTES * (1 + p.has_blo));
+    int it = 0;
+    for (int t = pair; t < ntiles; t += npairs) {
+      const int n0 = (t % nt_n) * TC_BN + (int)rank * (TC_BN / 2), m0 = ((t / nt_n) % nt_m) * (2 * TC_BM) + (int)rank * TC_BM;
+      const int z = t / (nt_n * nt_m);
+      const int kb0 = z * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % TC2_STAGES;
+        tc_mbar_wait(&bar_empty[s], ((it / TC2_STAGES) & 1) ^ 1);
+        const uint32_t full = tc_mapa(tc_smem_u32(&bar_full[s]), 0);  // the leader's barrier
+        if (rank == 0) tc_mbar_expect_tx(&bar_full[s], 2 * bytes_cta);
+        const uint32_t st = smem0 + s * TC2_STAGE_BYTES;
+        const uint32_t sA = st, sAlo = st + TC2_A_BYTES, sB = st + 2 * TC2_A_BYTES, sBlo = sB + TC2_B_BYTES;
+        if (AMAJ == 0) {
+          tc2_tma_2d(sA, &mapA, full, kb * TC_BK, m0);
+          if (p.has_alo) tc2_tma_2d(sAlo, &mapAlo, full, kb * TC_BK, m0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            tc2_tma_2d(sA + j * 4096, &mapA, full, m0 + 32 * j, kb * TC_BK);
+            if (p.has_alo) tc2_tma_2d(sAlo + j * 4096, &mapAlo, full, m0 + 32 * j, kb * TC_BK);
+          }
+        }
+        if (BMAJ == 0) {
+          tc2_tma_2d(sB, &mapB, full, kb * TC_BK, n0);
+          if (p.has_blo) tc2_tma_2d(sBlo, &mapBlo, full, kb * TC_BK, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            tc2_tma_2d(sB + j * 4096, &mapB, full, n0 + 32 * j, kb * TC_BK);
+            if (p.has_blo) tc2_tma_2d(sBlo + j * 4096, &mapBlo, full, n0 + 32 * j, kb * TC_BK);
+          }
+        }
+      }
+    }
+   }
+  } else if (warp == 1 && rank == 0) {
+   if (tc_elect_one()) {
+    // ------------------------------------------------------------ MMA issuer (one thread of the leader CTA), M = 256
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)AMAJ << 15) | ((uint32_t)BMAJ << 16) |
+                           ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+    int it = 0, j = 0;
+    for (int t = pair; t < ntiles; t += npairs, ++j) {
+      const int z = t / (nt_n * nt_m);
+      const int kb0 = z * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
+      const int buf = j & 1;
+      tc_mbar_wait(&bar_acc_empty[buf], ((j >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this accumulator set
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_main = tmem + (uint32_t)buf * (2 * TC_BN), d_corr = d_main + TC_BN;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % TC2_STAGES;
+        tc_mbar_wait(&bar_full[s], (it / TC2_STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = smem0 + s * TC2_STAGE_BYTES;
+        const uint32_t sA = st, sAlo = st + TC2_A_BYTES, sB = st + 2 * TC2_A_BYTES, sBlo = sB + TC2_B_BYTES;
+        const uint32_t a0 = tc_desc_lo<AMAJ>(sA), al0 = tc_desc_lo<AMAJ>(sAlo), b0 = tc_desc_lo<BMAJ>(sB), bl0 = tc_desc_lo<BMAJ>(sBlo);
+        const uint32_t ahi = tc_desc_hi<AMAJ>(), bhi = tc_desc_hi<BMAJ>();
+#pragma unroll
+        for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+          const uint32_t ka = k8 * tc_desc_k8_step<AMAJ>(), kb8 = k8 * tc_desc_k8_step<BMAJ>();
+          const uint32_t first = (kb == kb0 && k8 == 0) ? 0u : 1u;
+          tc_mma_lh<2>(d_main, a0 + ka, ahi, b0 + kb8, bhi, idesc, first);
+          if (p.has_alo) tc_mma_lh<2>(d_corr, al0 + ka, ahi, b0 + kb8, bhi, idesc, first);
+          if (p.has_blo) tc_mma_lh<2>(d_corr, a0 + ka, ahi, bl0 + kb8, bhi, idesc, (first || p.has_alo) ? 1u : 0u);
+        }
+        tc2_commit(&bar_empty[s]);  // frees the stage in both CTAs once these MMAs have read it
+      }
+      tc2_commit(&bar_acc_full[buf]);  // accumulator set complete, both CTAs
+    }
+   }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue: this CTA's 128 rows, TMEM -> registers -> smem -> global
+    const int q = warp & 3;
+    const bool partial = p.splits > 1;
+    const int n4 = (p.N + 3) & ~3;
+    const int ldo = partial ? n4 : p.ldc;
+    const int epi = partial ? EPI_STORE : p.epi;
+    const bool has_bias = epi >= EPI_BIAS && epi <= EPI_BIAS_ELU, has_src = epi == EPI_DRELU || epi == EPI_DELU;
+    const bool accum = !partial && p.accumulate;
+    const bool has_corr = p.has_alo || p.has_blo;
+    float* const stg = reinterpret_cast<float*>(tc_smem_raw + (smem0 - tc_smem_u32(tc_smem_raw)) + TC2_STAGES * TC2_STAGE_BYTES) + q * (32 * 36);
+    int j = 0;
+    for (int t = pair; t < ntiles; t += npairs, ++j) {
+      const int n0 = (t % nt_n) * TC_BN, m0 = ((t / nt_n) % nt_m) * (2 * TC_BM) + (int)rank * TC_BM, z = t / (nt_n * nt_m);
+      const int buf = j & 1;
+      float* const out = partial ? p.ws + (size_t)z * p.M * n4 : p.C;
+      float* const out_lo = (!partial && p.C_lo) ? p.C_lo : nullptr;
+      tc_mbar_wait(&bar_acc_full[buf], (j >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      int nchunks = (p.N - n0 + 31) / 32;
+      nchunks = nchunks > TC_BN / 32 ? TC_BN / 32 : nchunks;
+#pragma unroll 1
+      for (int ch = 0; ch < TC_BN / 32; ++ch) {
+        const int c0 = ch * 32;
+        float v[32];
+        if (ch < nchunks) {
+          uint32_t u[32], w[32];
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * TC_BN + c0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+              "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+                "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
+                "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
+                "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+              : "r"(taddr));
+          if (has_corr) {
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+                "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]), "=r"(w[9]),
+                  "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]), "=r"(w[16]), "=r"(w[17]), "=r"(w[18]),
+                  "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]), "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]),
+                  "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
+                : "r"(taddr + TC_BN));
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = has_corr ? __uint_as_float(u[i]) + __uint_as_float(w[i]) : __uint_as_float(u[i]);
+        }
+        if (ch == nchunks - 1) {
+          // all TMEM reads of this tile are done: hand the accumulator set back to the leader's MMA issuer
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0)
+            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tc_mapa(tc_smem_u32(&bar_acc_empty[buf]), 0)) : "memory");
+        }
+        if (ch >= nchunks) continue;  // warp-uniform
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          *reinterpret_cast<float4*>(stg + lane * 36 + j4 * 4) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+        __syncwarp();
+        const int c4 = (lane & 7) * 4, gn = n0 + c0 + c4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = (lane >> 3) + 4 * i, gm = m0 + q * 32 + r;
+          if (gm >= p.M || gn >= p.N) continue;
+          const float4 acc4 = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
+          float x[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
+          float* orow = out + (size_t)gm * ldo + gn;
+          if (gn + 3 < p.N) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = b4;
+            if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn));
+            if (has_src) s4 = __ldg(reinterpret_cast<const float4*>(p.act_src + (size_t)gm * p.ld_act + gn));
+            x[0] = tc_epi(x[0], epi, b4.x, s4.x); x[1] = tc_epi(x[1], epi, b4.y, s4.y);
+            x[2] = tc_epi(x[2], epi, b4.z, s4.z); x[3] = tc_epi(x[3], epi, b4.w, s4.w);
+            if (accum) {
+              const float4 o4 = *reinterpret_cast<const float4*>(orow);
+              x[0] += o4.x; x[1] += o4.y; x[2] += o4.z; x[3] += o4.w;
+            }
+            *reinterpret_cast<float4*>(orow) = make_float4(x[0], x[1], x[2], x[3]);
+            if (out_lo)
+              *reinterpret_cast<float4*>(out_lo + (size_t)gm * ldo + gn) = make_float4(tf32_lo(x[0]), tf32_lo(x[1]), tf32_lo(x[2]), tf32_lo(x[3]));
+          } else {
+            for (int jj = 0; jj < 4 && gn + jj < p.N; ++jj) {
+              const float bias = has_bias ? __ldg(p.bias + gn + jj) : 0.f;
+              const float src = has_src ? __ldg(p.act_src + (size_t)gm * p.ld_act + gn + jj) : 0.f;
+              float y = tc_epi(x[jj], epi, bias, src);
+              if (accum) y += orow[jj];
+              orow[jj] = y;
+              if (out_lo) out_lo[(size_t)gm * ldo + gn + jj] = tf32_lo(y);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  tc_cluster_sync();  // the peer may still be signalling this CTA's barriers / reading its shared memory through the pair's MMAs
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS));
+}
+
 // ------------------------------------------------------------------ host side: tensor-map cache + launcher
 typedef CUresult (*PFN_tc_encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -294,7 +591,7 @@ typedef CUresult (*PFN_tc_encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static PFN_tc_encode g_encode = nullptr;
 
 struct MapKey {
-  const void* p; int rows, k, ld, maj;
+  const void* p; int rows, k, ld, maj;  // maj: 0 K-major box 32k x 128 rows, 1 MN-major box 32 rows x 32k, 2 K-major box 32k x 64 rows
   bool operator==(const MapKey& o) const { return p == o.p && rows == o.rows && k == o.k && ld == o.ld && maj == o.maj; }
 };
 struct MapKeyHash {
@@ -321,7 +618,7 @@ static int tc_get_map(const float* base, int rows, int k, int ld, int maj, CUten
   cuuint64_t dims[2], strides[1] = {(cuuint64_t)ld * sizeof(float)};
   cuuint32_t box[2], es[2] = {1, 1};
   CUtensorMapSwizzle swz;
-  if (maj == 0) { dims[0] = k; dims[1] = rows; box[0] = TC_BK; box[1] = 128; swz = CU_TENSOR_MAP_SWIZZLE_128B; }
+  if (maj == 0 || maj == 2) { dims[0] = k; dims[1] = rows; box[0] = TC_BK; box[1] = maj == 0 ? 128 : 64; swz = CU_TENSOR_MAP_SWIZZLE_128B; }
   else { dims[0] = rows; dims[1] = k; box[0] = 32; box[1] = TC_BK; swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; }
   CUtensorMap m;
   CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
@@ -338,6 +635,26 @@ bool dtc_gemm_tc_eligible(const GemmArgs& a) {
   if (!a.A_lo || !a.B_lo) return false;  // fp32-grade results need both companions; otherwise the FP32 SIMT path runs
   if (a.a_kc != true && a.b_kc == true) return false;  // (MN-major A, K-major B) is not used by the learner
   return true;
+}
+
+static int g_tc_pair = -1;  // CTA-pair kernel for tile-rich shapes (env DTC_GEMM_PAIR=0 disables)
+static int tc_pair_mode() {
+  if (g_tc_pair < 0) { const char* e = getenv("DTC_GEMM_PAIR"); g_tc_pair = (e && e[0] == '0') ? 0 : 1; }
+  return g_tc_pair;
+}
+extern "C" void dtc_set_gemm_pair(int on) { g_tc_pair = on ? 1 : 0; }
+extern "C" int dtc_get_gemm_pair(void) { return tc_pair_mode(); }
+
+template <int AMAJ, int BMAJ>
+static int tc2_launch_t(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB, const CUtensorMap& mBlo, const TcParams& p,
+                        dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DTC_CUDA(cudaFuncSetAttribute(k_gemm_tc2<AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
+    attr_set = true;
+  }
+  k_gemm_tc2<AMAJ, BMAJ><<<grid, 256, TC2_SMEM_BYTES, st>>>(mA, mAlo, mB, mBlo, p);
+  return DTC_OK;
 }
 
 template <int AMAJ, int BMAJ>
@@ -370,18 +687,27 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   p.ws = a.ws;
   p.has_alo = a.A_lo ? 1 : 0; p.has_blo = a.B_lo ? 1 : 0;
   const int amaj = a.a_kc ? 0 : 1, bmaj = a.b_kc ? 0 : 1;
-  CUtensorMap mA, mAlo, mB, mBlo;
-  RETURN_IF_ERR(tc_get_map(a.A, a.M, a.K, a.lda, amaj, &mA));
-  RETURN_IF_ERR(tc_get_map(a.B, a.N, a.K, a.ldb, bmaj, &mB));
-  if (a.A_lo) RETURN_IF_ERR(tc_get_map(a.A_lo, a.M, a.K, a.lda, amaj, &mAlo)); else mAlo = mA;
-  if (a.B_lo) RETURN_IF_ERR(tc_get_map(a.B_lo, a.N, a.K, a.ldb, bmaj, &mBlo)); else mBlo = mB;
   static int num_sms = 0;
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
-  const int ntiles = ceil_div(a.N, TC_BN) * ceil_div(a.M, TC_BM) * splits;
-  dim3 grid(ntiles < num_sms ? ntiles : num_sms);
+  // CTA pairs pay off once there are enough 256-row tiles to keep every pair busy
+  const int pair_tiles = ceil_div(a.N, TC_BN) * ceil_div(a.M, 2 * TC_BM) * splits;
+  const bool use_pair = tc_pair_mode() && a.M > TC_BM && pair_tiles >= num_sms / 2;
+  const int bmap = (use_pair && bmaj == 0) ? 2 : bmaj;
+  CUtensorMap mA, mAlo, mB, mBlo;
+  RETURN_IF_ERR(tc_get_map(a.A, a.M, a.K, a.lda, amaj, &mA));
+  RETURN_IF_ERR(tc_get_map(a.B, a.N, a.K, a.ldb, bmap, &mB));
+  if (a.A_lo) RETURN_IF_ERR(tc_get_map(a.A_lo, a.M, a.K, a.lda, amaj, &mAlo)); else mAlo = mA;
+  if (a.B_lo) RETURN_IF_ERR(tc_get_map(a.B_lo, a.N, a.K, a.ldb, bmap, &mBlo)); else mBlo = mB;
+  const int ntiles = use_pair ? pair_tiles : ceil_div(a.N, TC_BN) * ceil_div(a.M, TC_BM) * splits;
+  dim3 grid(use_pair ? 2 * (ntiles < num_sms / 2 ? ntiles : num_sms / 2) : (ntiles < num_sms ? ntiles : num_sms));
   dtc_prof_begin(st, 0, 2.0 * a.M * a.N * a.K);
   int rc;
-  if (amaj == 0 && bmaj == 0) rc = tc_launch_t<0, 0>(mA, mAlo, mB, mBlo, p, grid, st);
+  if (use_pair) {
+    if (amaj == 0 && bmaj == 0) rc = tc2_launch_t<0, 0>(mA, mAlo, mB, mBlo, p, grid, st);
+    else if (amaj == 0 && bmaj == 1) rc = tc2_launch_t<0, 1>(mA, mAlo, mB, mBlo, p, grid, st);
+    else if (amaj == 1 && bmaj == 1) rc = tc2_launch_t<1, 1>(mA, mAlo, mB, mBlo, p, grid, st);
+    else DTC_FAIL(DTC_ERR_ARG, "gemm_tc: unsupported operand layout");
+  } else if (amaj == 0 && bmaj == 0) rc = tc_launch_t<0, 0>(mA, mAlo, mB, mBlo, p, grid, st);
   else if (amaj == 0 && bmaj == 1) rc = tc_launch_t<0, 1>(mA, mAlo, mB, mBlo, p, grid, st);
   else if (amaj == 1 && bmaj == 1) rc = tc_launch_t<1, 1>(mA, mAlo, mB, mBlo, p, grid, st);
   else DTC_FAIL(DTC_ERR_ARG, "gemm_tc: unsupported operand layout");

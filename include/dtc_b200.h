@@ -277,6 +277,10 @@ int dtc_gemm_debug(int32_t M, int32_t N, int32_t K, const float* A, const float*
 /* GEMM engine of the learner: 0 = FP32 SIMT, 1 = tcgen05 3xTF32 for tile-worthy shapes (default; env DTC_GEMM=simt|tc) */
 void dtc_set_gemm_mode(int mode);
 int dtc_get_gemm_mode(void);
+/* tensor-core engine only: 1 (default; env DTC_GEMM_PAIR) = shapes with enough 256-row tiles run on CTA pairs
+ * (tcgen05 cta_group::2, the two SMs of a TPC share each B tile), 0 = always the single-CTA kernel.  Same results. */
+void dtc_set_gemm_pair(int on);
+int dtc_get_gemm_pair(void);
 /* Intra-step concurrency of dtc_policy_act / dtc_vae_step / dtc_ppo_step (default on): the CENet chains and the weight
  * gradients are forked onto two library-owned non-blocking streams with events and joined back into the caller's stream
  * before the call returns; results are identical either way.  Off while dtc_profile_enable(1) is active. */

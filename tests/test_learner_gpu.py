@@ -67,7 +67,7 @@ def _gemm(lib, mode, M, N, K, A, a_kc, Bm, b_kc, Cd, splits=1, ws=None, C_lo=Non
 
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("M,N,K", [(4096, 512, 693), (300, 35, 64), (1000, 12, 128), (777, 693, 512), (64, 1, 128), (130, 588, 512),
-                                   (256, 128, 265), (5000, 256, 12)])
+                                   (256, 128, 265), (5000, 256, 12), (24576, 512, 693), (10000, 693, 512), (19000, 256, 512)])
 def test_gemm_forward_and_dgrad(M, N, K, mode):
     """mode 0: FP32 SIMT kernels; mode 1: tcgen05 3xTF32 (shapes too small for a tile fall back to SIMT inside the launcher)."""
     lib = B.lib()
@@ -117,6 +117,37 @@ def test_gemm_wgrad_splitk(M, N, K, mode):
         Cd = torch.full((M, r4(N)), 3.0, device=DEV)
         _gemm(lib, mode, M, N, K, dYd, 0, Xd, 0, Cd, splits=splits, ws=ws)
         _close(Cd[:, :N], ref, f"wgrad mode{mode} splits={splits}")
+
+
+@pytest.mark.parametrize("M,N,K,a_kc,b_kc,splits", [(24576, 512, 693, 1, 1, 1), (10000, 693, 512, 1, 0, 1), (24576, 752, 512, 1, 0, 1),
+                                                     (512, 693, 24576, 0, 0, 25), (693, 512, 6144, 0, 0, 7), (256, 512, 24576, 0, 0, 30),
+                                                     (19000, 256, 512, 1, 1, 1)])
+def test_gemm_cta_pair_matches_single(M, N, K, a_kc, b_kc, splits):
+    """The cta_group::2 kernel (256x128 pair tiles, B halves shared between the two SMs of a TPC) issues the same MMAs in the
+    same order as the single-CTA kernel: results must be bit-identical, including ragged last tiles and split-K partials."""
+    lib = B.lib()
+    g = torch.Generator().manual_seed(M + 7 * N + K)
+    r4 = lambda x: (x + 3) // 4 * 4
+    A = torch.zeros(M if a_kc else K, r4(K if a_kc else M)); A[:, :(K if a_kc else M)] = torch.randn(A.shape[0], K if a_kc else M, generator=g)
+    Bm = torch.zeros(N if b_kc else K, r4(K if b_kc else N)); Bm[:, :(K if b_kc else N)] = torch.randn(Bm.shape[0], K if b_kc else N, generator=g) * 0.1
+    Ad, Bd = A.to(DEV), Bm.to(DEV)
+    ws = torch.zeros(max(splits, -(-K // 1024)) * M * r4(N), device=DEV) if splits > 1 else None
+    out = {}
+    saved = lib.dtc_get_gemm_pair()
+    try:
+        for pair in (0, 1):
+            lib.dtc_set_gemm_pair(pair)
+            Cd = torch.full((M, r4(N)), 5.0, device=DEV)
+            Cl = torch.full((M, r4(N)), 5.0, device=DEV)
+            _gemm(lib, 1, M, N, K, Ad, a_kc, Bd, b_kc, Cd, splits=splits, ws=ws, C_lo=Cl if splits == 1 else None)
+            out[pair] = (Cd.clone(), Cl.clone())
+    finally:
+        lib.dtc_set_gemm_pair(saved)
+    Ar = (A[:, :K] if a_kc else A[:, :M].T).double()
+    Br = (Bm[:, :K] if b_kc else Bm[:, :N].T).double()
+    _close(out[1][0][:, :N], Ar @ Br.T, "pair vs fp64")
+    assert torch.equal(out[0][0], out[1][0]), f"pair kernel differs: {(out[0][0] - out[1][0]).abs().max().item()}"
+    assert torch.equal(out[0][1], out[1][1]), "companion output differs"
 
 
 # ------------------------------------------------------------------ policy forward
