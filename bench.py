@@ -30,6 +30,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 T_STEPS = 24
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of k_gemm_tc2 from the committed ncu --set full capture (profiles/)
+TRAFFIC_GEMM_TC2 = None
 BYTES_STATE_PER_ENV = (13 + 12 * 2 + 17 * 3 + 17 * 13) * 4  # root, dof, contact, rigid body
 
 
@@ -149,7 +151,8 @@ def run_cuda(args):
     env, fg, runner, state, pool_host, pool_dev = build_world(N, rank, device)
     lib = B.lib()
 
-    runner.learn(args.warmup)
+    if args.warmup > 0:
+        runner.learn(args.warmup)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = B.launch_count()
     ms = timed(runner, args.steps, world, device)
@@ -159,35 +162,46 @@ def run_cuda(args):
     value = env_steps / (ms * 1e-3)
 
     # e2e: simulator tensors come from pinned host memory every env step; statistics are read back every iteration
-    state["pool"] = pool_host
-    runner.learn(1)
-    ms_e2e = timed(runner, args.steps, world, device)
-    e2e_value = env_steps / (ms_e2e * 1e-3)
-    state["pool"] = pool_dev
+    if args.profile_lite:  # launch-list runs under ncu: one timed iteration is all that is wanted
+        ms_e2e, e2e_value = float("nan"), float("nan")
+    else:
+        state["pool"] = pool_host
+        runner.learn(1)
+        ms_e2e = timed(runner, args.steps, world, device)
+        e2e_value = env_steps / (ms_e2e * 1e-3)
+        state["pool"] = pool_dev
 
     # roofline of the dominant kernel (the GEMM family: > 90 % of the step), measured with CUDA events around every
     # launch of one extra iteration
     roof, fh = None, None
-    if rank == 0:
+    if rank == 0 and not args.profile_lite:
         lib.dtc_profile_enable(1)
-    runner.learn(1)  # every rank takes part (the optimizer steps all-reduce); only rank 0 records events
+    if not args.profile_lite:
+        runner.learn(1)  # every rank takes part (the optimizer steps all-reduce); only rank 0 records events
     torch.cuda.synchronize(device)
-    if rank == 0:
+    if rank == 0 and not args.profile_lite:
         import ctypes as C
         peaks = _peaks()
         flops, gms, fms, n_g, n_f = C.c_double(), C.c_double(), C.c_double(), C.c_int64(), C.c_int64()
         lib.dtc_profile_read(C.byref(flops), C.byref(gms), C.byref(n_g), C.byref(fms), C.byref(n_f))
         lib.dtc_profile_enable(0)
-        ach = flops.value / (gms.value * 1e-3) / 1e12 if gms.value > 0 else 0.0
-        roof = {"kernel": "k_gemm_tc (tcgen05 kind::tf32 3xTF32 GEMM: forward / dgrad / split-K wgrad) + SIMT k_gemm for small shapes", "bound": "tensor",
-                "achieved": round(ach, 2), "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
-                "frac": round(ach / peaks["tensor_sustained"], 4), "traffic": None,
+        fam = flops.value / (gms.value * 1e-3) / 1e12 if gms.value > 0 else 0.0
+        pw, pms, pn = C.c_double(), C.c_double(), C.c_int64()
+        lib.dtc_profile_kind(2, C.byref(pw), C.byref(pms), C.byref(pn))
+        ach = pw.value / (pms.value * 1e-3) / 1e12 if pms.value > 0 else 0.0
+        # ncu --set full of the same kernel (profiles/): DRAM bytes per launch on the learner's largest shape
+        roof = {"kernel": "k_gemm_tc2 (tcgen05 cta_group::2 kind::tf32, error-compensated 3xTF32: forward / dgrad / split-K wgrad of the 256..752-wide layers)",
+                "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
+                "frac": round(ach / peaks["tensor_sustained"], 4), "traffic": TRAFFIC_GEMM_TC2,
                 "peak_source": peaks["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
-                "launches_per_step": n_g.value, "gemm_ms_per_step": round(gms.value, 3),
-                "algorithmic_flops_per_step": flops.value,
-                "note": "fp32-equivalent FLOPs; the tensor pipe executes 3 TF32 MMAs per product (error-compensated split, 1e-5 parity), "
-                        "i.e. %.1f TF32 TFLOP/s = %.3f of the TF32 dense peak taken as half the measured bf16 figure" %
-                        (3 * ach, 3 * ach / (0.5 * peaks["tensor_sustained"]))}
+                "launches_per_step": pn.value, "kernel_ms_per_step": round(pms.value, 3),
+                "algorithmic_flops_per_launch": round(pw.value / max(1, pn.value), 1),
+                "share_of_gemm_family_time": round(pms.value / gms.value, 4) if gms.value > 0 else None,
+                "gemm_family": {"launches_per_step": n_g.value, "ms_per_step": round(gms.value, 3), "tflops": round(fam, 2),
+                                "algorithmic_flops_per_step": flops.value},
+                "note": "algorithmic = 2*M*N*K fp32-equivalent FLOPs; the tensor pipe executes 3 TF32 MMAs per product (1e-5 parity), "
+                        "i.e. %.1f TF32 TFLOP/s = %.3f of the TF32 dense peak taken as half the measured bf16 figure; per-launch CUDA "
+                        "events with the step's side streams serialised" % (3 * ach, 3 * ach / (0.5 * peaks["tensor_sustained"]))}
         fh_bytes = 3048.0 * N + 3942400.0
         fh_us = fms.value * 1e3 / max(1, n_f.value)
         fh = {"kernel": "k_foothold", "bound": "hbm", "achieved": round(fh_bytes / (fh_us * 1e-6) / 1e9, 1), "peak": peaks["hbm"],
@@ -299,8 +313,12 @@ def main():
     ap.add_argument("--cpu-envs", type=int, default=384, help="environments of the bounded CPU-baseline sample")
     ap.add_argument("--ref-envs", type=int, default=192, help="environments per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-lite", action="store_true",
+                    help="for launch lists under ncu (never a bench value): warm-up as given, no e2e / roofline / CPU legs")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "dtc_b200":
+    if args.profile_lite:
+        args.no_cpu_baseline = True
+    if args.warmup < 3 and args.impl == "dtc_b200" and not args.profile_lite:
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)

@@ -620,22 +620,32 @@ void dtc_prof_end(cudaStream_t st) {
   cudaEventRecord(g_prof_recs.back().b, st);
 }
 extern "C" void dtc_profile_enable(int on) { g_dtc_prof = on; }
+static double g_prof_last_work[4], g_prof_last_ms[4];
+static int64_t g_prof_last_n[4];
+// kinds: 0 = GEMM family except the CTA-pair kernel, 1 = foothold kernel, 2 = CTA-pair tensor-core GEMM (the dominant kernel)
 extern "C" int dtc_profile_read(double* gemm_flops, double* gemm_ms, int64_t* gemm_launches, double* foothold_ms, int64_t* foothold_launches) {
-  double fl = 0, gms = 0, fms = 0;
-  int64_t ng = 0, nf = 0;
+  for (int k = 0; k < 4; ++k) { g_prof_last_work[k] = g_prof_last_ms[k] = 0.0; g_prof_last_n[k] = 0; }
   for (auto& r : g_prof_recs) {
     float ms = 0.f;
     cudaEventSynchronize(r.b);
     cudaEventElapsedTime(&ms, r.a, r.b);
-    if (r.kind == 0) { fl += r.work; gms += ms; ++ng; } else { fms += ms; ++nf; }
+    const int k = r.kind >= 0 && r.kind < 4 ? r.kind : 3;
+    g_prof_last_work[k] += r.work; g_prof_last_ms[k] += ms; ++g_prof_last_n[k];
     cudaEventDestroy(r.a); cudaEventDestroy(r.b);
   }
   g_prof_recs.clear();
-  if (gemm_flops) *gemm_flops = fl;
-  if (gemm_ms) *gemm_ms = gms;
-  if (gemm_launches) *gemm_launches = ng;
-  if (foothold_ms) *foothold_ms = fms;
-  if (foothold_launches) *foothold_launches = nf;
+  if (gemm_flops) *gemm_flops = g_prof_last_work[0] + g_prof_last_work[2];
+  if (gemm_ms) *gemm_ms = g_prof_last_ms[0] + g_prof_last_ms[2];
+  if (gemm_launches) *gemm_launches = g_prof_last_n[0] + g_prof_last_n[2];
+  if (foothold_ms) *foothold_ms = g_prof_last_ms[1];
+  if (foothold_launches) *foothold_launches = g_prof_last_n[1];
+  return DTC_OK;
+}
+extern "C" int dtc_profile_kind(int kind, double* work, double* ms, int64_t* launches) {
+  if (kind < 0 || kind >= 4) DTC_FAIL(DTC_ERR_ARG, "dtc_profile_kind: unknown kind %d", kind);
+  if (work) *work = g_prof_last_work[kind];
+  if (ms) *ms = g_prof_last_ms[kind];
+  if (launches) *launches = g_prof_last_n[kind];
   return DTC_OK;
 }
 

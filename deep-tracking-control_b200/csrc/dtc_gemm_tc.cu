@@ -27,7 +27,8 @@
 #define TC_MAX_KB 32     // k-blocks (of 32) accumulated in TMEM before the fp32 split-K sum takes over
 #define TC_TILE_BYTES (128 * 32 * 4)
 #define TC_STAGE_BYTES (4 * TC_TILE_BYTES)
-#define TC_STG_BYTES (4 * 32 * 36 * 4)  // epilogue staging: 4 warps x 32 rows x 36 floats
+#define TC_STG_BYTES (8 * 32 * 32 * 4)  // epilogue staging: 8 warps x 32 rows x 32 floats (XOR-swizzled)
+#define TC_THREADS 384              // warp 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..11 epilogue
 #define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + TC_STG_BYTES + 1024)
 
 struct TcParams {
@@ -37,6 +38,7 @@ struct TcParams {
   const float* bias; const float* act_src; int ld_act; int epi; int accumulate;
   float* ws;
   int splits, has_alo, has_blo;
+  int debug;  // timing experiments only (env DTC_TC_DEBUG): 1 = epilogue skips its stores, 2 = producer stops loading after the first ring fill
 };
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -58,6 +60,13 @@ __device__ __forceinline__ void tc_tma_2d(uint32_t dst, const CUtensorMap* map, 
                "l"((uint64_t)map), "r"(tc_smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
 }
+// L2 prefetch of one TMA box (no shared memory, no barrier): the activation operands stream from DRAM once per GEMM and a
+// 3-4 stage smem ring (2300-3000 MMA cycles of lookahead) does not cover a loaded DRAM round trip
+__device__ __forceinline__ void tc_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1) : "memory");
+}
+#define TC_PF_DIST 0  // k-blocks of L2 look-ahead; 0 = off (measured: 8 blocks ahead made every shape 5-20 % slower)
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | layout <<61
 __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
@@ -122,11 +131,136 @@ __device__ __forceinline__ float tc_epi(float v, int epi, float bias, float src)
   }
 }
 
+// Epilogue of one 128-row x 128-column accumulator set by EIGHT warps: warp w drains TMEM lanes 32 (w & 3) .. +31 (the quadrant its
+// tcgen05.ld may touch) and the column half (w - 4) >> 2, in two chunks of 32 columns.  A chunk goes TMEM -> registers (main +
+// correction accumulators summed in fp32) -> a 32x32 XOR-swizzled staging tile -> global, so that every global access is a
+// coalesced 128-byte row segment; the act'(x) operand of a chunk is fetched with eight independent loads before any of it is used.
+// The accumulator set is handed back to the MMA issuer (acc_empty: 8 arrivals per CTA) as soon as this warp's TMEM reads are done.
+__device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tmem, int buf, int warp, int lane, int m0, int n0, int z,
+                                                 float* stg, uint32_t acc_empty_addr, bool cluster_arrive) {
+  const int q = warp & 3, half = (warp - 4) >> 2;
+  const bool partial = p.splits > 1;
+  const int n4 = (p.N + 3) & ~3;
+  const int ldo = partial ? n4 : p.ldc;
+  const int epi = partial ? EPI_STORE : p.epi;
+  const bool has_bias = epi >= EPI_BIAS && epi <= EPI_BIAS_ELU, has_src = epi == EPI_DRELU || epi == EPI_DELU;
+  const bool accum = !partial && p.accumulate;
+  const bool has_corr = p.has_alo || p.has_blo;
+  float* const out = partial ? p.ws + (size_t)z * p.M * n4 : p.C;
+  float* const out_lo = (!partial && p.C_lo) ? p.C_lo : nullptr;
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  int nchunks = (p.N - n0 + 31) / 32;  // live 32-column chunks of this tile
+  nchunks = nchunks > TC_BN / 32 ? TC_BN / 32 : nchunks;
+  const int ch_first = 2 * half;
+  const int ch_last = min(ch_first + 1, nchunks - 1);  // last chunk this warp reads (< ch_first: none)
+  if (ch_last < ch_first) {  // nothing to read: release the accumulator set right away
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      if (cluster_arrive) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(acc_empty_addr) : "memory");
+      else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty_addr) : "memory");
+    }
+    return;
+  }
+#pragma unroll 1
+  for (int ch = ch_first; ch <= ch_last; ++ch) {
+    const int c0 = ch * 32;
+    float v[32];
+    {
+      uint32_t u[32], w[32];
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * TC_BN + c0);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+          "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+            "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
+            "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
+            "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+          : "r"(taddr));
+      if (has_corr) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+            "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]), "=r"(w[9]),
+              "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]), "=r"(w[16]), "=r"(w[17]), "=r"(w[18]),
+              "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]), "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]),
+              "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
+            : "r"(taddr + TC_BN));
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = has_corr ? __uint_as_float(u[i]) + __uint_as_float(w[i]) : __uint_as_float(u[i]);
+    }
+    if (ch == ch_last) {
+      // all TMEM reads of this warp are done: hand the accumulator set back to the MMA issuer
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        if (cluster_arrive) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(acc_empty_addr) : "memory");
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty_addr) : "memory");
+      }
+    }
+    if (p.debug & 1) continue;
+    // row `lane`, 16-byte block j4 -> physical block j4 ^ (lane & 7): conflict-free for the row-wise writes and the
+    // 4-rows-x-8-blocks reads below
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4)
+      *reinterpret_cast<float4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2)) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+    __syncwarp();
+    const int cb = lane & 7, c4 = cb * 4, gn = n0 + c0 + c4;
+    const int r0 = lane >> 3, gm0 = m0 + q * 32 + r0;
+    if (gn + 3 < p.N) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn));
+      float4 s4[8], o4[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int gm = gm0 + 4 * i;
+        s4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        o4[i] = s4[i];
+        if (gm < p.M) {
+          if (has_src) s4[i] = __ldg(reinterpret_cast<const float4*>(p.act_src + (size_t)gm * p.ld_act + gn));
+          if (accum) o4[i] = *reinterpret_cast<const float4*>(out + (size_t)gm * ldo + gn);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + 4 * i, gm = gm0 + 4 * i;
+        if (gm >= p.M) continue;
+        const float4 a4 = *reinterpret_cast<const float4*>(stg + r * 32 + ((cb ^ (r & 7)) << 2));
+        float4 x;
+        x.x = tc_epi(a4.x, epi, b4.x, s4[i].x) + o4[i].x; x.y = tc_epi(a4.y, epi, b4.y, s4[i].y) + o4[i].y;
+        x.z = tc_epi(a4.z, epi, b4.z, s4[i].z) + o4[i].z; x.w = tc_epi(a4.w, epi, b4.w, s4[i].w) + o4[i].w;
+        *reinterpret_cast<float4*>(out + (size_t)gm * ldo + gn) = x;
+        if (out_lo) *reinterpret_cast<float4*>(out_lo + (size_t)gm * ldo + gn) = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+      }
+    } else if (gn < p.N) {  // ragged right edge: scalar tail
+#pragma unroll 1
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + 4 * i, gm = gm0 + 4 * i;
+        if (gm >= p.M) continue;
+        const float4 a4 = *reinterpret_cast<const float4*>(stg + r * 32 + ((cb ^ (r & 7)) << 2));
+        const float x[4] = {a4.x, a4.y, a4.z, a4.w};
+        float* orow = out + (size_t)gm * ldo + gn;
+        for (int jj = 0; jj < 4 && gn + jj < p.N; ++jj) {
+          const float bias = has_bias ? __ldg(p.bias + gn + jj) : 0.f;
+          const float src = has_src ? __ldg(p.act_src + (size_t)gm * p.ld_act + gn + jj) : 0.f;
+          float y = tc_epi(x[jj], epi, bias, src);
+          if (accum) y += orow[jj];
+          orow[jj] = y;
+          if (out_lo) out_lo[(size_t)gm * ldo + gn + jj] = tf32_lo(y);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // Persistent kernel: one CTA per SM walks the (split, m-tile, n-tile) list with stride gridDim.x.  TMEM holds two
 // accumulator sets (main | correction, 2 x 128 columns each), so the epilogue of tile j overlaps the MMAs of tile j+1; the TMA
 // producer runs ahead across tile boundaries.
 template <int AMAJ, int BMAJ>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapB,
           const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
   extern __shared__ uint8_t tc_smem_raw[];
@@ -139,7 +273,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(&bar_full[s], 1); tc_mbar_init(&bar_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { tc_mbar_init(&bar_acc_full[s], 1); tc_mbar_init(&bar_acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { tc_mbar_init(&bar_acc_full[s], 1); tc_mbar_init(&bar_acc_empty[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -156,10 +290,43 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     // ------------------------------------------------------------ TMA producer
     const uint32_t bytes = TC_TILE_BYTES * (2 + p.has_alo + p.has_blo);
     int it = 0;
+    // look-ahead cursor of the L2 prefetch: TC_PF_DIST k-blocks ahead of the loads, across tile boundaries
+    int pt = blockIdx.x, pkb = 0, pkb1 = 0, pm0 = 0, pn0 = 0;
+    auto pf_open = [&]() {
+      if (pt < ntiles) {
+        const int z = pt / (nt_n * nt_m);
+        pn0 = (pt % nt_n) * TC_BN; pm0 = ((pt / nt_n) % nt_m) * TC_BM;
+        pkb = z * p.kb_per_split; pkb1 = min(p.nkb, pkb + p.kb_per_split);
+      }
+    };
+    auto pf_step = [&]() {
+      if (pt >= ntiles) return;
+      if (AMAJ == 0) {
+        tc_prefetch_2d(&mapA, pkb * TC_BK, pm0);
+        if (p.has_alo) tc_prefetch_2d(&mapAlo, pkb * TC_BK, pm0);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          tc_prefetch_2d(&mapA, pm0 + 32 * j, pkb * TC_BK);
+          if (p.has_alo) tc_prefetch_2d(&mapAlo, pm0 + 32 * j, pkb * TC_BK);
+        }
+      }
+      if (BMAJ == 1 && AMAJ == 1) {  // weight gradients: the second operand streams as well
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          tc_prefetch_2d(&mapB, pn0 + 32 * j, pkb * TC_BK);
+          if (p.has_blo) tc_prefetch_2d(&mapBlo, pn0 + 32 * j, pkb * TC_BK);
+        }
+      }
+      if (++pkb >= pkb1) { pt += gridDim.x; pf_open(); }
+    };
+    pf_open();
+    for (int i = 0; i < TC_PF_DIST; ++i) pf_step();
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const int n0 = (t % nt_n) * TC_BN, m0 = ((t / nt_n) % nt_m) * TC_BM, z = t / (nt_n * nt_m);
       const int kb0 = z * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        if (TC_PF_DIST > 0) pf_step();
         const int s = it % TC_STAGES;
         tc_mbar_wait(&bar_empty[s], ((it / TC_STAGES) & 1) ^ 1);
         tc_mbar_expect_tx(&bar_full[s], bytes);
@@ -223,102 +390,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     }
    }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue: TMEM -> registers -> smem -> global
-    const int q = warp & 3;
-    const bool partial = p.splits > 1;
-    const int n4 = (p.N + 3) & ~3;
-    const int ldo = partial ? n4 : p.ldc;
-    const int epi = partial ? EPI_STORE : p.epi;
-    const bool has_bias = epi >= EPI_BIAS && epi <= EPI_BIAS_ELU, has_src = epi == EPI_DRELU || epi == EPI_DELU;
-    const bool accum = !partial && p.accumulate;
-    const bool has_corr = p.has_alo || p.has_blo;
-    // each epilogue warp stages its 32x32 chunk (row stride 36 floats) behind the pipeline stages so that every global
-    // access below is a coalesced 128-byte row segment
-    float* const stg = reinterpret_cast<float*>(tc_smem_raw + (smem0 - tc_smem_u32(tc_smem_raw)) + TC_STAGES * TC_STAGE_BYTES) + q * (32 * 36);
+    // ------------------------------------------------------------ epilogue: 8 warps, TMEM -> registers -> smem -> global
+    float* const stg = reinterpret_cast<float*>(tc_smem_raw + (smem0 - tc_smem_u32(tc_smem_raw)) + TC_STAGES * TC_STAGE_BYTES) + (warp - 4) * (32 * 32);
     int j = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
       const int n0 = (t % nt_n) * TC_BN, m0 = ((t / nt_n) % nt_m) * TC_BM, z = t / (nt_n * nt_m);
       const int buf = j & 1;
-      float* const out = partial ? p.ws + (size_t)z * p.M * n4 : p.C;
-      float* const out_lo = (!partial && p.C_lo) ? p.C_lo : nullptr;
       tc_mbar_wait(&bar_acc_full[buf], (j >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      int nchunks = (p.N - n0 + 31) / 32;
-      nchunks = nchunks > TC_BN / 32 ? TC_BN / 32 : nchunks;
-#pragma unroll 1
-      for (int ch = 0; ch < TC_BN / 32; ++ch) {
-        const int c0 = ch * 32;
-        float v[32];
-        if (ch < nchunks) {
-          uint32_t u[32], w[32];
-          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * TC_BN + c0);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
-              "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-              : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
-                "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
-                "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
-                "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-              : "r"(taddr));
-          if (has_corr) {
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
-                "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]), "=r"(w[9]),
-                  "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]), "=r"(w[16]), "=r"(w[17]), "=r"(w[18]),
-                  "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]), "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]),
-                  "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
-                : "r"(taddr + TC_BN));
-          }
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = has_corr ? __uint_as_float(u[i]) + __uint_as_float(w[i]) : __uint_as_float(u[i]);
-        }
-        if (ch == nchunks - 1) {
-          // all TMEM reads of this tile are done: hand the accumulator set back to the MMA issuer
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&bar_acc_empty[buf])) : "memory");
-        }
-        if (ch >= nchunks) continue;  // warp-uniform
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4)
-          *reinterpret_cast<float4*>(stg + lane * 36 + j4 * 4) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-        __syncwarp();
-        const int c4 = (lane & 7) * 4, gn = n0 + c0 + c4;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = (lane >> 3) + 4 * i, gm = m0 + q * 32 + r;
-          if (gm >= p.M || gn >= p.N) continue;
-          const float4 acc4 = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
-          float x[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
-          float* orow = out + (size_t)gm * ldo + gn;
-          if (gn + 3 < p.N) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = b4;
-            if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn));
-            if (has_src) s4 = __ldg(reinterpret_cast<const float4*>(p.act_src + (size_t)gm * p.ld_act + gn));
-            x[0] = tc_epi(x[0], epi, b4.x, s4.x); x[1] = tc_epi(x[1], epi, b4.y, s4.y);
-            x[2] = tc_epi(x[2], epi, b4.z, s4.z); x[3] = tc_epi(x[3], epi, b4.w, s4.w);
-            if (accum) {
-              const float4 o4 = *reinterpret_cast<const float4*>(orow);
-              x[0] += o4.x; x[1] += o4.y; x[2] += o4.z; x[3] += o4.w;
-            }
-            *reinterpret_cast<float4*>(orow) = make_float4(x[0], x[1], x[2], x[3]);
-            if (out_lo)
-              *reinterpret_cast<float4*>(out_lo + (size_t)gm * ldo + gn) = make_float4(tf32_lo(x[0]), tf32_lo(x[1]), tf32_lo(x[2]), tf32_lo(x[3]));
-          } else {
-            for (int jj = 0; jj < 4 && gn + jj < p.N; ++jj) {
-              const float bias = has_bias ? __ldg(p.bias + gn + jj) : 0.f;
-              const float src = has_src ? __ldg(p.act_src + (size_t)gm * p.ld_act + gn + jj) : 0.f;
-              float y = tc_epi(x[jj], epi, bias, src);
-              if (accum) y += orow[jj];
-              orow[jj] = y;
-              if (out_lo) out_lo[(size_t)gm * ldo + gn + jj] = tf32_lo(y);
-            }
-          }
-        }
-        __syncwarp();
-      }
+      tc_epilogue_tile(p, tmem, buf, warp, lane, m0, n0, z, stg, tc_smem_u32(&bar_acc_empty[buf]), false);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -379,7 +458,7 @@ __device__ __forceinline__ uint64_t tc2_b_desc(uint32_t tile, int k8) {  // 64-r
 }
 
 template <int AMAJ, int BMAJ>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapB,
            const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
   extern __shared__ uint8_t tc_smem_raw[];
@@ -394,7 +473,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC2_STAGES; ++s) { tc_mbar_init(&bar_full[s], 1); tc_mbar_init(&bar_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { tc_mbar_init(&bar_acc_full[s], 1); tc_mbar_init(&bar_acc_empty[s], 8); }
+    for (int s = 0; s < 2; ++s) { tc_mbar_init(&bar_acc_full[s], 1); tc_mbar_init(&bar_acc_empty[s], 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -412,14 +491,51 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     // ------------------------------------------------------------ TMA producer (both CTAs)
     const uint32_t bytes_cta = (uint32_t)(TC2_A_BYTES * (1 + p.has_alo) + TC2_B_BYTES * (1 + p.has_blo));
     int it = 0;
+    // look-ahead cursor of the L2 prefetch: TC_PF_DIST k-blocks ahead of the loads, across tile boundaries
+    int pt = pair, pkb = 0, pkb1 = 0, pm0 = 0, pn0 = 0;
+    auto pf_open = [&]() {
+      if (pt < ntiles) {
+        const int z = pt / (nt_n * nt_m);
+        pn0 = (pt % nt_n) * TC_BN + (int)rank * (TC_BN / 2); pm0 = ((pt / nt_n) % nt_m) * (2 * TC_BM) + (int)rank * TC_BM;
+        pkb = z * p.kb_per_split; pkb1 = min(p.nkb, pkb + p.kb_per_split);
+      }
+    };
+    auto pf_step = [&]() {
+      if (pt >= ntiles) return;
+      if (AMAJ == 0) {
+        tc_prefetch_2d(&mapA, pkb * TC_BK, pm0);
+        if (p.has_alo) tc_prefetch_2d(&mapAlo, pkb * TC_BK, pm0);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          tc_prefetch_2d(&mapA, pm0 + 32 * j, pkb * TC_BK);
+          if (p.has_alo) tc_prefetch_2d(&mapAlo, pm0 + 32 * j, pkb * TC_BK);
+        }
+      }
+      if (BMAJ == 1 && AMAJ == 1) {  // weight gradients: the second operand streams as well
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          tc_prefetch_2d(&mapB, pn0 + 32 * j, pkb * TC_BK);
+          if (p.has_blo) tc_prefetch_2d(&mapBlo, pn0 + 32 * j, pkb * TC_BK);
+        }
+      }
+      if (++pkb >= pkb1) { pt += npairs; pf_open(); }
+    };
+    pf_open();
+    for (int i = 0; i < TC_PF_DIST; ++i) pf_step();
     for (int t = pair; t < ntiles; t += npairs) {
       const int n0 = (t % nt_n) * TC_BN + (int)rank * (TC_BN / 2), m0 = ((t / nt_n) % nt_m) * (2 * TC_BM) + (int)rank * TC_BM;
       const int z = t / (nt_n * nt_m);
       const int kb0 = z * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        if (TC_PF_DIST > 0) pf_step();
         const int s = it % TC2_STAGES;
         tc_mbar_wait(&bar_empty[s], ((it / TC2_STAGES) & 1) ^ 1);
         const uint32_t full = tc_mapa(tc_smem_u32(&bar_full[s]), 0);  // the leader's barrier
+        if ((p.debug & 2) && it >= TC2_STAGES) {
+          if (rank == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&bar_full[s])) : "memory");
+          continue;
+        }
         if (rank == 0) tc_mbar_expect_tx(&bar_full[s], 2 * bytes_cta);
         const uint32_t st = smem0 + s * TC2_STAGE_BYTES;
         const uint32_t sA = st, sAlo = st + TC2_A_BYTES, sB = st + 2 * TC2_A_BYTES, sBlo = sB + TC2_B_BYTES;
@@ -481,101 +597,14 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     }
    }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue: this CTA's 128 rows, TMEM -> registers -> smem -> global
-    const int q = warp & 3;
-    const bool partial = p.splits > 1;
-    const int n4 = (p.N + 3) & ~3;
-    const int ldo = partial ? n4 : p.ldc;
-    const int epi = partial ? EPI_STORE : p.epi;
-    const bool has_bias = epi >= EPI_BIAS && epi <= EPI_BIAS_ELU, has_src = epi == EPI_DRELU || epi == EPI_DELU;
-    const bool accum = !partial && p.accumulate;
-    const bool has_corr = p.has_alo || p.has_blo;
-    float* const stg = reinterpret_cast<float*>(tc_smem_raw + (smem0 - tc_smem_u32(tc_smem_raw)) + TC2_STAGES * TC2_STAGE_BYTES) + q * (32 * 36);
+    // ------------------------------------------------------------ epilogue: this CTA's 128 rows, 8 warps
+    float* const stg = reinterpret_cast<float*>(tc_smem_raw + (smem0 - tc_smem_u32(tc_smem_raw)) + TC2_STAGES * TC2_STAGE_BYTES) + (warp - 4) * (32 * 32);
     int j = 0;
     for (int t = pair; t < ntiles; t += npairs, ++j) {
       const int n0 = (t % nt_n) * TC_BN, m0 = ((t / nt_n) % nt_m) * (2 * TC_BM) + (int)rank * TC_BM, z = t / (nt_n * nt_m);
       const int buf = j & 1;
-      float* const out = partial ? p.ws + (size_t)z * p.M * n4 : p.C;
-      float* const out_lo = (!partial && p.C_lo) ? p.C_lo : nullptr;
       tc_mbar_wait(&bar_acc_full[buf], (j >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      int nchunks = (p.N - n0 + 31) / 32;
-      nchunks = nchunks > TC_BN / 32 ? TC_BN / 32 : nchunks;
-#pragma unroll 1
-      for (int ch = 0; ch < TC_BN / 32; ++ch) {
-        const int c0 = ch * 32;
-        float v[32];
-        if (ch < nchunks) {
-          uint32_t u[32], w[32];
-          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * TC_BN + c0);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
-              "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-              : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
-                "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
-                "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
-                "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-              : "r"(taddr));
-          if (has_corr) {
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
-                "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]), "=r"(w[9]),
-                  "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]), "=r"(w[16]), "=r"(w[17]), "=r"(w[18]),
-                  "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]), "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]),
-                  "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
-                : "r"(taddr + TC_BN));
-          }
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = has_corr ? __uint_as_float(u[i]) + __uint_as_float(w[i]) : __uint_as_float(u[i]);
-        }
-        if (ch == nchunks - 1) {
-          // all TMEM reads of this tile are done: hand the accumulator set back to the leader's MMA issuer
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0)
-            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tc_mapa(tc_smem_u32(&bar_acc_empty[buf]), 0)) : "memory");
-        }
-        if (ch >= nchunks) continue;  // warp-uniform
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4)
-          *reinterpret_cast<float4*>(stg + lane * 36 + j4 * 4) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-        __syncwarp();
-        const int c4 = (lane & 7) * 4, gn = n0 + c0 + c4;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = (lane >> 3) + 4 * i, gm = m0 + q * 32 + r;
-          if (gm >= p.M || gn >= p.N) continue;
-          const float4 acc4 = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
-          float x[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
-          float* orow = out + (size_t)gm * ldo + gn;
-          if (gn + 3 < p.N) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = b4;
-            if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn));
-            if (has_src) s4 = __ldg(reinterpret_cast<const float4*>(p.act_src + (size_t)gm * p.ld_act + gn));
-            x[0] = tc_epi(x[0], epi, b4.x, s4.x); x[1] = tc_epi(x[1], epi, b4.y, s4.y);
-            x[2] = tc_epi(x[2], epi, b4.z, s4.z); x[3] = tc_epi(x[3], epi, b4.w, s4.w);
-            if (accum) {
-              const float4 o4 = *reinterpret_cast<const float4*>(orow);
-              x[0] += o4.x; x[1] += o4.y; x[2] += o4.z; x[3] += o4.w;
-            }
-            *reinterpret_cast<float4*>(orow) = make_float4(x[0], x[1], x[2], x[3]);
-            if (out_lo)
-              *reinterpret_cast<float4*>(out_lo + (size_t)gm * ldo + gn) = make_float4(tf32_lo(x[0]), tf32_lo(x[1]), tf32_lo(x[2]), tf32_lo(x[3]));
-          } else {
-            for (int jj = 0; jj < 4 && gn + jj < p.N; ++jj) {
-              const float bias = has_bias ? __ldg(p.bias + gn + jj) : 0.f;
-              const float src = has_src ? __ldg(p.act_src + (size_t)gm * p.ld_act + gn + jj) : 0.f;
-              float y = tc_epi(x[jj], epi, bias, src);
-              if (accum) y += orow[jj];
-              orow[jj] = y;
-              if (out_lo) out_lo[(size_t)gm * ldo + gn + jj] = tf32_lo(y);
-            }
-          }
-        }
-        __syncwarp();
-      }
+      tc_epilogue_tile(p, tmem, buf, warp, lane, m0, n0, z, stg, tc_mapa(tc_smem_u32(&bar_acc_empty[buf]), 0), true);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -653,7 +682,7 @@ static int tc2_launch_t(const CUtensorMap& mA, const CUtensorMap& mAlo, const CU
     DTC_CUDA(cudaFuncSetAttribute(k_gemm_tc2<AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
     attr_set = true;
   }
-  k_gemm_tc2<AMAJ, BMAJ><<<grid, 256, TC2_SMEM_BYTES, st>>>(mA, mAlo, mB, mBlo, p);
+  k_gemm_tc2<AMAJ, BMAJ><<<grid, TC_THREADS, TC2_SMEM_BYTES, st>>>(mA, mAlo, mB, mBlo, p);
   return DTC_OK;
 }
 
@@ -665,7 +694,7 @@ static int tc_launch_t(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUt
     DTC_CUDA(cudaFuncSetAttribute(k_gemm_tc<AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set = true;
   }
-  k_gemm_tc<AMAJ, BMAJ><<<grid, 256, TC_SMEM_BYTES, st>>>(mA, mAlo, mB, mBlo, p);
+  k_gemm_tc<AMAJ, BMAJ><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mA, mAlo, mB, mBlo, p);
   return DTC_OK;
 }
 
@@ -686,6 +715,7 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   p.bias = a.bias; p.act_src = a.act_src; p.ld_act = a.ld_act; p.epi = a.epi; p.accumulate = a.accumulate ? 1 : 0;
   p.ws = a.ws;
   p.has_alo = a.A_lo ? 1 : 0; p.has_blo = a.B_lo ? 1 : 0;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DTC_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
   const int amaj = a.a_kc ? 0 : 1, bmaj = a.b_kc ? 0 : 1;
   static int num_sms = 0;
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
@@ -700,7 +730,7 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   if (a.B_lo) RETURN_IF_ERR(tc_get_map(a.B_lo, a.N, a.K, a.ldb, bmap, &mBlo)); else mBlo = mB;
   const int ntiles = use_pair ? pair_tiles : ceil_div(a.N, TC_BN) * ceil_div(a.M, TC_BM) * splits;
   dim3 grid(use_pair ? 2 * (ntiles < num_sms / 2 ? ntiles : num_sms / 2) : (ntiles < num_sms ? ntiles : num_sms));
-  dtc_prof_begin(st, 0, 2.0 * a.M * a.N * a.K);
+  dtc_prof_begin(st, use_pair ? 2 : 0, 2.0 * a.M * a.N * a.K);
   int rc;
   if (use_pair) {
     if (amaj == 0 && bmaj == 0) rc = tc2_launch_t<0, 0>(mA, mAlo, mB, mBlo, p, grid, st);

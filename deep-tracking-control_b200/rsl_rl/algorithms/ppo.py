@@ -22,31 +22,94 @@ from ..utils import dp
 
 
 class _DeviceAdamHandle:
-    """`alg.optimizer` of the reference, reduced to what the runner's save/load touches."""
+    """`alg.optimizer` / `alg.vae_optimizer` of the reference (torch.optim.Adam, ppo.py:78-79), reduced to what the runner's
+    save/load touches.  `state_dict()` / `load_state_dict()` speak torch.optim.Adam's own format - parameter index i is the
+    i-th entry of `actor_critic.parameters()` (main) / `actor_critic.vae.parameters()` (vae), i.e. of the state_dict key order
+    - so `model_*.pt` files written by the reference's OnPolicyRunner.save (on_policy_runner.py:249-255) resume here and
+    files written here resume there.  Only parameters that receive a gradient in that optimizer's step carry state, as in
+    the reference (the others keep `.grad is None` and torch skips them)."""
 
     def __init__(self, alg, which):
         self._alg, self._which = alg, which
 
-    def state_dict(self):
+    def _keys(self):
+        from ..modules.actor_critic_decoder import STATE_KEYS
         ac = self._alg.actor_critic
+        keys = [k for k in STATE_KEYS if self._which == "main" or k.startswith("vae.")]
+        b, e = ac._table.ranges["policy" if self._which == "main" else "vae"]
+        live = []
+        for i, k in enumerate(keys):
+            idx = ac._table.index[k]
+            lo, hi = int(idx.min()), int(idx.max())
+            if lo >= b and hi < e:
+                live.append((i, k))
+        return keys, live
+
+    def _mv(self):
+        ac = self._alg.actor_critic
+        return ac._adam[0 if self._which == "main" else 2], ac._adam[1 if self._which == "main" else 3]
+
+    def _steps(self):
+        ac = self._alg.actor_critic
+        if self._which in self._alg._pending_steps:
+            return int(self._alg._pending_steps[self._which])
         a, b = C.c_int64(), C.c_int64()
         if ac._h is not None:
             B.lib().dtc_learner_get_adam_steps(ac._h, C.byref(a), C.byref(b))
-        m, v = ac._adam[0 if self._which == "main" else 2], ac._adam[1 if self._which == "main" else 3]
-        return {"layout": "dtc_b200.flat", "step": b.value if self._which == "main" else a.value,
-                "exp_avg": m.clone(), "exp_avg_sq": v.clone(), "lr": self._alg.learning_rate}
+        return b.value if self._which == "main" else a.value
+
+    def state_dict(self):
+        ac = self._alg.actor_critic
+        keys, live = self._keys()
+        m, v = self._mv()
+        steps = self._steps()
+        state = {}
+        if steps > 0:
+            for i, k in live:
+                idx = ac._idx[k]
+                shape = ac._table.shape[k]
+                state[i] = {"step": torch.tensor(float(steps)), "exp_avg": m[idx].view(shape).clone(),
+                            "exp_avg_sq": v[idx].view(shape).clone()}
+        lr = self._alg.learning_rate if self._which == "main" else 5.e-4
+        group = {"lr": lr, "betas": (0.9, 0.999), "eps": 1e-08, "weight_decay": 0, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(keys)))}
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
-        if sd.get("layout") != "dtc_b200.flat":
-            raise ValueError("optimizer state was not written by dtc_b200 (per-parameter torch.optim state is not convertible "
-                             "without the parameter order; load the model weights only)")
         ac = self._alg.actor_critic
-        m, v = ac._adam[0 if self._which == "main" else 2], ac._adam[1 if self._which == "main" else 3]
-        m.copy_(sd["exp_avg"])
-        v.copy_(sd["exp_avg_sq"])
-        self._alg._pending_steps[self._which] = int(sd["step"])
+        m, v = self._mv()
+        if sd.get("layout") == "dtc_b200.flat":  # files written by earlier builds of this package
+            m.copy_(sd["exp_avg"])
+            v.copy_(sd["exp_avg_sq"])
+            self._alg._pending_steps[self._which] = int(sd["step"])
+            if self._which == "main":
+                self._alg.learning_rate = float(sd["lr"])
+            return
+        keys, live = self._keys()
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(keys):
+            raise ValueError(f"optimizer state has {sum(len(g['params']) for g in groups)} parameters in {len(groups)} groups; "
+                             f"expected one group of {len(keys)} (torch.optim.Adam over the reference's parameter list)")
+        order = list(groups[0]["params"])
+        state = sd["state"]
+        m.zero_()
+        v.zero_()
+        steps = 0
+        for i, k in live:
+            st = state.get(order[i])
+            if st is None:
+                continue
+            shape = ac._table.shape[k]
+            if tuple(st["exp_avg"].shape) != shape:
+                raise ValueError(f"optimizer state of {k}: shape {tuple(st['exp_avg'].shape)} != {shape}")
+            idx = ac._idx[k]
+            m[idx] = st["exp_avg"].to(m.device, torch.float32).reshape(-1)
+            v[idx] = st["exp_avg_sq"].to(v.device, torch.float32).reshape(-1)
+            steps = max(steps, int(float(st["step"])))
+        self._alg._pending_steps[self._which] = steps
         if self._which == "main":
-            self._alg.learning_rate = float(sd["lr"])
+            self._alg.learning_rate = float(groups[0]["lr"])
 
 
 class PPO:

@@ -9,6 +9,8 @@ import statistics
 import time
 from collections import deque
 
+import collections
+
 import torch
 
 from ..algorithms import PPO
@@ -141,15 +143,15 @@ class OnPolicyRunner:
     def save(self, path, infos=None):
         """Same checkpoint dict as the reference (:249-255): model + main optimizer only (the VAE optimizer state is
         not saved there either)."""
-        torch.save({"model_state_dict": {k: v.cpu() for k, v in self.alg.actor_critic.state_dict().items()},
-                    "optimizer_state_dict": {k: (v.cpu() if torch.is_tensor(v) else v)
-                                             for k, v in self.alg.optimizer.state_dict().items()},
-                    "iter": self.current_learning_iteration, "infos": infos}, path)
+        osd = self.alg.optimizer.state_dict()  # torch.optim.Adam's own layout (per-parameter exp_avg / exp_avg_sq / step)
+        osd["state"] = {i: {k: v.cpu() for k, v in st.items()} for i, st in osd["state"].items()}
+        torch.save({"model_state_dict": collections.OrderedDict((k, v.cpu()) for k, v in self.alg.actor_critic.state_dict().items()),
+                    "optimizer_state_dict": osd, "iter": self.current_learning_iteration, "infos": infos}, path)
 
     def load(self, path, load_optimizer=True):
         loaded_dict = torch.load(path, map_location="cpu", weights_only=True)
         self.alg.actor_critic.load_state_dict(loaded_dict["model_state_dict"])
-        if load_optimizer and loaded_dict.get("optimizer_state_dict", {}).get("layout") == "dtc_b200.flat":
+        if load_optimizer:
             self.alg.optimizer.load_state_dict(loaded_dict["optimizer_state_dict"])
         self.current_learning_iteration = loaded_dict["iter"]
         return loaded_dict["infos"]

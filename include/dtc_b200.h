@@ -28,6 +28,9 @@ int dtc_struct_size(int which);
 /* bench.py roofline leg: CUDA events around every GEMM-family and foothold launch while enabled */
 void dtc_profile_enable(int on);
 int dtc_profile_read(double* gemm_flops, double* gemm_ms, int64_t* gemm_launches, double* foothold_ms, int64_t* foothold_launches);
+/* per-kind totals of the last dtc_profile_read: 0 = GEMM family except the CTA-pair kernel, 1 = foothold kernel,
+ * 2 = CTA-pair tcgen05 GEMM (work = 2*M*N*K fp32-equivalent flops) */
+int dtc_profile_kind(int kind, double* work, double* ms, int64_t* launches);
 
 /* ------------------------------------------------------------------ environment half */
 

@@ -423,6 +423,81 @@ def test_adam_and_clip_match_torch(which):
         assert calg.learning_rate == pytest.approx(lr, rel=1e-12)
 
 
+def test_checkpoint_interchange_with_torch_adam(tmp_path):
+    """a `model_*.pt` as the reference's OnPolicyRunner.save writes it (on_policy_runner.py:249-255: state_dict of
+    the nn.Module + state_dict of torch.optim.Adam over actor_critic.parameters()) resumes on the CUDA path, and the CUDA path
+    exports the same layout.  Three optimizer steps on identical gradients on both sides, checkpoint written by the torch side,
+    resumed into a fresh CUDA learner, one more step everywhere."""
+    from dtc_b200.rsl_rl.modules import ActorCriticDecoder
+    from dtc_b200.rsl_rl.modules.actor_critic_decoder import STATE_KEYS
+    from dtc_b200.rsl_rl.algorithms import PPO
+    oac, cac, _ = _make_policies(21)
+    assert [k for k, _ in oac.named_parameters()] == list(STATE_KEYS)
+    opt = torch.optim.Adam(oac.parameters(), lr=1e-3)
+    calg = PPO(cac, learning_rate=1e-3, schedule="fixed", device=DEV)
+    lib, st = B.lib(), B.stream_ptr()
+    b0, b1 = cac._table.ranges["policy"]
+    piggy = cac._table.ranges["policy_sync"][1] - 4
+    g = torch.Generator().manual_seed(5)
+
+    def step(algs, seed_scale):
+        grad = torch.randn(b1 - b0, generator=g) * seed_scale  # global norm < 1: the clip does not engage
+        for alg in algs:
+            ac = alg.actor_critic
+            h = ac._learner(64)
+            alg._push_lr(h)
+            if alg._pending_steps:
+                a, b = C.c_int64(), C.c_int64()
+                lib.dtc_learner_get_adam_steps(h, C.byref(a), C.byref(b))
+                lib.dtc_learner_set_adam_steps(h, alg._pending_steps.get("vae", a.value), alg._pending_steps.get("main", b.value))
+                alg._pending_steps = {}
+            ac._grads.zero_()
+            ac._grads[b0:b1] = grad.to(DEV)
+            ac._grads[piggy] = 0.01 * 1000
+            hp = alg._hparams()
+            B.check(lib.dtc_optimizer_apply(h, 1, C.byref(hp), 1.0, 1000, st), "apply")
+        per_key = _grads_as_state_dict(algs[0].actor_critic)
+        live = {k for k in STATE_KEYS if b0 <= int(cac._table.index[k].min()) and int(cac._table.index[k].max()) < b1}
+        for k, p in oac.named_parameters():
+            p.grad = per_key[k].cpu() if k in live else None
+        opt.step()
+        return live
+
+    for i in range(3):
+        live = step([calg], 1e-4)
+    ours, theirs = calg.optimizer.state_dict(), opt.state_dict()
+    assert ours["param_groups"][0]["params"] == theirs["param_groups"][0]["params"]
+    assert set(ours["state"].keys()) == set(theirs["state"].keys()) and len(ours["state"]) == len(live) == 31
+    for i, stt in theirs["state"].items():
+        assert float(ours["state"][i]["step"]) == float(stt["step"]) == 3.0
+        for key in ("exp_avg", "exp_avg_sq"):
+            a, b_ = ours["state"][i][key].cpu(), stt[key]
+            assert a.shape == b_.shape
+            assert torch.allclose(a, b_, rtol=1e-5, atol=1e-12), (STATE_KEYS[i], key, (a - b_).abs().max())
+    # the reference side writes the checkpoint; a fresh CUDA learner resumes from it
+    path = str(tmp_path / "model_7.pt")
+    torch.save({"model_state_dict": oac.state_dict(), "optimizer_state_dict": opt.state_dict(), "iter": 7, "infos": None}, path)
+    loaded = torch.load(path, map_location="cpu", weights_only=True)
+    cac2 = ActorCriticDecoder(53, 1389, 12).to(DEV)
+    calg2 = PPO(cac2, learning_rate=3e-4, schedule="fixed", device=DEV)
+    cac2.load_state_dict(loaded["model_state_dict"])
+    calg2.optimizer.load_state_dict(loaded["optimizer_state_dict"])
+    assert calg2.learning_rate == pytest.approx(1e-3)
+    step([calg, calg2], 1e-4)
+    p1, p2 = cac._flat[b0:b1].cpu(), cac2._flat[b0:b1].cpu()
+    assert (p1 - p2).abs().max().item() <= 2e-7, "resumed learner diverges from the uninterrupted one"
+    sd = cac2.state_dict()
+    for k, p in oac.named_parameters():
+        assert torch.allclose(sd[k].cpu(), p.detach(), rtol=0, atol=3e-7), k
+    assert float(calg2.optimizer.state_dict()["state"][0]["step"]) == 4.0
+    # and the file this side writes loads into torch.optim.Adam over the reference module
+    opt2 = torch.optim.Adam(oac.parameters(), lr=1.0)
+    osd = calg2.optimizer.state_dict()
+    osd["state"] = {i: {k: v.cpu() for k, v in s_.items()} for i, s_ in osd["state"].items()}
+    opt2.load_state_dict(osd)
+    assert opt2.param_groups[0]["lr"] == pytest.approx(1e-3)
+
+
 def test_policy_step_gradients(engine):
     """Raw gradients of one policy step (sync_grads=1) against autograd, incl. the outlier->median gradient routing."""
     oac, cac, rng = _make_policies(6)
