@@ -30,8 +30,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 T_STEPS = 24
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of k_gemm_tc2 from the committed ncu --set full capture (profiles/)
-TRAFFIC_GEMM_TC2 = None
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_gemm_tc2 launch from the committed ncu --set full capture
+# (profiles/r1_gemm_tc2_ncu_raw.csv: dgrad 24576 x 693 x 512, 103.94 MB read + 37.52 MB written; algorithmic 100.7 MB of operands +
+# 68.4 MB of output, part of which is still L2-resident when the kernel ends)
+TRAFFIC_GEMM_TC2 = 141465344
+TRAFFIC_FOOTHOLD_16384 = 11525376
 BYTES_STATE_PER_ENV = (13 + 12 * 2 + 17 * 3 + 17 * 13) * 4  # root, dof, contact, rigid body
 
 
@@ -206,7 +209,9 @@ def run_cuda(args):
         fh_us = fms.value * 1e3 / max(1, n_f.value)
         fh = {"kernel": "k_foothold", "bound": "hbm", "achieved": round(fh_bytes / (fh_us * 1e-6) / 1e9, 1), "peak": peaks["hbm"],
               "unit": "GB/s", "frac": round(fh_bytes / (fh_us * 1e-6) / 1e9 / peaks["hbm"], 4), "us_per_launch": round(fh_us, 2),
-              "envs": N, "traffic": None}
+              "envs": N, "traffic": TRAFFIC_FOOTHOLD_16384,
+              "traffic_note": "ncu --set full at 16384 envs (profiles/r1_foothold_v5_ncu_raw.csv): 10.82 MB read + 0.71 MB written per launch; "
+                              "the 46 MB of outputs stay L2-resident for the consumer kernels, so DRAM traffic is below the algorithmic bytes"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -672,10 +672,17 @@ k_foothold_v5(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const i
     gyk[k] = cfg->grid_y[iy];
     if (!SEP) { p0k[k] = cfg->plane_op[p]; p1k[k] = cfg->plane_op[NP + p]; }
   }
-  // window slots of the per-leg 7x7 search
-  int wi_k[2], wj_k[2];
-#pragma unroll
-  for (int k = 0; k < 2; ++k) { const int slot = lane + 32 * k; wi_k[k] = slot / 7 - 3; wj_k[k] = slot - (slot / 7) * 7 - 3; }
+  // window slots of the per-leg search: the 7x7 lattice window around the cell nearest to the nominal foothold minus its four
+  // corners (>= 0.177 m away, never inside the 0.16 m radius) = 45 candidates.  Two legs share three passes: slots 0..31 of
+  // each leg fill one pass, slots 32..44 of both legs share the third (lanes 0..12 / 16..28).
+  auto slot_offset = [](int s, int& wi, int& wj) {
+    const int r = s < 5 ? s + 1 : (s < 40 ? s + 2 : s + 3);  // raw 7x7 index with the corners 0, 6, 42, 48 skipped
+    wi = r / 7 - 3; wj = r - (r / 7) * 7 - 3;
+  };
+  int wi_a, wj_a, wi_c, wj_c;
+  slot_offset(lane, wi_a, wj_a);
+  slot_offset(32 + min(lane & 15, 12), wi_c, wj_c);
+  const bool c_live = (lane & 15) < 13;
 
   int buf = 0;
   V5Env E = v5_prepare(cfg, b, min3, n, lane, S.patch[0], P);
@@ -815,36 +822,54 @@ k_foothold_v5(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const i
     }
     int my_idx = 0x7fffffff, my_nom = 0x7fffffff;  // results of leg `lane` (lanes 0..3)
     bool need_fallback = false;
+    // one candidate of leg `leg` at window offset (wi, wj): distance to the nominal foothold, admissibility, combined score
+    auto candidate = [&](int leg, int wi, int wj, bool live, unsigned& db, unsigned& vb, int& p, bool& in_r, bool& adm) {
+      const float lpfx = __shfl_sync(0xffffffffu, pfx, leg), lpfy = __shfl_sync(0xffffffffu, pfy, leg);
+      const int i = __shfl_sync(0xffffffffu, ci, leg) + wi, j = __shfl_sync(0xffffffffu, cj, leg) + wj;
+      const bool valid = live && i >= 0 && i < GXN && j >= 0 && j < GYN;
+      const int ic = min(max(i, 0), GXN - 1), jc = min(max(j, 0), GYN - 1);
+      p = ic * GYN + jc;
+      const float4 a = S.tx[ic], c = S.ty[jc];
+      const float wx = __fadd_rn(__fadd_rn(__fadd_rn(a.x, c.y), a.y), root_x);
+      const float wy = __fadd_rn(__fadd_rn(__fadd_rn(c.x, a.z), c.z), root_y);
+      const float ddx = __fsub_rn(lpfx, wx), ddy = __fsub_rn(lpfy, wy);
+      const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
+      const unsigned em = __shfl_sync(0xffffffffu, excm, p & 31);
+      in_r = valid && d < 0.16f;
+      adm = in_r && !((em >> (p >> 5)) & 1u);
+      const float v = __fadd_rn(__fmul_rn(score(p, ic, jc), 0.2f), __fmul_rn(d, 0.8f));
+      db = __float_as_uint(d); vb = __float_as_uint(v);
+    };
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
-      const float lpfx = __shfl_sync(0xffffffffu, pfx, l), lpfy = __shfl_sync(0xffffffffu, pfy, l);
-      const int lci = __shfl_sync(0xffffffffu, ci, l), lcj = __shfl_sync(0xffffffffu, cj, l);
-      unsigned bs = 0x7f7fffffu, bd = 0x7f7fffffu;  // value bits; FLT_MAX = nothing found
-      int bsi = 0x7fffffff, bdi = 0x7fffffff;
+    for (int lp = 0; lp < 2; ++lp) {
+      const int l0 = 2 * lp, l1 = l0 + 1;
+      unsigned bs[2] = {0x7f7fffffu, 0x7f7fffffu}, bd[2] = {0x7f7fffffu, 0x7f7fffffu};  // value bits; FLT_MAX = nothing found
+      int bsi[2] = {0x7fffffff, 0x7fffffff}, bdi[2] = {0x7fffffff, 0x7fffffff};
+      unsigned db, vb;
+      int p;
+      bool in_r, adm;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {  // passes A and B: slots 0..31 of leg l0 / l1
+        candidate(k == 0 ? l0 : l1, wi_a, wj_a, true, db, vb, p, in_r, adm);
+        if (in_r) { bd[k] = db; bdi[k] = p; }
+        if (adm) { bs[k] = vb; bsi[k] = p; }
+      }
+      // pass C: slots 32..44 of both legs (lanes 0..12 -> l0, lanes 16..28 -> l1)
+      candidate(lane < 16 ? l0 : l1, wi_c, wj_c, c_live, db, vb, p, in_r, adm);
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const int i = lci + wi_k[k], j = lcj + wj_k[k];
-        const bool valid = (k == 0 || lane < 49 - 32) && i >= 0 && i < GXN && j >= 0 && j < GYN;
-        const int ic = min(max(i, 0), GXN - 1), jc = min(max(j, 0), GYN - 1);
-        const int p = ic * GYN + jc;
-        const float4 a = S.tx[ic], c = S.ty[jc];
-        const float wx = __fadd_rn(__fadd_rn(__fadd_rn(a.x, c.y), a.y), root_x);
-        const float wy = __fadd_rn(__fadd_rn(__fadd_rn(c.x, a.z), c.z), root_y);
-        const float ddx = __fsub_rn(lpfx, wx), ddy = __fsub_rn(lpfy, wy);
-        const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
-        const unsigned em = __shfl_sync(0xffffffffu, excm, p & 31);
-        const bool in_r = valid && d < 0.16f;
-        const bool adm = in_r && !((em >> (p >> 5)) & 1u);
-        const float v = __fadd_rn(__fmul_rn(score(p, ic, jc), 0.2f), __fmul_rn(d, 0.8f));
-        const unsigned db = __float_as_uint(d), vb = __float_as_uint(v);
-        if (in_r && (db < bd || (db == bd && p < bdi))) { bd = db; bdi = p; }
-        if (adm && (vb < bs || (vb == bs && p < bsi))) { bs = vb; bsi = p; }
+        const bool mine = (lane < 16) == (k == 0);
+        if (mine && in_r && (db < bd[k] || (db == bd[k] && p < bdi[k]))) { bd[k] = db; bdi[k] = p; }
+        if (mine && adm && (vb < bs[k] || (vb == bs[k] && p < bsi[k]))) { bs[k] = vb; bsi[k] = p; }
       }
-      int ri, rn;
-      v5_argmin(bs, bsi, ri);
-      v5_argmin(bd, bdi, rn);
-      if (lane == l) { my_idx = ri; my_nom = rn; }
-      need_fallback |= (ri == 0x7fffffff);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        int ri, rn;
+        v5_argmin(bs[k], bsi[k], ri);
+        v5_argmin(bd[k], bdi[k], rn);
+        if (lane == l0 + k) { my_idx = ri; my_nom = rn; }
+        need_fallback |= (ri == 0x7fffffff);
+      }
     }
     int fbi = 0;
     if (need_fallback) {  // warp-uniform: argmin_p (exc ? 10 : 0.2 s_p + 8), lowest index on ties

@@ -281,9 +281,13 @@ extern "C" void dtc_learner_destroy(dtc_learner* l) {
 // optimizer), and the 512-wide activation-gradient chain that is the critical path.  The step forks the first two onto side
 // streams (events, no host synchronisation) so that they run in the shadow of the big tensor-core GEMMs and fill the tails of
 // their persistent grids; everything is joined back into the caller's stream before the call returns.
-static int g_overlap = 1;
+static int g_overlap = -1;  // -1: not read yet (env DTC_OVERLAP=0 disables)
+static int overlap_on() {
+  if (g_overlap < 0) { const char* e = getenv("DTC_OVERLAP"); g_overlap = (e && e[0] == '0') ? 0 : 1; }
+  return g_overlap;
+}
 extern "C" void dtc_set_overlap(int on) { g_overlap = on ? 1 : 0; }
-extern "C" int dtc_get_overlap(void) { return g_overlap; }
+extern "C" int dtc_get_overlap(void) { return overlap_on(); }
 
 struct StepStreams { cudaStream_t main, w, c; };  // w: weight gradients + critic forward; c: CENet chains + critic backward
 
@@ -298,7 +302,7 @@ static int chain(dtc_learner* l, cudaStream_t from, cudaStream_t to) {
 }
 static int streams_begin(dtc_learner* l, cudaStream_t st, StepStreams* S) {
   S->main = S->w = S->c = st;
-  if (!g_overlap || g_dtc_prof) return DTC_OK;  // per-launch profiling wants every kernel alone on the device
+  if (!overlap_on() || g_dtc_prof) return DTC_OK;  // per-launch profiling wants every kernel alone on the device
   if (!l->side_ready) {
     for (int i = 0; i < 2; ++i) DTC_CUDA(cudaStreamCreateWithFlags(&l->side[i], cudaStreamNonBlocking));
     for (int i = 0; i < DTC_NEV; ++i) DTC_CUDA(cudaEventCreateWithFlags(&l->ev[i], cudaEventDisableTiming));

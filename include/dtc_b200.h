@@ -290,6 +290,18 @@ int dtc_get_gemm_pair(void);
 void dtc_set_overlap(int on);
 int dtc_get_overlap(void);
 
+/* ------------------------------------------------------------------ P14 / SURVEY 8f N2: the optional GRU `Memory`
+ * Memory.forward / Memory.reset (rsl_rl/rsl_rl/modules/actor_critic_decoder.py:584-614): nn.GRU(input_size, hidden_size,
+ * num_layers) over T time steps for N rows.  `weights`: per layer weight_ih_l [3H,in_l] | weight_hh_l [3H,H] | bias_ih_l [3H] |
+ * bias_hh_l [3H] back to back (nn.GRU's parameter and gate order r|z|n; dtc_gru_param_floats gives the total).
+ * x [T,N,input_size]; h [num_layers,N,H] initial hidden state in, final hidden state out; out [T,N,H] top-layer outputs
+ * (may be NULL for a single layer).  The reference never instantiates Memory on its training path. */
+int64_t dtc_gru_param_floats(int32_t input_size, int32_t hidden_size, int32_t num_layers);
+int dtc_gru_forward(int32_t T, int32_t N, int32_t input_size, int32_t hidden_size, int32_t num_layers, const float* weights,
+                    const float* x, float* h, float* out, void* stream);
+/* hidden_state[..., dones, :] = 0 (Memory.reset, actor_critic_decoder.py:609-613) */
+int dtc_gru_reset(int32_t N, int32_t hidden_size, int32_t num_layers, float* h, const uint8_t* dones, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

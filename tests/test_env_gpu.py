@@ -177,6 +177,38 @@ def test_foothold_variants_agree(N, kind):
                 assert torch.equal(a, b), f"{nme} rep{rep}: {int((a != b).sum())} mismatches"
 
 
+def test_heightmap_update_rebuilds_the_min3_table():
+    """The default kernel samples a library-owned table derived from height_samples at bind time; after an in-place terrain
+    edit dtc_env_heightmap_updated() must bring it back in step with the brute-force variant (which reads height_samples)."""
+    import ctypes as C
+    from dtc_b200 import _lib as B
+    from dtc_b200.legged_gym.envs import LeggedRobotDTC, Lite3DTCCfg
+    N, dev = 1024, "cuda"
+    hs, tor = sim_stub.make_heightmap("stones", 0)
+    layout = sim_stub.initial_env_layout(N, tor, 1)
+    fg = sim_stub.FakeGym(N, device=dev)
+    cfg = Lite3DTCCfg()
+    cfg.env.num_envs = N
+    env = LeggedRobotDTC(cfg, sim_device=dev, gym=fg, height_samples=hs, terrain_origins=tor, layout=layout, seed=1)
+    g = torch.Generator(device=dev).manual_seed(2)
+    fg.load(sim_stub.synth_state(N, env.env_origins, g, device=dev))
+    env.reset()
+    fg.load(sim_stub.synth_state(N, env.env_origins, g, device=dev))
+    stp = B.stream_ptr()
+
+    def heights(v):
+        B.check(env.lib.dtc_foothold_step(env._h, v, C.c_void_p(0), stp), "foothold")
+        torch.cuda.synchronize()
+        return env.measured_heights.clone()
+
+    assert torch.equal(heights(0), heights(5))
+    env.height_samples.add_(torch.randint(-40, 40, env.height_samples.shape, device=dev, generator=g, dtype=torch.int16))
+    h0 = heights(0)
+    assert not torch.equal(h0, heights(5)), "stale table expected before the update call"
+    B.check(env.lib.dtc_env_heightmap_updated(env._h), "heightmap_updated")
+    assert torch.equal(h0, heights(5))
+
+
 def test_philox_noise_statistics():
     """Production mode (no injected draws): in-kernel Philox noise has the reference's distribution."""
     N = 2048

@@ -439,9 +439,12 @@ def test_checkpoint_interchange_with_torch_adam(tmp_path):
     b0, b1 = cac._table.ranges["policy"]
     piggy = cac._table.ranges["policy_sync"][1] - 4
     g = torch.Generator().manual_seed(5)
+    covered = torch.zeros(cac._flat.numel())
+    for k in STATE_KEYS:
+        covered[cac._table.index[k]] = 1.0  # zero-pad columns of the flat layout never see a gradient in training
 
     def step(algs, seed_scale):
-        grad = torch.randn(b1 - b0, generator=g) * seed_scale  # global norm < 1: the clip does not engage
+        grad = torch.randn(b1 - b0, generator=g) * seed_scale * covered[b0:b1]  # global norm < 1: the clip does not engage
         for alg in algs:
             ac = alg.actor_critic
             h = ac._learner(64)
@@ -473,7 +476,8 @@ def test_checkpoint_interchange_with_torch_adam(tmp_path):
         for key in ("exp_avg", "exp_avg_sq"):
             a, b_ = ours["state"][i][key].cpu(), stt[key]
             assert a.shape == b_.shape
-            assert torch.allclose(a, b_, rtol=1e-5, atol=1e-12), (STATE_KEYS[i], key, (a - b_).abs().max())
+            # fp32 moment updates: fma / rounding order differs from torch's foreach kernels by a few ulp of the largest entries
+            assert (a - b_).abs().max().item() <= 1e-5 * b_.abs().max().item() + 1e-30, (STATE_KEYS[i], key, (a - b_).abs().max())
     # the reference side writes the checkpoint; a fresh CUDA learner resumes from it
     path = str(tmp_path / "model_7.pt")
     torch.save({"model_state_dict": oac.state_dict(), "optimizer_state_dict": opt.state_dict(), "iter": 7, "infos": None}, path)
@@ -485,7 +489,16 @@ def test_checkpoint_interchange_with_torch_adam(tmp_path):
     assert calg2.learning_rate == pytest.approx(1e-3)
     step([calg, calg2], 1e-4)
     p1, p2 = cac._flat[b0:b1].cpu(), cac2._flat[b0:b1].cpu()
-    assert (p1 - p2).abs().max().item() <= 2e-7, "resumed learner diverges from the uninterrupted one"
+    if (p1 - p2).abs().max().item() > 2e-7:
+        sd1, sd2 = cac.state_dict(), cac2.state_dict()
+        o1, o2 = calg.optimizer.state_dict()["state"], calg2.optimizer.state_dict()["state"]
+        rep = []
+        for i, k in enumerate(STATE_KEYS):
+            d = (sd1[k] - sd2[k]).abs().max().item()
+            if d > 2e-7:
+                rep.append((k, d, (o1[i]["exp_avg"] - o2[i]["exp_avg"]).abs().max().item() if i in o1 else None,
+                            (o1[i]["exp_avg_sq"] - o2[i]["exp_avg_sq"]).abs().max().item() if i in o1 else None))
+        raise AssertionError(f"resumed learner diverges from the uninterrupted one: {rep}")
     sd = cac2.state_dict()
     for k, p in oac.named_parameters():
         assert torch.allclose(sd[k].cpu(), p.detach(), rtol=0, atol=3e-7), k
