@@ -310,6 +310,20 @@ __global__ void k_colsum2(const float* __restrict__ ws, int N, float* __restrict
 int dtc_gemm_pick_splits(int M, int N, int K) {
   const int tc_min = ceil_div(ceil_div(K, 32), 32);  // the tensor-core path keeps <= 32 k-blocks per TMEM accumulation
   if (K < 2048) return tc_min;
+  if (M > 128 && N >= 100) {
+    // CTA-pair kernel (256 x 128 tiles on 74 SM pairs): the split count that minimises rounds x k-blocks per split, e.g.
+    // 512 x 693 over 24 576 rows: 24 splits = 288 tiles = 4 rounds of 32 k-blocks instead of 25 splits = 5 rounds of 31
+    const int pt = ceil_div(M, 256) * ceil_div(N, 128), nkb = ceil_div(K, 32), pairs = 74;
+    int best = tc_min < 1 ? 1 : tc_min;
+    long best_cost = -1;
+    for (int c = best; c <= best + 24 && c <= nkb; ++c) {
+      if ((long)pt * c < pairs && c < best + 24) continue;  // too few tiles for the pair kernel
+      // + the partial-tile round trip through the workspace: one split of a 512 x 693 output costs about 2.4 k-blocks of MMA time
+      const long cost = 5 * (long)ceil_div((long)pt * c, pairs) * ceil_div(nkb, c) + (long)pt * c;
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }
+    }
+    return best;
+  }
   int bm = M > 64 ? 128 : (M > 32 ? 64 : 32), bn = N > 64 ? 128 : 64;
   int tiles = ceil_div(M, bm) * ceil_div(N, bn);
   int s = ceil_div(592, tiles);

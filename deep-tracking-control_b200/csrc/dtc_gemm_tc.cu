@@ -729,7 +729,12 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   if (a.A_lo) RETURN_IF_ERR(tc_get_map(a.A_lo, a.M, a.K, a.lda, amaj, &mAlo)); else mAlo = mA;
   if (a.B_lo) RETURN_IF_ERR(tc_get_map(a.B_lo, a.N, a.K, a.ldb, bmap, &mBlo)); else mBlo = mB;
   const int ntiles = use_pair ? pair_tiles : ceil_div(a.N, TC_BN) * ceil_div(a.M, TC_BM) * splits;
-  dim3 grid(use_pair ? 2 * (ntiles < num_sms / 2 ? ntiles : num_sms / 2) : (ntiles < num_sms ? ntiles : num_sms));
+  // persistent grid: the tile list takes R = ceil(tiles / units) rounds whatever happens, so launch only ceil(tiles / R) units -
+  // same makespan, and the SMs left over run the side streams' small kernels (nothing can co-reside with these CTAs)
+  const int units = use_pair ? num_sms / 2 : num_sms;
+  const int rounds = ceil_div(ntiles, units);
+  const int used = ceil_div(ntiles, rounds);
+  dim3 grid(use_pair ? 2 * used : used);
   dtc_prof_begin(st, use_pair ? 2 : 0, 2.0 * a.M * a.N * a.K);
   int rc;
   if (use_pair) {
