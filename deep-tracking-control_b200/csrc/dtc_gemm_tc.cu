@@ -1,6 +1,8 @@
-// Tensor-core GEMM for the MLP stack on sm_100a: tcgen05.mma kind::tf32 with TMEM accumulators, operands staged by TMA
-// into 128-byte-swizzled shared memory, three-stage mbarrier pipeline, warp-specialised (TMA producer / MMA issuer /
-// TMEM allocator / 4 epilogue warps).
+// Tensor-core GEMMs for the MLP stack on sm_100a: tcgen05.mma kind::tf32 with TMEM accumulators, operands staged by TMA
+// into 128-byte-swizzled shared memory, 3-4 stage mbarrier pipeline, warp-specialised (TMA producer / MMA issuer /
+// TMEM allocator / 8 epilogue warps), persistent over the tile list.  Two kernels share the epilogue:
+//   k_gemm_tc   one CTA per 128x128 tile (rollout shapes, narrow layers),
+//   k_gemm_tc2  a CTA pair (cta_group::2) per 256x128 tile, B halves shared across the TPC (the 24 576-row update shapes).
 //
 // fp32 accuracy (the 1e-5 parity bar) comes from error-compensated 3xTF32: the tensor core TRUNCATES fp32 operands to
 // TF32 (measured, tools/tc_probe.cu), so with  x_lo = rn_tf32(x - trunc_tf32(x))  kept next to every operand,
@@ -60,31 +62,9 @@ __device__ __forceinline__ void tc_tma_2d(uint32_t dst, const CUtensorMap* map, 
                "l"((uint64_t)map), "r"(tc_smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
 }
-// L2 prefetch of one TMA box (no shared memory, no barrier): the activation operands stream from DRAM once per GEMM and a
-// 3-4 stage smem ring (2300-3000 MMA cycles of lookahead) does not cover a loaded DRAM round trip
-__device__ __forceinline__ void tc_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1) : "memory");
-}
-#define TC_PF_DIST 0  // k-blocks of L2 look-ahead; 0 = off (measured: 8 blocks ahead made every shape 5-20 % slower)
-
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | layout <<61
-__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)layout_type << 61);
-}
-template <int MAJ>
-__device__ __forceinline__ uint64_t tc_operand_desc(uint32_t tile, int k8) {
-  // K-major : rows of 128 B (32 k), 8-row swizzle atoms 1024 B apart; one MMA (K = 8) advances 32 B inside the row
-  // MN-major: 4 blocks (32 mn each, 4096 B apart) of 32 k-rows x 128 B, 4-row swizzle atoms 512 B apart; one MMA = 8 k-rows
-  return MAJ == 0 ? tc_desc(tile + k8 * 32, 16, 1024, 2) : tc_desc(tile + k8 * 1024, 4096, 512, 1);
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
-      : "memory");
-}
+// shared-memory matrix descriptors (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | layout <<61.
+//   K-major : rows of 128 B (32 k), 8-row swizzle atoms 1024 B apart (SBO), LBO 16; one MMA (K = 8) advances 32 B inside the row
+//   MN-major: blocks of 32 mn (4096 B apart = LBO) of 32 k-rows x 128 B, 4-row swizzle atoms 512 B apart (SBO); one MMA = 8 k-rows
 // one elected lane of a converged warp (CUTLASS elect_one_sync): unlike `lane == 0`, ptxas knows the guarded region has a single
 // active thread and issues UTMALDG / UTCHMMA / UTCBAR straight from uniform registers instead of wrapping each in an ELECT loop
 __device__ __forceinline__ bool tc_elect_one() {
@@ -290,43 +270,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     // ------------------------------------------------------------ TMA producer
     const uint32_t bytes = TC_TILE_BYTES * (2 + p.has_alo + p.has_blo);
     int it = 0;
-    // look-ahead cursor of the L2 prefetch: TC_PF_DIST k-blocks ahead of the loads, across tile boundaries
-    int pt = blockIdx.x, pkb = 0, pkb1 = 0, pm0 = 0, pn0 = 0;
-    auto pf_open = [&]() {
-      if (pt < ntiles) {
-        const int z = pt / (nt_n * nt_m);
-        pn0 = (pt % nt_n) * TC_BN; pm0 = ((pt / nt_n) % nt_m) * TC_BM;
-        pkb = z * p.kb_per_split; pkb1 = min(p.nkb, pkb + p.kb_per_split);
-      }
-    };
-    auto pf_step = [&]() {
-      if (pt >= ntiles) return;
-      if (AMAJ == 0) {
-        tc_prefetch_2d(&mapA, pkb * TC_BK, pm0);
-        if (p.has_alo) tc_prefetch_2d(&mapAlo, pkb * TC_BK, pm0);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          tc_prefetch_2d(&mapA, pm0 + 32 * j, pkb * TC_BK);
-          if (p.has_alo) tc_prefetch_2d(&mapAlo, pm0 + 32 * j, pkb * TC_BK);
-        }
-      }
-      if (BMAJ == 1 && AMAJ == 1) {  // weight gradients: the second operand streams as well
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          tc_prefetch_2d(&mapB, pn0 + 32 * j, pkb * TC_BK);
-          if (p.has_blo) tc_prefetch_2d(&mapBlo, pn0 + 32 * j, pkb * TC_BK);
-        }
-      }
-      if (++pkb >= pkb1) { pt += gridDim.x; pf_open(); }
-    };
-    pf_open();
-    for (int i = 0; i < TC_PF_DIST; ++i) pf_step();
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const int n0 = (t % nt_n) * TC_BN, m0 = ((t / nt_n) % nt_m) * TC_BM, z = t / (nt_n * nt_m);
       const int kb0 = z * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
-        if (TC_PF_DIST > 0) pf_step();
         const int s = it % TC_STAGES;
         tc_mbar_wait(&bar_empty[s], ((it / TC_STAGES) & 1) ^ 1);
         tc_mbar_expect_tx(&bar_full[s], bytes);
@@ -439,24 +386,12 @@ __device__ __forceinline__ void tc2_tma_2d(uint32_t dst, const CUtensorMap* map,
                "l"((uint64_t)map), "r"(bar_cluster), "r"(c0), "r"(c1)
                : "memory");
 }
-__device__ __forceinline__ void tc2_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // arrives (once all MMAs issued so far have completed) on the barrier at the same shared-memory offset in both CTAs of the pair
 __device__ __forceinline__ void tc2_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)),
                "h"((uint16_t)3)
                : "memory");
 }
-template <int MAJ>
-__device__ __forceinline__ uint64_t tc2_b_desc(uint32_t tile, int k8) {  // 64-row B half: same atoms as tc_operand_desc, two MN blocks
-  return MAJ == 0 ? tc_desc(tile + k8 * 32, 16, 1024, 2) : tc_desc(tile + k8 * 1024, 4096, 512, 1);
-}
-
 template <int AMAJ, int BMAJ>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapB,
@@ -491,44 +426,11 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     // ------------------------------------------------------------ TMA producer (both CTAs)
     const uint32_t bytes_cta = (uint32_t)(TC2_A_BYTES * (1 + p.has_alo) + TC2_B_BYTES * (1 + p.has_blo));
     int it = 0;
-    // look-ahead cursor of the L2 prefetch: TC_PF_DIST k-blocks ahead of the loads, across tile boundaries
-    int pt = pair, pkb = 0, pkb1 = 0, pm0 = 0, pn0 = 0;
-    auto pf_open = [&]() {
-      if (pt < ntiles) {
-        const int z = pt / (nt_n * nt_m);
-        pn0 = (pt % nt_n) * TC_BN + (int)rank * (TC_BN / 2); pm0 = ((pt / nt_n) % nt_m) * (2 * TC_BM) + (int)rank * TC_BM;
-        pkb = z * p.kb_per_split; pkb1 = min(p.nkb, pkb + p.kb_per_split);
-      }
-    };
-    auto pf_step = [&]() {
-      if (pt >= ntiles) return;
-      if (AMAJ == 0) {
-        tc_prefetch_2d(&mapA, pkb * TC_BK, pm0);
-        if (p.has_alo) tc_prefetch_2d(&mapAlo, pkb * TC_BK, pm0);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          tc_prefetch_2d(&mapA, pm0 + 32 * j, pkb * TC_BK);
-          if (p.has_alo) tc_prefetch_2d(&mapAlo, pm0 + 32 * j, pkb * TC_BK);
-        }
-      }
-      if (BMAJ == 1 && AMAJ == 1) {  // weight gradients: the second operand streams as well
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          tc_prefetch_2d(&mapB, pn0 + 32 * j, pkb * TC_BK);
-          if (p.has_blo) tc_prefetch_2d(&mapBlo, pn0 + 32 * j, pkb * TC_BK);
-        }
-      }
-      if (++pkb >= pkb1) { pt += npairs; pf_open(); }
-    };
-    pf_open();
-    for (int i = 0; i < TC_PF_DIST; ++i) pf_step();
     for (int t = pair; t < ntiles; t += npairs) {
       const int n0 = (t % nt_n) * TC_BN + (int)rank * (TC_BN / 2), m0 = ((t / nt_n) % nt_m) * (2 * TC_BM) + (int)rank * TC_BM;
       const int z = t / (nt_n * nt_m);
       const int kb0 = z * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
-        if (TC_PF_DIST > 0) pf_step();
         const int s = it % TC2_STAGES;
         tc_mbar_wait(&bar_empty[s], ((it / TC2_STAGES) & 1) ^ 1);
         const uint32_t full = tc_mapa(tc_smem_u32(&bar_full[s]), 0);  // the leader's barrier
