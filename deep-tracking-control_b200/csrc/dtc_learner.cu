@@ -543,23 +543,35 @@ __global__ void __launch_bounds__(256) k_lv_final(int M, LvStat* st) {
 __global__ void __launch_bounds__(256) k_pack_inputs(int M, const float* __restrict__ obs, int obs_ld, const float* __restrict__ hist,
                                                      int hist_ld, const float* __restrict__ priv, int priv_ld,
                                                      const float* __restrict__ bv, int bv_ld, float* __restrict__ xh,
-                                                     float* __restrict__ xp, float* __restrict__ xc) {
+                                                     float* __restrict__ xp, float* __restrict__ xc, float* __restrict__ xh_lo,
+                                                     float* __restrict__ xp_lo, float* __restrict__ xc_lo) {
   const int W = LD_HIST + LD_PRIVA + LD_XC;
   const long long total = (long long)M * W;
   for (long long e = blockIdx.x * 256ll + threadIdx.x; e < total; e += gridDim.x * 256ll) {
     int m = (int)(e / W), c = (int)(e - (long long)m * W);
     if (c < LD_HIST) {
-      if (xh) xh[(size_t)m * LD_HIST + c] = c < 265 ? hist[(size_t)m * hist_ld + c] : 0.f;
+      if (xh) {
+        const float v = c < 265 ? hist[(size_t)m * hist_ld + c] : 0.f;
+        xh[(size_t)m * LD_HIST + c] = v;
+        if (xh_lo) xh_lo[(size_t)m * LD_HIST + c] = tf32_lo(v);  // TF32 companions written here: no separate k_split_lo pass
+      }
     } else if (c < LD_HIST + LD_PRIVA) {
       c -= LD_HIST;
-      if (xp) xp[(size_t)m * LD_PRIVA + c] = c < 693 ? priv[(size_t)m * priv_ld + c] : 0.f;
+      if (xp) {
+        const float v = c < 693 ? priv[(size_t)m * priv_ld + c] : 0.f;
+        xp[(size_t)m * LD_PRIVA + c] = v;
+        if (xp_lo) xp_lo[(size_t)m * LD_PRIVA + c] = tf32_lo(v);
+      }
     } else {
       c -= LD_HIST + LD_PRIVA;
       float v;
       if (c < XC_OBS) v = priv[(size_t)m * priv_ld + 693 + c];
       else if (c < XC_BV) v = obs[(size_t)m * obs_ld + (c - XC_OBS)];
       else v = bv[(size_t)m * bv_ld + (c - XC_BV)];
-      if (xc) xc[(size_t)m * LD_XC + c] = v;
+      if (xc) {
+        xc[(size_t)m * LD_XC + c] = v;
+        if (xc_lo) xc_lo[(size_t)m * LD_XC + c] = tf32_lo(v);
+      }
     }
   }
 }
@@ -570,7 +582,7 @@ __global__ void __launch_bounds__(256) k_pack_inputs(int M, const float* __restr
 __global__ void __launch_bounds__(128) k_latent_fwd(int M, int mode, float* __restrict__ ML, const LvStat* __restrict__ st,
                                                     const float* __restrict__ eps_in, uint64_t seed, uint64_t counter,
                                                     float* __restrict__ EPS, float* __restrict__ OUTM, const float* __restrict__ xc,
-                                                    float* __restrict__ X) {
+                                                    float* __restrict__ X, float* __restrict__ X_lo) {
   const int r8 = threadIdx.x >> 4, j = threadIdx.x & 15;
   const int row = blockIdx.x * 8 + r8;
   const int ldx = mode == 0 ? LD_XA : LD_XD, zoff = mode == 0 ? XA_Z : XD_Z, muoff = mode == 0 ? XA_MU : XD_MU;
@@ -585,14 +597,24 @@ __global__ void __launch_bounds__(128) k_latent_fwd(int M, int mode, float* __re
     float sd = expf(__fmul_rn(0.5f, lv));
     float z = __fadd_rn(__fmul_rn(e, sd), ml[3 + j]);
     float* x = X + (size_t)row * ldx;
+    float* xl = X_lo ? X_lo + (size_t)row * ldx : nullptr;  // the l_t columns' companions come from the TE4 GEMM epilogue
     x[zoff + j] = z;
-    if (j < 4) x[muoff + j] = j < 3 ? ml[j] : 0.f;
+    if (xl) xl[zoff + j] = tf32_lo(z);
+    if (j < 4) {
+      const float mu = j < 3 ? ml[j] : 0.f;
+      x[muoff + j] = mu;
+      if (xl) xl[muoff + j] = tf32_lo(mu);
+    }
     if (j == 0) ml[LD_ML - 1] = 0.f;
   }
   if (mode == 0) {
     for (int e = threadIdx.x; e < 8 * 56; e += 128) {
       int rr = blockIdx.x * 8 + e / 56, c = e % 56;
-      if (rr < M) X[(size_t)rr * LD_XA + XA_OBS + c] = c < 53 ? xc[(size_t)rr * LD_XC + XC_OBS + c] : 0.f;
+      if (rr < M) {
+        const float v = c < 53 ? xc[(size_t)rr * LD_XC + XC_OBS + c] : 0.f;
+        X[(size_t)rr * LD_XA + XA_OBS + c] = v;
+        if (X_lo) X_lo[(size_t)rr * LD_XA + XA_OBS + c] = tf32_lo(v);
+      }
     }
   }
 }
@@ -825,7 +847,7 @@ __global__ void __launch_bounds__(128) k_vae_loss_rows(int M, float inv_rows, co
 // height reconstruction loss (ppo.py:218-223): mse(terrain_decoder(l_t), priv[:, 696:]) and its gradient
 __global__ void __launch_bounds__(256) k_vae_loss_height(int M, float inv_count, const float* __restrict__ HR,
                                                          const float* __restrict__ xc, float* __restrict__ dHR,
-                                                         double* __restrict__ stats) {
+                                                         float* __restrict__ dHR_lo, double* __restrict__ stats) {
   __shared__ double sh[32];
   const long long total = (long long)M * 696;
   double s = 0.0;
@@ -839,6 +861,7 @@ __global__ void __launch_bounds__(256) k_vae_loss_height(int M, float inv_count,
       g = c * d;
     }
     dHR[e] = g;
+    if (dHR_lo) dHR_lo[e] = tf32_lo(g);
   }
   s = block_sum(s, sh);
   if (threadIdx.x == 0) atomicAdd(&stats[ST_HEIGHT], s * (double)inv_count);
@@ -1017,9 +1040,9 @@ static int encode(dtc_learner* l, int M, const float* hist, const float* priv_a,
   RET_IF(fwd(l, TE2, l->T1, 512, l->T2, 512, 1, M, st));
   RET_IF(fwd(l, TE4, l->T2, 512, X, ldx, 0, M, st));
   RET_IF(chain(l, sc, st));
-  k_latent_fwd<<<ceil_div(M, 8), 128, 0, st>>>(M, mode, l->ML, l->lvstat, eps, seed, counter, l->EPS, l->OUTM, xc, X);
+  k_latent_fwd<<<ceil_div(M, 8), 128, 0, st>>>(M, mode, l->ML, l->lvstat, eps, seed, counter, l->EPS, l->OUTM, xc, X, lo_of(l, X));
   DTC_CHECK_LAUNCH("k_latent_fwd");
-  return split_lo(X, lo_of(l, X), (int64_t)M * ldx, st);  // z / mu / obs columns were written outside a GEMM epilogue
+  return DTC_OK;
 }
 
 // backward of encode(): dX holds d l_t | d z | d mu[:3] (layout of X); fills the gradients of CE0, CE2, LAT, TE0..TE4.
@@ -1090,9 +1113,6 @@ extern "C" int dtc_policy_act(dtc_learner* l, int32_t M, const float* obs, int32
     o_val = s->values + b; o_logp = s->logp + b;
   }
   l->last_M = M;
-  k_pack_inputs<<<grid1d((long long)M * (LD_HIST + LD_PRIVA + LD_XC), 256), 256, 0, st>>>(M, obs, obs_ld, hist, hist_ld, priv, priv_ld,
-                                                                                           base_vel, bv_ld, xh, xp, xc);
-  DTC_CHECK_LAUNCH("k_pack_inputs");
   if (s) {
     const size_t b = (size_t)step * s->N;
     l->ext[0] = {xh, (size_t)M * LD_HIST, s->hist_lo ? s->hist_lo + b * LD_HIST : nullptr};
@@ -1101,9 +1121,10 @@ extern "C" int dtc_policy_act(dtc_learner* l, int32_t M, const float* obs, int32
   } else {
     memset(l->ext, 0, sizeof(l->ext));
   }
-  RET_IF(split_lo(xh, lo_of(l, xh), (int64_t)M * LD_HIST, st));
-  RET_IF(split_lo(xp, lo_of(l, xp), (int64_t)M * LD_PRIVA, st));
-  RET_IF(split_lo(xc, lo_of(l, xc), (int64_t)M * LD_XC, st));
+  k_pack_inputs<<<grid1d((long long)M * (LD_HIST + LD_PRIVA + LD_XC), 256), 256, 0, st>>>(M, obs, obs_ld, hist, hist_ld, priv, priv_ld,
+                                                                                           base_vel, bv_ld, xh, xp, xc, lo_of(l, xh),
+                                                                                           lo_of(l, xp), lo_of(l, xc));
+  DTC_CHECK_LAUNCH("k_pack_inputs");
   StepStreams S;
   RET_IF(streams_begin(l, st, &S));
   RET_IF(critic_fwd(l, M, xc, S.w));
@@ -1122,9 +1143,9 @@ extern "C" int dtc_policy_evaluate(dtc_learner* l, int32_t M, const float* obs, 
   if (M <= 0 || M > l->R) DTC_FAIL(DTC_ERR_ARG, "dtc_policy_evaluate: M=%d outside (0,%d]", M, l->R);
   cudaStream_t st = (cudaStream_t)stream;
   k_pack_inputs<<<grid1d((long long)M * (LD_HIST + LD_PRIVA + LD_XC), 256), 256, 0, st>>>(M, obs, obs_ld, nullptr, 0, priv, priv_ld,
-                                                                                           base_vel, bv_ld, nullptr, nullptr, l->XC);
+                                                                                           base_vel, bv_ld, nullptr, nullptr, l->XC, nullptr,
+                                                                                           nullptr, lo_of(l, l->XC));
   DTC_CHECK_LAUNCH("k_pack_inputs");
-  RET_IF(split_lo(l->XC, lo_of(l, l->XC), (int64_t)M * LD_XC, st));
   RET_IF(critic_fwd(l, M, l->XC, st));
   k_copy_col0<<<ceil_div(M, 256), 256, 0, st>>>(M, l->V, 4, values);
   DTC_CHECK_LAUNCH("k_copy_col0");
@@ -1163,10 +1184,9 @@ extern "C" int dtc_policy_act_teacher(dtc_learner* l, int32_t M, const float* ob
   l->last_M = M;
   // base_vel is not an input of this path: the obs pointer doubles as a dummy source for the 3 base_vel columns
   k_pack_inputs<<<grid1d((long long)M * (LD_HIST + LD_PRIVA + LD_XC), 256), 256, 0, st>>>(M, obs, obs_ld, hist, hist_ld, priv, priv_ld,
-                                                                                           obs, obs_ld, l->XH, l->XP, l->XC);
+                                                                                           obs, obs_ld, l->XH, l->XP, l->XC, lo_of(l, l->XH),
+                                                                                           lo_of(l, l->XP), nullptr);
   DTC_CHECK_LAUNCH("k_pack_inputs");
-  RET_IF(split_lo(l->XH, lo_of(l, l->XH), (int64_t)M * LD_HIST, st));
-  RET_IF(split_lo(l->XP, lo_of(l, l->XP), (int64_t)M * LD_PRIVA, st));
   RET_IF(fwd(l, CE0, l->XH, LD_HIST, l->H1, 128, 1, M, st));
   RET_IF(fwd(l, CE2, l->H1, 128, l->E, 64, 0, M, st));
   RET_IF(fwd(l, LAT, l->E, 64, l->ML, LD_ML, 0, M, st));
@@ -1297,9 +1317,9 @@ extern "C" int dtc_vae_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
   k_vae_loss_rows<<<ceil_div(M, 128), 128, 0, sc>>>(M, inv_rows, l->REC, next_obs, l->ML, xc, l->dREC, l->dML, l->stats);
   DTC_CHECK_LAUNCH("k_vae_loss_rows");
   RET_IF(split_lo(l->dREC, lo_of(l, l->dREC), (int64_t)M * 56, sc));
-  k_vae_loss_height<<<grid1d((long long)M * 696, 256), 256, 0, st>>>(M, 1.0f / ((float)M * 693.0f), l->HR, xc, l->dHR, l->stats);
+  k_vae_loss_height<<<grid1d((long long)M * 696, 256), 256, 0, st>>>(M, 1.0f / ((float)M * 693.0f), l->HR, xc, l->dHR, lo_of(l, l->dHR),
+                                                                     l->stats);
   DTC_CHECK_LAUNCH("k_vae_loss_height");
-  RET_IF(split_lo(l->dHR, lo_of(l, l->dHR), (int64_t)M * 696, st));
   // backward: cenet decoder (stream c), terrain decoder (caller's stream), weight gradients (stream w)
   RET_IF(chain(l, sc, sw));
   RET_IF(wgrad(l, CD4, l->dREC, 56, l->D2, 128, M, sw));
