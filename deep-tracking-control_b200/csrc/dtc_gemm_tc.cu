@@ -624,7 +624,9 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
   // CTA pairs pay off once there are enough 256-row tiles to keep every pair busy
   const int pair_tiles = ceil_div(a.N, TC_BN) * ceil_div(a.M, 2 * TC_BM) * splits;
-  const bool use_pair = tc_pair_mode() && a.M > TC_BM && pair_tiles >= num_sms / 2;
+  static int pair_min = -1;  // fewest pair tiles worth a cluster launch (env DTC_GEMM_PAIR_MIN, default: one per SM pair)
+  if (pair_min < 0) { const char* e = getenv("DTC_GEMM_PAIR_MIN"); pair_min = e ? atoi(e) : num_sms / 2; }
+  const bool use_pair = tc_pair_mode() && a.M > TC_BM && pair_tiles >= pair_min;
   const int bmap = (use_pair && bmaj == 0) ? 2 : bmaj;
   CUtensorMap mA, mAlo, mB, mBlo;
   RETURN_IF_ERR(tc_get_map(a.A, a.M, a.K, a.lda, amaj, &mA));

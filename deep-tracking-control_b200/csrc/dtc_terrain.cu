@@ -1,0 +1,88 @@
+// terrain rasterisation on the device.  The reference builds its int16 heightfield on the host with
+// isaacgym.terrain_utils (legged_gym/utils/terrain.py:9-243: pyramid stairs, discrete obstacles, stepping stones laid out as
+// num_rows x num_cols sub-terrains inside a flat border) and uploads it; here the host only draws the handful of random
+// parameters (as the reference does, with numpy) and one thread per map cell evaluates the sub-terrain's closed form, so
+// the 1760 x 1120 map, the env-origin heights and the foothold kernel's tables never exist on the host.
+// Oracle: deep-tracking-control_b200/sim_stub.make_heightmap (numpy), bit-exact (tests/test_env_gpu.py).
+#include "dtc_common.cuh"
+
+#define TERRAIN_TABLE 256  // int32 entries per sub-terrain: stepping-stone column offsets or 20 x {x, y, w, l, height} rectangles
+
+__device__ __forceinline__ int terrain_cell(const dtc_subterrain& s, const int32_t* __restrict__ tab, int x, int y, int px) {
+  int h = 0;
+  if (s.type == 1) {  // stepping stones: stones of side a separated by gaps b over a pit of depth c; column k starts at tab[k]
+    const int P = s.a + s.b, cx = x / P;
+    h = s.c;
+    if (x - cx * P < s.a) {
+      const int y0 = tab[cx];
+      if (y < max(0, y0 - s.b) || (y >= y0 && (y - y0) % P < s.a)) h = 0;
+    }
+  } else if (s.type == 2) {  // pyramid stairs: step width a, step height b (signed), platform c
+    const int m = min(min(x, px - 1 - x), min(y, px - 1 - y)) / s.a;
+    int T = 0;  // number of rings the host loop lays down: ring t while px - 2 a (t - 1) > c
+    if (px > s.c) T = (px - s.c - 1) / (2 * s.a) + 1;
+    h = s.b * min(m, T);
+  } else if (s.type == 3) {  // discrete obstacles: a rectangles, later ones override earlier ones
+    for (int r = 0; r < s.a; ++r) {
+      const int32_t* q = tab + 5 * r;
+      if (x >= q[0] && x < q[0] + q[2] && y >= q[1] && y < q[1] + q[3]) h = q[4];
+    }
+  }
+  if (s.platform_half > 0) {
+    const int c = px / 2, p = s.platform_half;
+    if (x >= c - p && x < c + p && y >= c - p && y < c + p) h = 0;
+  }
+  return h;
+}
+
+__global__ void __launch_bounds__(256) k_terrain_rasterize(int rows, int cols, int border_px, int sub_px, int n_rows, int n_cols,
+                                                           const dtc_subterrain* __restrict__ subs, const int32_t* __restrict__ tables,
+                                                           int16_t* __restrict__ out) {
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t e = blockIdx.x * 256ll + threadIdx.x; e < total; e += gridDim.x * 256ll) {
+    const int gx = (int)(e / cols), gy = (int)(e - (int64_t)gx * cols);
+    const int lx = gx - border_px, ly = gy - border_px;
+    int h = 0;
+    if (lx >= 0 && ly >= 0 && lx < n_rows * sub_px && ly < n_cols * sub_px) {
+      const int i = lx / sub_px, j = ly / sub_px, s = i * n_cols + j;
+      h = terrain_cell(subs[s], tables + (size_t)s * TERRAIN_TABLE, lx - i * sub_px, ly - j * sub_px, sub_px);
+    }
+    out[e] = (int16_t)h;
+  }
+}
+
+// origins[i][j] = ((i + 0.5) L, (j + 0.5) L, max over the central 20 x 20 cells * vertical_scale): one warp per sub-terrain
+__global__ void __launch_bounds__(32) k_terrain_origins(int cols, int border_px, int sub_px, int n_cols, double terrain_length,
+                                                        double vertical_scale, const int16_t* __restrict__ map, float* __restrict__ origins) {
+  const int s = blockIdx.x, i = s / n_cols, j = s - i * n_cols, c = sub_px / 2;
+  int mx = -32768;
+  for (int e = threadIdx.x; e < 400; e += 32) {
+    const int x = border_px + i * sub_px + c - 10 + e / 20, y = border_px + j * sub_px + c - 10 + e % 20;
+    mx = max(mx, (int)map[(size_t)x * cols + y]);
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (threadIdx.x == 0) {
+    origins[s * 3 + 0] = (float)(((double)i + 0.5) * terrain_length);
+    origins[s * 3 + 1] = (float)(((double)j + 0.5) * terrain_length);
+    origins[s * 3 + 2] = (float)((double)mx * vertical_scale);
+  }
+}
+
+extern "C" int dtc_terrain_rasterize(int32_t rows, int32_t cols, int32_t border_px, int32_t sub_px, int32_t n_rows, int32_t n_cols,
+                                     const dtc_subterrain* subs, const int32_t* tables, double terrain_length, double vertical_scale,
+                                     int16_t* height_samples, float* terrain_origins, void* stream) {
+  if (!subs || !tables || !height_samples) DTC_FAIL(DTC_ERR_ARG, "dtc_terrain_rasterize: null argument");
+  if (rows <= 0 || cols <= 0 || sub_px < 20 || n_rows <= 0 || n_cols <= 0 || border_px < 0 || n_rows * sub_px + 2 * border_px > rows ||
+      n_cols * sub_px + 2 * border_px > cols)
+    DTC_FAIL(DTC_ERR_ARG, "dtc_terrain_rasterize: %d x %d sub-terrains of %d px + 2 x %d px border do not fit a %d x %d map", n_rows, n_cols,
+             sub_px, border_px, rows, cols);
+  cudaStream_t st = (cudaStream_t)stream;
+  k_terrain_rasterize<<<148 * 8, 256, 0, st>>>(rows, cols, border_px, sub_px, n_rows, n_cols, subs, tables, height_samples);
+  DTC_CHECK_LAUNCH("k_terrain_rasterize");
+  if (terrain_origins) {
+    k_terrain_origins<<<n_rows * n_cols, 32, 0, st>>>(cols, border_px, sub_px, n_cols, terrain_length, vertical_scale, height_samples,
+                                                      terrain_origins);
+    DTC_CHECK_LAUNCH("k_terrain_origins");
+  }
+  return DTC_OK;
+}

@@ -118,6 +118,74 @@ def make_heightmap(kind="stones", seed=0):
     return hs, origins
 
 
+def describe_terrain(kind="stones", seed=0):
+    """The random parameters of `make_heightmap(kind, seed)` - same generator, same draw order - as the two arrays
+    `dtc_terrain_rasterize` (include/dtc_b200.h) takes: subs int32 [12, 5] = (type, a, b, c, platform_half) per
+    sub-terrain in row-major (i, j) order and tables int32 [12, 256]."""
+    rng = np.random.default_rng(seed)
+    n = L.NUM_ROWS * L.NUM_COLS
+    subs = np.zeros((n, 5), dtype=np.int32)
+    tables = np.zeros((n, 256), dtype=np.int32)
+    px = int(L.TERRAIN_LENGTH / L.HORIZONTAL_SCALE)
+
+    def stones(s, size_m, gap_m, depth_m=-2.0, platform_m=1.0):
+        stone = max(1, int(size_m / L.HORIZONTAL_SCALE))
+        gap = max(1, int(round(gap_m / L.HORIZONTAL_SCALE)))
+        x = k = 0
+        while x < px:
+            tables[s, k] = int(rng.integers(0, stone))
+            k += 1
+            x += stone + gap
+        subs[s] = (1, stone, gap, int(depth_m / L.VERTICAL_SCALE), int(platform_m / L.HORIZONTAL_SCALE / 2))
+
+    for j in range(L.NUM_COLS):
+        for i in range(L.NUM_ROWS):
+            s, d = i * L.NUM_COLS + j, i / L.NUM_ROWS
+            if kind == "flat":
+                continue
+            if kind == "stones":
+                size = float(rng.uniform(0.3, 1.0))
+                gap = float(rng.uniform(0.06, 0.10))
+                stones(s, size, gap)
+            elif kind == "curriculum":
+                if j == 0:
+                    which = i % 3
+                    if which < 2:
+                        step_h = -(0.05 + 0.13 * d) if which == 0 else 0.05 + 0.13 * d
+                        subs[s] = (2, int(0.31 / L.HORIZONTAL_SCALE), int(step_h / L.VERTICAL_SCALE), int(3.0 / L.HORIZONTAL_SCALE), 0)
+                    else:
+                        mh = int((0.05 + 0.15 * d) / L.VERTICAL_SCALE)
+                        for r in range(20):
+                            w = int(rng.integers(20, 41))
+                            l = int(rng.integers(20, 41))
+                            x = int(rng.integers(0, px - w))
+                            y = int(rng.integers(0, px - l))
+                            tables[s, 5 * r:5 * r + 5] = (x, y, w, l, int(rng.choice([-mh, -mh // 2, mh // 2, mh])))
+                        subs[s] = (3, 20, 0, 0, int(3.0 / L.HORIZONTAL_SCALE / 2))
+                else:
+                    stones(s, 1.0 * (1.05 - d), 0.03 if d == 0 else 0.06)
+            else:
+                raise ValueError(kind)
+    return subs, tables
+
+
+def make_heightmap_device(kind="stones", seed=0, device="cuda"):
+    """`make_heightmap` with the rasterisation on the device: (height_samples int16 [1760,1120], terrain_origins float32 [6,2,3])
+    as CUDA tensors, bit-identical to the numpy version (tests/test_env_gpu.py::test_terrain_rasterize_matches_numpy)."""
+    import ctypes as C
+    from . import _lib as B
+    subs, tables = describe_terrain(kind, seed)
+    dev = torch.device(device)
+    d_subs, d_tab = torch.from_numpy(subs).to(dev), torch.from_numpy(tables).to(dev)
+    hs = torch.empty(L.MAP_ROWS, L.MAP_COLS, dtype=torch.int16, device=dev)
+    origins = torch.empty(L.NUM_ROWS, L.NUM_COLS, 3, device=dev)
+    B.check(B.lib().dtc_terrain_rasterize(L.MAP_ROWS, L.MAP_COLS, int(L.BORDER_SIZE / L.HORIZONTAL_SCALE),
+                                          int(L.TERRAIN_LENGTH / L.HORIZONTAL_SCALE), L.NUM_ROWS, L.NUM_COLS, B.ptr(d_subs), B.ptr(d_tab),
+                                          C.c_double(L.TERRAIN_LENGTH), C.c_double(L.VERTICAL_SCALE), B.ptr(hs), B.ptr(origins),
+                                          B.stream_ptr(dev)), "dtc_terrain_rasterize")
+    return hs, origins
+
+
 # ----------------------------------------------------------------------------- synthetic state
 HIP_OFFSETS = torch.tensor([[0.1745, 0.159, 0.0], [0.1745, -0.159, 0.0],
                             [-0.1745, 0.159, 0.0], [-0.1745, -0.159, 0.0]])

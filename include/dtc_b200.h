@@ -290,6 +290,19 @@ int dtc_get_gemm_pair(void);
 void dtc_set_overlap(int on);
 int dtc_get_overlap(void);
 
+/* ------------------------------------------------------------------ terrain rasterisation on the device
+ * legged_gym/utils/terrain.py:9-243 lays num_rows x num_cols sub-terrains (pyramid stairs, discrete obstacles, stepping
+ * stones: isaacgym.terrain_utils) inside a flat border and uploads the int16 heightfield.  Here the host draws only the random
+ * parameters and the device evaluates every cell.  type: 0 flat; 1 stepping stones (a = stone side px, b = gap px, c = pit depth
+ * in height units, table = first-stone offset of every stone column); 2 pyramid stairs (a = step width px, b = signed step
+ * height in units, c = platform px); 3 discrete obstacles (a = count <= 20, table = {x, y, w, l, height} per rectangle).
+ * platform_half > 0 flattens the central square of that half-width.  tables: int32 [n_rows * n_cols][256] (device).
+ * terrain_origins [n_rows, n_cols, 3] (may be NULL) = sub-terrain centres with the height of their central 20 x 20 cells. */
+typedef struct { int32_t type, a, b, c, platform_half; } dtc_subterrain;
+int dtc_terrain_rasterize(int32_t rows, int32_t cols, int32_t border_px, int32_t sub_px, int32_t n_rows, int32_t n_cols,
+                          const dtc_subterrain* subs, const int32_t* tables, double terrain_length, double vertical_scale,
+                          int16_t* height_samples, float* terrain_origins, void* stream);
+
 /* ------------------------------------------------------------------ P14 / SURVEY 8f N2: the optional GRU `Memory`
  * Memory.forward / Memory.reset (rsl_rl/rsl_rl/modules/actor_critic_decoder.py:584-614): nn.GRU(input_size, hidden_size,
  * num_layers) over T time steps for N rows.  `weights`: per layer weight_ih_l [3H,in_l] | weight_hh_l [3H,H] | bias_ih_l [3H] |

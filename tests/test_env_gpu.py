@@ -177,6 +177,17 @@ def test_foothold_variants_agree(N, kind):
                 assert torch.equal(a, b), f"{nme} rep{rep}: {int((a != b).sum())} mismatches"
 
 
+@pytest.mark.parametrize("kind,seed", [("flat", 0), ("stones", 0), ("stones", 7), ("curriculum", 0), ("curriculum", 3)])
+def test_terrain_rasterize_matches_numpy(kind, seed):
+    """the device rasteriser (closed form per cell) against the host loops of sim_stub.make_heightmap on the same
+    random parameters: int16 map and env-origin heights bit-exact."""
+    hs, tor = sim_stub.make_heightmap(kind, seed)
+    d_hs, d_tor = sim_stub.make_heightmap_device(kind, seed, "cuda")
+    assert d_hs.dtype == torch.int16 and tuple(d_hs.shape) == hs.shape
+    assert torch.equal(d_hs.cpu(), torch.from_numpy(hs)), int((d_hs.cpu() != torch.from_numpy(hs)).sum())
+    assert torch.equal(d_tor.cpu(), torch.from_numpy(tor))
+
+
 def test_heightmap_update_rebuilds_the_min3_table():
     """The default kernel samples a library-owned table derived from height_samples at bind time; after an in-place terrain
     edit dtc_env_heightmap_updated() must bring it back in step with the brute-force variant (which reads height_samples)."""
