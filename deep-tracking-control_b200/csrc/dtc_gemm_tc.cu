@@ -40,6 +40,7 @@ struct TcParams {
   const float* bias; const float* act_src; int ld_act; int epi; int accumulate;
   float* ws;
   int splits, has_alo, has_blo;
+  int neff;   // 1: the MMA of a ragged / narrow n-tile covers only the live columns rounded up to the instruction granularity
   int debug;  // timing experiments only (env DTC_TC_DEBUG): 1 = epilogue skips its stores, 2 = producer stops loading after the first ring fill
 };
 
@@ -65,6 +66,14 @@ __device__ __forceinline__ void tc_tma_2d(uint32_t dst, const CUtensorMap* map, 
 // shared-memory matrix descriptors (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | layout <<61.
 //   K-major : rows of 128 B (32 k), 8-row swizzle atoms 1024 B apart (SBO), LBO 16; one MMA (K = 8) advances 32 B inside the row
 //   MN-major: blocks of 32 mn (4096 B apart = LBO) of 32 k-rows x 128 B, 4-row swizzle atoms 512 B apart (SBO); one MMA = 8 k-rows
+// columns the MMAs of the n-tile starting at n0 must produce: all 128, or - for the ragged last tile of the 693 / 588 / 532-wide
+// layers and for the 35..64-wide ones - the live columns rounded up to `gran` (16 for cta_group::1, 32 for a CTA pair, whose two
+// halves each supply N/2 rows of B)
+__device__ __forceinline__ int tc_n_eff(const TcParams& p, int n0, int gran) {
+  if (!p.neff) return TC_BN;
+  const int live = min(TC_BN, p.N - n0);
+  return min(TC_BN, (live + gran - 1) / gran * gran);
+}
 // one elected lane of a converged warp (CUTLASS elect_one_sync): unlike `lane == 0`, ptxas knows the guarded region has a single
 // active thread and issues UTMALDG / UTCHMMA / UTCBAR straight from uniform registers instead of wrapping each in an ELECT loop
 __device__ __forceinline__ bool tc_elect_one() {
@@ -305,11 +314,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
    if (tc_elect_one()) {
     // ------------------------------------------------------------ MMA issuer (one thread)
     // instruction descriptor: D f32 | A,B tf32 | majors | N >> 3 | M >> 4   (cute::UMMA::InstrDescriptor)
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)AMAJ << 15) | ((uint32_t)BMAJ << 16) |
-                           ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)AMAJ << 15) | ((uint32_t)BMAJ << 16) |
+                            ((uint32_t)(TC_BM >> 4) << 24);
     int it = 0, j = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
       const int z = t / (nt_n * nt_m);
+      const uint32_t idesc = idesc0 | ((uint32_t)(tc_n_eff(p, (t % nt_n) * TC_BN, 16) >> 3) << 17);
       const int kb0 = z * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
       const int buf = j & 1;
       tc_mbar_wait(&bar_acc_empty[buf], ((j >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator set
@@ -427,7 +437,8 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     const uint32_t bytes_cta = (uint32_t)(TC2_A_BYTES * (1 + p.has_alo) + TC2_B_BYTES * (1 + p.has_blo));
     int it = 0;
     for (int t = pair; t < ntiles; t += npairs) {
-      const int n0 = (t % nt_n) * TC_BN + (int)rank * (TC_BN / 2), m0 = ((t / nt_n) % nt_m) * (2 * TC_BM) + (int)rank * TC_BM;
+      const int nt0 = (t % nt_n) * TC_BN;
+      const int n0 = nt0 + (int)rank * (tc_n_eff(p, nt0, 32) / 2), m0 = ((t / nt_n) % nt_m) * (2 * TC_BM) + (int)rank * TC_BM;
       const int z = t / (nt_n * nt_m);
       const int kb0 = z * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -467,11 +478,12 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
   } else if (warp == 1 && rank == 0) {
    if (tc_elect_one()) {
     // ------------------------------------------------------------ MMA issuer (one thread of the leader CTA), M = 256
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)AMAJ << 15) | ((uint32_t)BMAJ << 16) |
-                           ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+    const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)AMAJ << 15) | ((uint32_t)BMAJ << 16) |
+                            ((uint32_t)((2 * TC_BM) >> 4) << 24);
     int it = 0, j = 0;
     for (int t = pair; t < ntiles; t += npairs, ++j) {
       const int z = t / (nt_n * nt_m);
+      const uint32_t idesc = idesc0 | ((uint32_t)(tc_n_eff(p, (t % nt_n) * TC_BN, 32) >> 3) << 17);
       const int kb0 = z * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
       const int buf = j & 1;
       tc_mbar_wait(&bar_acc_empty[buf], ((j >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this accumulator set
@@ -619,6 +631,7 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   p.ws = a.ws;
   p.has_alo = a.A_lo ? 1 : 0; p.has_blo = a.B_lo ? 1 : 0;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DTC_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
+  { static int neff = -1; if (neff < 0) { const char* e = getenv("DTC_TC_NEFF"); neff = e ? atoi(e) : 1; } p.neff = neff; }  // DTC_TC_NEFF=0: always 128-column MMAs
   const int amaj = a.a_kc ? 0 : 1, bmaj = a.b_kc ? 0 : 1;
   static int num_sms = 0;
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
