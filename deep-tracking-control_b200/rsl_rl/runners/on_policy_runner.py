@@ -14,6 +14,7 @@ import collections
 import torch
 
 from ..algorithms import PPO
+from ..env.vec_env import check_env
 from ..env.wrappers import HistoryWrapper
 from ..modules import ActorCriticDecoder
 
@@ -24,7 +25,7 @@ class OnPolicyRunner:
         self.alg_cfg = train_cfg["algorithm"]
         self.policy_cfg = train_cfg["policy"]
         self.device = device
-        self.env = HistoryWrapper(env)
+        self.env = HistoryWrapper(check_env(env))
         num_critic_obs = self.env.num_privileged_obs if self.env.num_privileged_obs is not None else self.env.num_obs
         actor_critic = ActorCriticDecoder(self.env.num_obs, num_critic_obs, self.env.num_actions, **self.policy_cfg).to(self.device)
         actor_critic.seed = int(getattr(env, "seed", 0))  # per-rank noise stream under data parallelism
