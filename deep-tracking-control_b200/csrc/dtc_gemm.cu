@@ -314,10 +314,11 @@ int dtc_gemm_pick_splits(int M, int N, int K) {
     // CTA-pair kernel (256 x 128 tiles on 74 SM pairs): the split count that minimises rounds x k-blocks per split, e.g.
     // 512 x 693 over 24 576 rows: 24 splits = 288 tiles = 4 rounds of 32 k-blocks instead of 25 splits = 5 rounds of 31
     const int pt = ceil_div(M, 256) * ceil_div(N, 128), nkb = ceil_div(K, 32), pairs = 74;
-    int best = tc_min < 1 ? 1 : tc_min;
+    const int lo = tc_min < 1 ? 1 : tc_min;
+    int best = lo;
     long best_cost = -1;
-    for (int c = best; c <= best + 24 && c <= nkb; ++c) {
-      if ((long)pt * c < pairs && c < best + 24) continue;  // too few tiles for the pair kernel
+    for (int c = lo; c <= lo + 24 && c <= nkb; ++c) {
+      if ((long)pt * c < pairs && c < lo + 24) continue;  // too few tiles for the pair kernel
       // + the partial-tile round trip through the workspace: one split of a 512 x 693 output costs about 2.4 k-blocks of MMA time
       const long cost = 5 * (long)ceil_div((long)pt * c, pairs) * ceil_div(nkb, c) + (long)pt * c;
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }

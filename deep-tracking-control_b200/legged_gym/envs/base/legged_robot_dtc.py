@@ -70,7 +70,9 @@ class LeggedRobotDTC:
         self.dof_vel = self.dof_state.view(N, L.NUM_DOF, 2)[..., 1]
         self.base_quat = self.root_states[:, 3:7]
         self.base_pos = self.root_states[:, :3]
-        self.height_samples = torch.as_tensor(np.asarray(height_samples)).to(dev).view(L.MAP_ROWS, L.MAP_COLS).contiguous()
+        # numpy (host generator) or a tensor, e.g. straight from sim_stub.make_heightmap_device / dtc_terrain_rasterize
+        hs_t = height_samples if torch.is_tensor(height_samples) else torch.as_tensor(np.asarray(height_samples))
+        self.height_samples = hs_t.to(dev).view(L.MAP_ROWS, L.MAP_COLS).contiguous()
         assert self.height_samples.dtype == torch.int16
         levels, types, origins, tor = layout
         self.terrain_levels = levels.to(dev).clone()

@@ -299,5 +299,5 @@ def initial_env_layout(num_envs, terrain_origins, seed, curriculum=True):
     max_init = 5 if curriculum else L.NUM_ROWS - 1
     levels = torch.randint(0, max_init + 1, (num_envs,), generator=g)
     types = torch.div(torch.arange(num_envs), (num_envs / L.NUM_COLS), rounding_mode="floor").to(torch.long)
-    to = torch.from_numpy(np.asarray(terrain_origins)).to(torch.float)
+    to = (terrain_origins.detach().cpu() if torch.is_tensor(terrain_origins) else torch.from_numpy(np.asarray(terrain_origins))).to(torch.float)
     return levels, types, to[levels, types].clone(), to

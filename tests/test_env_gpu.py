@@ -186,6 +186,23 @@ def test_terrain_rasterize_matches_numpy(kind, seed):
     assert d_hs.dtype == torch.int16 and tuple(d_hs.shape) == hs.shape
     assert torch.equal(d_hs.cpu(), torch.from_numpy(hs)), int((d_hs.cpu() != torch.from_numpy(hs)).sum())
     assert torch.equal(d_tor.cpu(), torch.from_numpy(tor))
+    if kind == "curriculum" and seed == 0:
+        # the device-built map drives an environment without ever visiting the host
+        from dtc_b200.legged_gym.envs import LeggedRobotDTC, Lite3DTCCfg
+        N = 256
+        envs = []
+        for h_, t_ in ((hs, tor), (d_hs, d_tor)):
+            layout = sim_stub.initial_env_layout(N, t_, 1)
+            fg = sim_stub.FakeGym(N, device="cuda")
+            cfg = Lite3DTCCfg()
+            cfg.env.num_envs = N
+            env = LeggedRobotDTC(cfg, sim_device="cuda", gym=fg, height_samples=h_, terrain_origins=t_, layout=layout, seed=1)
+            g = torch.Generator(device="cuda").manual_seed(2)
+            fg.load(sim_stub.synth_state(N, env.env_origins, g, device="cuda"))
+            env.reset()
+            envs.append(env)
+        assert torch.equal(envs[0].measured_heights, envs[1].measured_heights)
+        assert torch.equal(envs[0].obs_buf, envs[1].obs_buf)
 
 
 def test_heightmap_update_rebuilds_the_min3_table():
