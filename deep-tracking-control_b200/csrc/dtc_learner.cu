@@ -371,13 +371,14 @@ extern "C" int dtc_learner_debug_buffer(dtc_learner* l, const char* name, float*
 // ------------------------------------------------------------------ GEMM helpers
 #define RET_IF(x) RETURN_IF_ERR(x)
 
-static int fwd(dtc_learner* l, int id, const float* A, int lda, float* C, int ldc, int act, int M, cudaStream_t st) {
+// need_lo = false for outputs no GEMM reads (reconstructions, heads, latent statistics): their TF32 companion is never used
+static int fwd(dtc_learner* l, int id, const float* A, int lda, float* C, int ldc, int act, int M, cudaStream_t st, bool need_lo = true) {
   const Layer& L = g_layers[id];
   GemmArgs g{};
   g.A = A; g.lda = lda; g.a_kc = true;
   g.B = l->params + L.w; g.ldb = L.ld; g.b_kc = true;
   g.C = C; g.ldc = ldc; g.M = M; g.N = L.out; g.K = L.in;
-  g.A_lo = lo_of(l, A); g.B_lo = lo_of(l, g.B); g.C_lo = lo_of(l, C);
+  g.A_lo = lo_of(l, A); g.B_lo = lo_of(l, g.B); g.C_lo = need_lo ? lo_of(l, C) : nullptr;
   g.bias = l->params + L.b;
   g.epi = act == 1 ? EPI_BIAS_RELU : act == 2 ? EPI_BIAS_ELU : EPI_BIAS;
   g.splits = 1;
@@ -1028,7 +1029,7 @@ static int encode(dtc_learner* l, int M, const float* hist, const float* priv_a,
   cudaStream_t st = S.main, sc = S.c;
   RET_IF(fwd(l, CE0, hist, LD_HIST, l->H1, 128, 1, M, sc));
   RET_IF(fwd(l, CE2, l->H1, 128, l->E, 64, 0, M, sc));
-  RET_IF(fwd(l, LAT, l->E, 64, l->ML, LD_ML, 0, M, sc));
+  RET_IF(fwd(l, LAT, l->E, 64, l->ML, LD_ML, 0, M, sc, false));
   DTC_CUDA(cudaMemsetAsync(l->lvstat, 0, sizeof(LvStat), sc));
   const int gb = grid1d((long long)M * 16, 256, 148 * 2);
   k_lv_moments<<<gb, 256, 0, sc>>>(l->ML, M, l->lvstat); DTC_CHECK_LAUNCH("k_lv_moments");
@@ -1078,13 +1079,13 @@ static int actor_fwd(dtc_learner* l, int M, cudaStream_t st) {
   RET_IF(fwd(l, AB0, l->XA, LD_XA, l->A1, 512, 2, M, st));
   RET_IF(fwd(l, AB2, l->A1, 512, l->A2, 256, 2, M, st));
   RET_IF(fwd(l, AB4, l->A2, 256, l->A3, 128, 2, M, st));
-  return fwd(l, AB6, l->A3, 128, l->MEAN, 12, 0, M, st);
+  return fwd(l, AB6, l->A3, 128, l->MEAN, 12, 0, M, st, false);
 }
 static int critic_fwd(dtc_learner* l, int M, const float* xc, cudaStream_t st) {
   RET_IF(fwd(l, CB0, xc, LD_XC, l->C1, 512, 2, M, st));
   RET_IF(fwd(l, CB2, l->C1, 512, l->C2, 256, 2, M, st));
   RET_IF(fwd(l, CB4, l->C2, 256, l->C3, 128, 2, M, st));
-  return fwd(l, CB6, l->C3, 128, l->V, 4, 0, M, st);
+  return fwd(l, CB6, l->C3, 128, l->V, 4, 0, M, st, false);
 }
 
 static int check_storage(const dtc_storage* s, const char* who) {
@@ -1309,10 +1310,10 @@ extern "C" int dtc_vae_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
   RET_IF(chain(l, st, sc));
   RET_IF(fwd(l, CD0, l->XD, LD_XD, l->D1, 64, 1, M, sc));
   RET_IF(fwd(l, CD2, l->D1, 64, l->D2, 128, 1, M, sc));
-  RET_IF(fwd(l, CD4, l->D2, 128, l->REC, 56, 0, M, sc));
+  RET_IF(fwd(l, CD4, l->D2, 128, l->REC, 56, 0, M, sc, false));
   RET_IF(fwd(l, TD0, l->XD, LD_XD, l->U1, 512, 1, M, st));
   RET_IF(fwd(l, TD2, l->U1, 512, l->U2, 512, 1, M, st));
-  RET_IF(fwd(l, TD4, l->U2, 512, l->HR, 696, 0, M, st));
+  RET_IF(fwd(l, TD4, l->U2, 512, l->HR, 696, 0, M, st, false));
   // losses and output gradients (ppo.py:213-247)
   k_vae_loss_rows<<<ceil_div(M, 128), 128, 0, sc>>>(M, inv_rows, l->REC, next_obs, l->ML, xc, l->dREC, l->dML, l->stats);
   DTC_CHECK_LAUNCH("k_vae_loss_rows");

@@ -14,7 +14,7 @@ def bench(fn, iters=20, warm=3):
 M = 24576
 out = {}
 lo = lambda x: x - (x.view(torch.int32) & -8192).view(torch.float32)
-for (N, K) in ((512, 693), (512, 512), (693, 512)):
+for (N, K) in ((512, 693), (512, 512), (256, 512), (128, 256), (64, 128)):
     r4 = lambda x: (x + 3) // 4 * 4
     A = torch.randn(M, r4(K), device="cuda"); W = torch.randn(N, r4(K), device="cuda")
     Cc = torch.empty(M, r4(N), device="cuda"); Cl = torch.empty_like(Cc)
