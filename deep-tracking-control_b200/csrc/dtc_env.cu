@@ -533,8 +533,6 @@ extern "C" int dtc_env_create(const dtc_env_config* cfg, dtc_env** out) {
   dtc_env* e = new dtc_env();
   e->cfg = *cfg;
   e->bound = false;
-  e->tmap_ready = false;
-  e->d_tmap = nullptr;
   e->min3 = nullptr;
   e->min3_bytes = 0;
   cudaError_t ce = cudaMalloc(&e->d_cfg, sizeof(dtc_env_config));
@@ -546,7 +544,6 @@ extern "C" int dtc_env_create(const dtc_env_config* cfg, dtc_env** out) {
 extern "C" void dtc_env_destroy(dtc_env* e) {
   if (!e) return;
   cudaFree(e->d_cfg);
-  if (e->d_tmap) cudaFree(e->d_tmap);
   if (e->min3) cudaFree(e->min3);
   delete e;
 }
@@ -559,12 +556,10 @@ extern "C" int dtc_env_bind(dtc_env* e, const dtc_env_buffers* buf) {
   if (buf->priv_ld < 2 * NP + 3 || buf->hist_ld < 265) DTC_FAIL(DTC_ERR_ARG, "dtc_env_bind: row strides too small");
   e->buf = *buf;
   e->bound = true;
-  e->tmap_ready = false;
   return dtc_env_build_min3(e);
 }
 extern "C" int dtc_env_heightmap_updated(dtc_env* e) {
   if (!e || !e->bound) DTC_FAIL(DTC_ERR_STATE, "dtc_env_heightmap_updated: env not bound");
-  e->tmap_ready = false;
   return dtc_env_build_min3(e);
 }
 extern "C" int dtc_env_pre_physics(dtc_env* e, const float* actions_in, const int32_t lag_choice[4], void* stream) {

@@ -7,9 +7,6 @@ struct dtc_env {
   dtc_env_buffers buf;
   bool bound;
   dtc_env_config* d_cfg;  // device copy (tables are too large for kernel parameters)
-  CUtensorMap tmap;       // heightmap descriptor for the TMA variant of the foothold kernel
-  bool tmap_ready;
-  CUtensorMap* d_tmap;    // device-memory copy of the descriptor (variant 2)
   int16_t* min3;          // variant 5: min(H[x][y], H[x+1][y], H[x][y+1]) of the bound heightmap (library-owned)
   size_t min3_bytes;
 };

@@ -12,8 +12,10 @@
 // <= 0.2*10 + 0.8*0.16 = 2.128, every other point scores >= 8, so if the window holds one the global argmin of
 // the reference's brute-force 693x4 scan is inside the window; otherwise every in-radius point is an exception
 // (score 10) and the scan reduces to argmin_p (exc ? 10 : 0.2*s_p + 8), which phase 2 already has.
-// Height taps: variant 0 reads the int16 map through L1/L2 (3.9 MB, L2 resident); variant 1 stages the 48x48
-// patch under the robot with one TMA 2-D box load (cp.async.bulk.tensor.2d + mbarrier) and taps shared memory.
+// Height taps: variant 0 reads the int16 map through L1/L2 (3.9 MB, L2 resident); variant 3 stages the 48x56-cell patch under the
+// robot with one cp.async.bulk row copy per map row (mbarrier completion) and taps shared memory.  (Variants 1 / 2 staged the patch
+// with a cp.async.bulk.tensor.2d box load; an int16 / SWIZZLE_NONE tensor map raises "illegal instruction" on this device for every
+// box shape tried, so they were removed and the launcher rejects those ids.)
 #include <cuda.h>
 #include "dtc_common.cuh"
 #include "dtc_env_internal.cuh"
@@ -28,10 +30,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 template <int VARIANT>
 __global__ void __launch_bounds__(FH_WARPS * 32)
-k_foothold(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, float* __restrict__ dbg_score,
-           const __grid_constant__ CUtensorMap tmap, const CUtensorMap* __restrict__ tmap_g) {
-  // VARIANT 0: taps through L1/L2.  1: TMA tensor box, descriptor in kernel params.  2: same, descriptor in global
-  // memory.  3: TMA 1-D bulk row copies (cp.async.bulk, no descriptor).
+k_foothold(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, float* __restrict__ dbg_score) {
+  // VARIANT 0: taps through L1/L2.  3: TMA 1-D bulk row copies (cp.async.bulk, no descriptor).
   constexpr bool STAGED = VARIANT != 0;
   constexpr int PW = VARIANT == 3 ? PATCH_W : PATCH;
   __shared__ float mh_s[FH_WARPS][NP + 3];
@@ -66,7 +66,7 @@ k_foothold(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, float* __r
     ox = (int)floorf((root_x + border) / hscale) - 21;
     oy = (int)floorf((root_y + border) / hscale) - 21;
     const uint32_t mb = smem_u32(&mbar_s[warp]);
-    if (VARIANT == 3) {
+    {
       oy = min(max(oy & ~7, 0), cols - PW);  // 16-byte aligned column origin, kept inside the map
       if (lane == 0)
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(PATCH * PW * 2) : "memory");
@@ -79,14 +79,6 @@ k_foothold(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, float* __r
                      "l"(src), "r"(PW * 2), "r"(mb)
                      : "memory");
       }
-    } else if (lane == 0) {
-      const void* desc = VARIANT == 1 ? (const void*)&tmap : (const void*)tmap_g;
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(PATCH * PATCH * 2) : "memory");
-      asm volatile(
-          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-              smem_u32(&patch_s[warp][0])),
-          "l"(desc), "r"(oy), "r"(ox), "r"(mb)
-          : "memory");
     }
     // all lanes wait for the patch (phase parity 0; one patch per warp lifetime)
     uint32_t done = 0;
@@ -971,43 +963,18 @@ static int launch_v5(dtc_env* e, const V5Params& P, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static int make_heightmap_tmap(dtc_env* e) {
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  DTC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-  if (!fn || qres != cudaDriverEntryPointSuccess) DTC_FAIL(DTC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
-  cuuint64_t dims[2] = {(cuuint64_t)e->cfg.map_cols, (cuuint64_t)e->cfg.map_rows};
-  cuuint64_t strides[1] = {(cuuint64_t)e->cfg.map_cols * 2};
-  cuuint32_t box[2] = {PATCH, PATCH};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = ((PFN_encodeTiled)fn)(&e->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, (void*)e->buf.height_samples, dims, strides, box,
-                                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) DTC_FAIL(DTC_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
-  if (!e->d_tmap) DTC_CUDA(cudaMalloc(&e->d_tmap, sizeof(CUtensorMap)));
-  DTC_CUDA(cudaMemcpy(e->d_tmap, &e->tmap, sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-  e->tmap_ready = true;
-  return DTC_OK;
-}
-
 extern "C" int dtc_foothold_step(dtc_env* e, int variant, float* debug_score, void* stream) {
   if (!e || !e->bound) DTC_FAIL(DTC_ERR_STATE, "dtc_foothold_step: env not bound");
   cudaStream_t st = (cudaStream_t)stream;
   int N = e->cfg.num_envs;
   dim3 grid(ceil_div(N, FH_WARPS)), block(FH_WARPS * 32);
-  if (variant >= 1 && variant <= 5 && (e->cfg.map_cols * 2) % 16 != 0)
+  if (variant >= 3 && variant <= 5 && (e->cfg.map_cols * 2) % 16 != 0)
     DTC_FAIL(DTC_ERR_ARG, "TMA variants need 16-byte aligned heightmap rows");
   dtc_prof_begin(st, 1, 0.0);
   if (variant == 1 || variant == 2) {
-    if (!e->tmap_ready) { int rc = make_heightmap_tmap(e); if (rc) return rc; }
-    if (variant == 1) k_foothold<1><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score, e->tmap, e->d_tmap);
-    else k_foothold<2><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score, e->tmap, e->d_tmap);
+    DTC_FAIL(DTC_ERR_ARG, "dtc_foothold_step: variants 1 and 2 (tensor-map staging) were removed; use 0, 3, 4 or 5");
   } else if (variant == 3) {
-    k_foothold<3><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score, e->tmap, e->d_tmap);
+    k_foothold<3><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score);
   } else if (variant == 4) {
     k_foothold_v4<<<ceil_div(N, V4_WARPS), V4_WARPS * 32, 0, st>>>(e->d_cfg, e->buf, debug_score);
   } else if (variant == 5 && !debug_score) {
@@ -1016,7 +983,7 @@ extern "C" int dtc_foothold_step(dtc_env* e, int variant, float* debug_score, vo
     const V5Params P = v5_params(e->cfg, &sep);
     RETURN_IF_ERR(sep ? launch_v5<true>(e, P, st) : launch_v5<false>(e, P, st));
   } else if (variant == 0 || variant == 5) {  // the brute-force debug dump of variant 5 is variant 0's
-    k_foothold<0><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score, e->tmap, e->d_tmap);
+    k_foothold<0><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score);
   } else {
     DTC_FAIL(DTC_ERR_ARG, "dtc_foothold_step: unknown variant %d", variant);
   }

@@ -154,8 +154,8 @@ int dtc_env_state_prep(dtc_env* e, int64_t common_step_counter, uint64_t seed, c
 
 /* E5 + E7..E10: height sampling, Raibert footholds, terrain score, argmin, decode
  * (legged_robot.py:1279-1317; legged_robot_dtc.py:100-201).  THE foothold-scoring kernel.
- * variant 0 = L2 gathers, 1..3 = TMA-staged patch (tensor box / descriptor in global / bulk rows), 4 = lazy window
- * scoring, 5 = persistent warps + min3 map + prefetched tight patch (default).  debug_score may be NULL or [N,693,4]. */
+ * variant 0 = brute force with L2 gathers, 3 = patch staged with bulk row copies, 4 = lazy window scoring, 5 = persistent warps +
+ * min3 map + prefetched patch (default); 1 and 2 are rejected (removed).  debug_score may be NULL or [N,693,4]. */
 int dtc_foothold_step(dtc_env* e, int variant, float* debug_score, void* stream);
 
 /* E4(rest), E6, E11, E12, E13: push, foot clearance, contact filter, termination, 23 rewards, reset

@@ -235,6 +235,11 @@ def test_heightmap_update_rebuilds_the_min3_table():
     assert not torch.equal(h0, heights(5)), "stale table expected before the update call"
     B.check(env.lib.dtc_env_heightmap_updated(env._h), "heightmap_updated")
     assert torch.equal(h0, heights(5))
+    # removed variants are refused with an error code (they used to take the CUDA context down), unknown ones too
+    for v in (1, 2, 9):
+        with pytest.raises(B.DtcError):
+            B.check(env.lib.dtc_foothold_step(env._h, v, C.c_void_p(0), stp), "foothold")
+    assert torch.equal(h0, heights(3))
 
 
 def test_philox_noise_statistics():
