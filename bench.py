@@ -14,6 +14,12 @@ root/dof/contact/rigid-body tensors (SURVEY.md 8d distributions).
 `value`  : simulator tensors already resident in HBM (a device-side pool refreshed by device-to-device copies).
 `e2e`    : the same loop through the public Python API with the simulator tensors arriving from PINNED HOST memory every
            environment step (host->device copies inside the timed region) and the iteration's statistics read back.
+`roofline`: the dominant kernel, k_gemm_tc2 (CTA-pair tcgen05 GEMM): algorithmic 2*M*N*K FLOPs / CUDA-event time around every
+           launch of one extra iteration (side streams serialised for it), against the measured sustained bf16 tensor peak of
+           MEASURED_PEAKS.json; `traffic` = DRAM bytes of one launch from the committed ncu capture (profiles/).  The whole GEMM
+           family and the foothold kernel (`roofline_foothold`, HBM bound, 3048 B/env + the 3.9 MB map) ride along.
+`cpu_baseline`: the CPU restatement of the reference (oracle/, pinned to golden vectors of the unmodified reference) on the host
+           cores, bounded sample; `--impl reference` runs the same as its own arm.
 Timing   : CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  The per-iteration
            working set (717 MB rollout storage + its gathered copy) exceeds the 126 MB L2, so no explicit flush is used.
 """

@@ -915,6 +915,7 @@ int dtc_env_build_min3(dtc_env* e) {
   const size_t bytes = (size_t)e->cfg.map_rows * e->cfg.map_cols * sizeof(int16_t);
   if (e->min3 && e->min3_bytes != bytes) { cudaFree(e->min3); e->min3 = nullptr; }
   if (!e->min3) { DTC_CUDA(cudaMalloc(&e->min3, bytes)); e->min3_bytes = bytes; }
+  DTC_CUDA(cudaDeviceSynchronize());  // init-time call: whatever stream produced height_samples has finished
   k_min3_map<<<148 * 4, 256>>>(e->buf.height_samples, e->min3, e->cfg.map_rows, e->cfg.map_cols);
   DTC_CHECK_LAUNCH("k_min3_map");
   DTC_CUDA(cudaDeviceSynchronize());
