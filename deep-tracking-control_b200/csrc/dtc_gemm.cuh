@@ -28,7 +28,12 @@ struct GemmArgs {
   // 3xTF32 companions (dtc_gemm_tc.cu): x_lo = rn_tf32(x - trunc_tf32(x)).  A_lo / B_lo feed the tensor-core path (NULL = that
   // correction term is skipped); C_lo, when set, receives the companion of the result from either path's epilogue.
   const float* A_lo; const float* B_lo; float* C_lo;
+  // tensor-core path only, splits == 1: when set, the epilogue also writes the column sums of every 32-row block of the final C
+  // to colsum_part[ceil(M/32)][round4(N)] (the bias gradient of the layer below a dgrad, without re-reading C from HBM)
+  float* colsum_part;
 };
+// out[n] = sum_b part[b*ld + n], b < nblk (deterministic order)
+int dtc_colsum_part_launch(const float* part, int nblk, int ld, int ncols, float* out, cudaStream_t st);
 
 // GEMM engine: 0 = FP32 SIMT everywhere, 1 = tcgen05 3xTF32 where the shape is tile-worthy (default; env DTC_GEMM=simt|tc)
 int dtc_gemm_mode();

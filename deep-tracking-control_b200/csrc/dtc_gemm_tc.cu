@@ -39,6 +39,7 @@ struct TcParams {
   float* C; float* C_lo; int ldc;
   const float* bias; const float* act_src; int ld_act; int epi; int accumulate;
   float* ws;
+  float* colsum_part;  // [ceil(M/32)][round4(N)] column sums per 32-row block of the final output, or NULL
   int splits, has_alo, has_blo;
   int neff;   // 1: the MMA of a ragged / narrow n-tile covers only the live columns rounded up to the instruction granularity
   int debug;  // timing experiments only (env DTC_TC_DEBUG): 1 = epilogue skips its stores, 2 = producer stops loading after the first ring fill
@@ -198,6 +199,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
     __syncwarp();
     const int cb = lane & 7, c4 = cb * 4, gn = n0 + c0 + c4;
     const int r0 = lane >> 3, gm0 = m0 + q * 32 + r0;
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);  // column sums of this lane's 8 rows (colsum_part)
     if (gn + 3 < p.N) {
       float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn));
@@ -222,6 +224,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
         x.z = tc_epi(a4.z, epi, b4.z, s4[i].z) + o4[i].z; x.w = tc_epi(a4.w, epi, b4.w, s4[i].w) + o4[i].w;
         *reinterpret_cast<float4*>(out + (size_t)gm * ldo + gn) = x;
         if (out_lo) *reinterpret_cast<float4*>(out_lo + (size_t)gm * ldo + gn) = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+        cs.x += x.x; cs.y += x.y; cs.z += x.z; cs.w += x.w;
       }
     } else if (gn < p.N) {  // ragged right edge: scalar tail
 #pragma unroll 1
@@ -238,10 +241,20 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
           if (accum) y += orow[jj];
           orow[jj] = y;
           if (out_lo) out_lo[(size_t)gm * ldo + gn + jj] = tf32_lo(y);
+          if (jj == 0) cs.x += y; else if (jj == 1) cs.y += y; else if (jj == 2) cs.z += y; else cs.w += y;
         }
       }
     }
     __syncwarp();
+    if (p.colsum_part && !partial) {  // warp-uniform, outside the per-lane branches above: every lane takes part in the shuffles
+      // lanes with the same column block (lane & 7) hold the four row groups: fold them, lanes 0..7 store (n4 covers gn + 3)
+      cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
+      cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
+      cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
+      cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+      if (lane < 8 && gn < p.N && m0 + q * 32 < p.M)
+        *reinterpret_cast<float4*>(p.colsum_part + (size_t)((m0 + q * 32) >> 5) * n4 + gn) = cs;
+    }
   }
 }
 
@@ -629,6 +642,7 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   p.C = a.C; p.C_lo = a.C_lo; p.ldc = a.ldc;
   p.bias = a.bias; p.act_src = a.act_src; p.ld_act = a.ld_act; p.epi = a.epi; p.accumulate = a.accumulate ? 1 : 0;
   p.ws = a.ws;
+  p.colsum_part = (splits == 1) ? a.colsum_part : nullptr;
   p.has_alo = a.A_lo ? 1 : 0; p.has_blo = a.B_lo ? 1 : 0;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DTC_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
   { static int neff = -1; if (neff < 0) { const char* e = getenv("DTC_TC_NEFF"); neff = e ? atoi(e) : 1; } p.neff = neff; }  // DTC_TC_NEFF=0: always 128-column MMAs

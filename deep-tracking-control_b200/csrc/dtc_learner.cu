@@ -177,6 +177,10 @@ struct dtc_learner {
   double* stats;
   float* skws;  // split-K partials
   float* csws;  // column-sum partials
+  // bias gradients fused into the dgrad that produces their dY: per-32-row-block column sums from the tensor-core epilogue, one
+  // buffer per stream that runs dgrads (0: caller's stream, 1: side stream c); bias_done[layer] tells wgrad() to skip its own colsum
+  float* cspart[2];
+  bool bias_done[NLAYERS];
   // 3xTF32 companions (dtc_gemm_tc.cu): every activation / gradient buffer has a twin at +lo_shift floats, the parameters
   // have params_lo, the packed batch rows have the *_lo arrays of dtc_storage (registered per call in ext[])
   float* ws_val_begin; float* ws_val_end; ptrdiff_t lo_shift;
@@ -228,6 +232,7 @@ extern "C" int64_t dtc_learner_workspace_bytes(int32_t max_rows) {
   tot += align256(sizeof(LvStat)) + align256(ST_COUNT * sizeof(double));
   tot += align256(splitk_ws_floats(max_rows) * sizeof(float));
   tot += align256((size_t)COLSUM_CHUNKS * 768 * sizeof(float));
+  tot += 2 * align256((size_t)((R + 31) / 32) * 768 * sizeof(float));
   return (int64_t)tot;
 }
 
@@ -256,7 +261,9 @@ extern "C" int dtc_learner_create(int32_t max_rows, float* params, float* grads,
   l->lvstat = (LvStat*)p; p += align256(sizeof(LvStat));
   l->stats = (double*)p; p += align256(ST_COUNT * sizeof(double));
   l->skws = (float*)p; p += align256(splitk_ws_floats(max_rows) * sizeof(float));
-  l->csws = (float*)p;
+  l->csws = (float*)p; p += align256((size_t)COLSUM_CHUNKS * 768 * sizeof(float));
+  for (int i = 0; i < 2; ++i) { l->cspart[i] = (float*)p; p += align256((size_t)((R + 31) / 32) * 768 * sizeof(float)); }
+  memset(l->bias_done, 0, sizeof(l->bias_done));
   l->vae_steps = l->main_steps = 0;
   l->last_M = 0;
   l->side_ready = false;
@@ -396,11 +403,14 @@ static int wgrad(dtc_learner* l, int id, const float* dY, int ldy, const float* 
   g.splits = dtc_gemm_pick_splits(L.out, L.in, M);
   g.ws = l->skws;
   RET_IF(dtc_gemm_launch(g, st));
+  if (l->bias_done[id]) { l->bias_done[id] = false; return DTC_OK; }  // db came out of the dgrad that produced dY
   return dtc_colsum_launch(dY, ldy, M, L.out, l->grads + L.b, l->csws, st);
 }
 // dX[:, :ncols] (+)= (dY W[:, :ncols]) * act'(act_src)
+// bias_layer >= 0: dX[:, :out(bias_layer)] is that layer's dY, so its bias gradient = column sums of dX; on the tensor-core path
+// they come out of this GEMM's epilogue (slot: 0 when st is the caller's stream, 1 for side stream c)
 static int dgrad(dtc_learner* l, int id, const float* dY, int ldy, float* dX, int lddx, int ncols, const float* act_src,
-                 int ld_act, int epi, bool accumulate, int M, cudaStream_t st) {
+                 int ld_act, int epi, bool accumulate, int M, cudaStream_t st, int bias_layer = -1, int slot = 0) {
   const Layer& L = g_layers[id];
   GemmArgs g{};
   g.A = dY; g.lda = ldy; g.a_kc = true;
@@ -409,7 +419,15 @@ static int dgrad(dtc_learner* l, int id, const float* dY, int ldy, float* dX, in
   g.C = dX; g.ldc = lddx; g.M = M; g.N = ncols; g.K = L.out;
   g.act_src = act_src; g.ld_act = ld_act; g.epi = epi; g.accumulate = accumulate;
   g.splits = 1;
-  return dtc_gemm_launch(g, st);
+  const bool fuse = bias_layer >= 0 && dtc_gemm_mode() == 1 && dtc_gemm_tc_eligible(g) && g_layers[bias_layer].out <= ncols && ncols <= 768;
+  if (fuse) g.colsum_part = l->cspart[slot];
+  RET_IF(dtc_gemm_launch(g, st));
+  if (fuse) {
+    const Layer& Lb = g_layers[bias_layer];
+    RET_IF(dtc_colsum_part_launch(l->cspart[slot], (M + 31) / 32, round4(ncols), Lb.out, l->grads + Lb.b, st));
+    l->bias_done[bias_layer] = true;
+  }
+  return DTC_OK;
 }
 
 // ------------------------------------------------------------------ small device helpers
@@ -1060,16 +1078,16 @@ static int encode_bwd(dtc_learner* l, int M, const float* hist, const float* pri
   RET_IF(chain(l, st, sc));
   RET_IF(wgrad(l, TE4, l->dX, ldx, l->T2, 512, M, sw));
   RET_IF(wgrad(l, LAT, l->dML, LD_ML, l->E, 64, M, sw));
-  RET_IF(dgrad(l, LAT, l->dML, LD_ML, l->dE, 64, 64, nullptr, 0, EPI_STORE, false, M, sc));
+  RET_IF(dgrad(l, LAT, l->dML, LD_ML, l->dE, 64, 64, nullptr, 0, EPI_STORE, false, M, sc, CE2, 1));
   RET_IF(chain(l, sc, sw));
   RET_IF(wgrad(l, CE2, l->dE, 64, l->H1, 128, M, sw));
-  RET_IF(dgrad(l, TE4, l->dX, ldx, l->dT2, 512, 512, l->T2, 512, EPI_DRELU, false, M, st));
+  RET_IF(dgrad(l, TE4, l->dX, ldx, l->dT2, 512, 512, l->T2, 512, EPI_DRELU, false, M, st, TE2, 0));
   RET_IF(chain(l, st, sw));
   RET_IF(wgrad(l, TE2, l->dT2, 512, l->T1, 512, M, sw));
-  RET_IF(dgrad(l, CE2, l->dE, 64, l->dH1, 128, 128, l->H1, 128, EPI_DRELU, false, M, sc));
+  RET_IF(dgrad(l, CE2, l->dE, 64, l->dH1, 128, 128, l->H1, 128, EPI_DRELU, false, M, sc, CE0, 1));
   RET_IF(chain(l, sc, sw));
   RET_IF(wgrad(l, CE0, l->dH1, 128, hist, LD_HIST, M, sw));
-  RET_IF(dgrad(l, TE2, l->dT2, 512, l->dT1, 512, 512, l->T1, 512, EPI_DRELU, false, M, st));
+  RET_IF(dgrad(l, TE2, l->dT2, 512, l->dT1, 512, 512, l->T1, 512, EPI_DRELU, false, M, st, TE0, 0));
   RET_IF(chain(l, st, sw));
   RET_IF(wgrad(l, TE0, l->dT1, 512, priv_a, LD_PRIVA, M, sw));
   return DTC_OK;
@@ -1326,22 +1344,22 @@ extern "C" int dtc_vae_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
   RET_IF(wgrad(l, CD4, l->dREC, 56, l->D2, 128, M, sw));
   RET_IF(chain(l, st, sw));
   RET_IF(wgrad(l, TD4, l->dHR, 696, l->U2, 512, M, sw));
-  RET_IF(dgrad(l, CD4, l->dREC, 56, l->dD2, 128, 128, l->D2, 128, EPI_DRELU, false, M, sc));
+  RET_IF(dgrad(l, CD4, l->dREC, 56, l->dD2, 128, 128, l->D2, 128, EPI_DRELU, false, M, sc, CD2, 1));
   RET_IF(chain(l, sc, sw));
   RET_IF(wgrad(l, CD2, l->dD2, 128, l->D1, 64, M, sw));
-  RET_IF(dgrad(l, TD4, l->dHR, 696, l->dU2, 512, 512, l->U2, 512, EPI_DRELU, false, M, st));
+  RET_IF(dgrad(l, TD4, l->dHR, 696, l->dU2, 512, 512, l->U2, 512, EPI_DRELU, false, M, st, TD2, 0));
   RET_IF(chain(l, st, sw));
   RET_IF(wgrad(l, TD2, l->dU2, 512, l->U1, 512, M, sw));
-  RET_IF(dgrad(l, CD2, l->dD2, 128, l->dD1, 64, 64, l->D1, 64, EPI_DRELU, false, M, sc));
+  RET_IF(dgrad(l, CD2, l->dD2, 128, l->dD1, 64, 64, l->D1, 64, EPI_DRELU, false, M, sc, CD0, 1));
   RET_IF(chain(l, sc, sw));
   RET_IF(wgrad(l, CD0, l->dD1, 64, l->XD, LD_XD, M, sw));
-  RET_IF(dgrad(l, TD2, l->dU2, 512, l->dU1, 512, 512, l->U1, 512, EPI_DRELU, false, M, st));
+  RET_IF(dgrad(l, TD2, l->dU2, 512, l->dU1, 512, 512, l->U1, 512, EPI_DRELU, false, M, st, TD0, 0));
   RET_IF(chain(l, st, sw));
   RET_IF(wgrad(l, TD0, l->dU1, 512, l->XD, LD_XD, M, sw));
   RET_IF(dgrad(l, CD0, l->dD1, 64, l->dX, LD_XD, LD_XD, nullptr, 0, EPI_STORE, false, M, sc));
   // fan-in into d l_t: the terrain decoder's input gradient accumulates onto the CENet decoder's (dML comes from stream c too)
   RET_IF(chain(l, sc, st));
-  RET_IF(dgrad(l, TD0, l->dU1, 512, l->dX, LD_XD, 512, nullptr, 0, EPI_STORE, true, M, st));
+  RET_IF(dgrad(l, TD0, l->dU1, 512, l->dX, LD_XD, 512, nullptr, 0, EPI_STORE, true, M, st, TE4, 0));
   RET_IF(encode_bwd(l, M, hist, priv_a, 1, 1, S));
   RET_IF(streams_end(l, S));
   if (sync_grads) return DTC_OK;
@@ -1384,25 +1402,25 @@ extern "C" int dtc_ppo_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
   RET_IF(chain(l, st, sc));
   RET_IF(wgrad(l, AB6, l->dMEAN, 12, l->A3, 128, M, sw));
   RET_IF(wgrad(l, CB6, l->dV, 4, l->C3, 128, M, sw));
-  RET_IF(dgrad(l, AB6, l->dMEAN, 12, l->dA3, 128, 128, l->A3, 128, EPI_DELU, false, M, st));
+  RET_IF(dgrad(l, AB6, l->dMEAN, 12, l->dA3, 128, 128, l->A3, 128, EPI_DELU, false, M, st, AB4, 0));
   RET_IF(chain(l, st, sw));
   RET_IF(wgrad(l, AB4, l->dA3, 128, l->A2, 256, M, sw));
-  RET_IF(dgrad(l, CB6, l->dV, 4, l->dC3, 128, 128, l->C3, 128, EPI_DELU, false, M, sc));
+  RET_IF(dgrad(l, CB6, l->dV, 4, l->dC3, 128, 128, l->C3, 128, EPI_DELU, false, M, sc, CB4, 1));
   RET_IF(chain(l, sc, sw));
   RET_IF(wgrad(l, CB4, l->dC3, 128, l->C2, 256, M, sw));
-  RET_IF(dgrad(l, AB4, l->dA3, 128, l->dA2, 256, 256, l->A2, 256, EPI_DELU, false, M, st));
+  RET_IF(dgrad(l, AB4, l->dA3, 128, l->dA2, 256, 256, l->A2, 256, EPI_DELU, false, M, st, AB2, 0));
   RET_IF(chain(l, st, sw));
   RET_IF(wgrad(l, AB2, l->dA2, 256, l->A1, 512, M, sw));
-  RET_IF(dgrad(l, CB4, l->dC3, 128, l->dC2, 256, 256, l->C2, 256, EPI_DELU, false, M, sc));
+  RET_IF(dgrad(l, CB4, l->dC3, 128, l->dC2, 256, 256, l->C2, 256, EPI_DELU, false, M, sc, CB2, 1));
   RET_IF(chain(l, sc, sw));
   RET_IF(wgrad(l, CB2, l->dC2, 256, l->C1, 512, M, sw));
-  RET_IF(dgrad(l, AB2, l->dA2, 256, l->dA1, 512, 512, l->A1, 512, EPI_DELU, false, M, st));
+  RET_IF(dgrad(l, AB2, l->dA2, 256, l->dA1, 512, 512, l->A1, 512, EPI_DELU, false, M, st, AB0, 0));
   RET_IF(chain(l, st, sw));
   RET_IF(wgrad(l, AB0, l->dA1, 512, l->XA, LD_XA, M, sw));
-  RET_IF(dgrad(l, CB2, l->dC2, 256, l->dC1, 512, 512, l->C1, 512, EPI_DELU, false, M, sc));
+  RET_IF(dgrad(l, CB2, l->dC2, 256, l->dC1, 512, 512, l->C1, 512, EPI_DELU, false, M, sc, CB0, 1));
   RET_IF(chain(l, sc, sw));
   RET_IF(wgrad(l, CB0, l->dC1, 512, xc, LD_XC, M, sw));
-  RET_IF(dgrad(l, AB0, l->dA1, 512, l->dX, LD_XA, LD_XA, nullptr, 0, EPI_STORE, false, M, st));
+  RET_IF(dgrad(l, AB0, l->dA1, 512, l->dX, LD_XA, LD_XA, nullptr, 0, EPI_STORE, false, M, st, TE4, 0));
   RET_IF(encode_bwd(l, M, hist, priv_a, 0, 0, S));
   RET_IF(streams_end(l, S));
   if (sync_grads) return DTC_OK;
