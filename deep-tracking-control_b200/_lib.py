@@ -43,7 +43,7 @@ ENV_BUFFER_NAMES = [
     "last_dof_vel", "last_root_vel", "last_foot_vel", "motor_strengths", "robot_mass", "height_noise_offset",
     "forces0", "episode_length_buf", "terrain_levels", "terrain_types", "env_origins", "terrain_origins",
     "reset_buf", "time_out_buf", "rew_buf", "episode_sums", "reward_terms", "obs_buf", "privileged_obs_buf",
-    "obs_history", "episode_stats",
+    "obs_history", "episode_stats", "episode_stats_last", "time_outs_sent",
 ]
 
 
@@ -99,7 +99,7 @@ def lib():
     L.dtc_env_destroy.argtypes = [vp]
     L.dtc_env_destroy.restype = None
     L.dtc_env_bind.argtypes = [vp, C.POINTER(EnvBuffers)]
-    L.dtc_env_pre_physics.argtypes = [vp, vp, C.POINTER(C.c_int32), vp]
+    L.dtc_env_pre_physics.argtypes = [vp, vp, C.POINTER(C.c_int32), C.c_int32, C.c_int32, vp]
     L.dtc_env_state_prep.argtypes = [vp, C.c_int64, C.c_uint64, C.POINTER(EnvNoise), vp]
     L.dtc_foothold_step.argtypes = [vp, C.c_int, vp, vp]
     L.dtc_env_reward_reset.argtypes = [vp, C.c_int64, C.c_uint64, C.c_float, C.POINTER(EnvNoise), vp]
@@ -113,7 +113,7 @@ def lib():
     L.dtc_learner_stats.argtypes = [vp]
     L.dtc_param_get.argtypes = [C.c_int, C.POINTER(ParamInfo)]
     L.dtc_param_range.argtypes = [C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
-    L.dtc_learner_create.argtypes = [C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.POINTER(vp)]
+    L.dtc_learner_create.argtypes = [C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int64, vp, C.POINTER(vp)]
     L.dtc_learner_destroy.argtypes = [vp]
     L.dtc_learner_destroy.restype = None
     L.dtc_learner_refresh_params.argtypes = [vp, vp]

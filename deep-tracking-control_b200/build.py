@@ -29,7 +29,7 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         sp = os.path.join(CSRC, src)
         if not os.path.exists(sp):
-            continue
+            raise FileNotFoundError(f"{sp}: every source in SOURCES must exist (a partial libdtc_b200.so is never linked)")
         obj = os.path.join(PKG, "build", src.replace(".cu", ".o"))
         objs.append(obj)
         procs.append((src, subprocess.Popen([nvcc, *FLAGS, "-c", sp, "-o", obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

@@ -10,16 +10,23 @@ __device__ __forceinline__ Philox env_rng(uint64_t seed, int64_t step, int env, 
 }
 
 // ================================================================== E1 + E2
-// legged_robot.py:92-111 (clip, decimation loop) and :595-630 (_compute_torques).  With the simulator stubbed
-// dof_pos/dof_vel do not change inside the decimation loop, so the four sub-steps run back to back per thread.
+// legged_robot.py:92-111 (clip, decimation loop) and :595-630 (_compute_torques): sub-steps [first, first + count) of the
+// decimation loop.  A real simulator changes dof_pos / dof_vel between sub-steps, so the host launches one sub-step at a time
+// around gym.simulate(); when the simulator is a stub that leaves the dof state alone inside the loop the four sub-steps run
+// back to back in one launch (count = 4) - the same arithmetic either way.
 __global__ void __launch_bounds__(256) k_pre_physics(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b,
-                                                     const float* __restrict__ actions_in, int4 choice) {
+                                                     const float* __restrict__ actions_in, int4 choice, int first, int count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int N = cfg->num_envs;
   if (i >= N * 12) return;
-  int n = i / 12, j = i - n * 12;
-  float a = fminf(fmaxf(actions_in[i], -cfg->clip_actions), cfg->clip_actions);
-  b.actions[i] = a;
+  int j = i % 12;
+  float a;
+  if (first == 0) {
+    a = fminf(fmaxf(actions_in[i], -cfg->clip_actions), cfg->clip_actions);
+    b.actions[i] = a;
+  } else {
+    a = b.actions[i];
+  }
   float scaled = a * cfg->action_scale;
   float lag[6];
 #pragma unroll
@@ -30,6 +37,7 @@ __global__ void __launch_bounds__(256) k_pre_physics(const dtc_env_config* __res
   float tq = 0.f;
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
+    if (s < first || s >= first + count) continue;
 #pragma unroll
     for (int k = 0; k < 5; ++k) lag[k] = lag[k + 1];
     lag[5] = scaled;
@@ -45,7 +53,6 @@ __global__ void __launch_bounds__(256) k_pre_physics(const dtc_env_config* __res
   b.torques[i] = tq;
 #pragma unroll
   for (int k = 0; k < 6; ++k) b.lag_buffer[(size_t)k * N * 12 + i] = lag[k];
-  (void)n;
 }
 
 // ================================================================== E3 + E4 (command part)
@@ -172,10 +179,14 @@ __global__ void __launch_bounds__(128) k_reward_reset(const dtc_env_config* __re
     px = min(max(px, 1), rows - 3);
     py = min(max(py, 1), cols - 3);
     const int16_t* g = hs + (size_t)px * cols + py;
+    // px - 2 / py - 2 reach -1 for a foot at the low map edge (px, py are clipped to >= 1): torch indexing wraps a negative
+    // index to the far edge (height_samples[-1, py] is the LAST row), legged_robot.py:1456-1470
+    const int16_t* gxm2 = hs + (size_t)(px - 2 < 0 ? px - 2 + rows : px - 2) * cols + py;
+    const int16_t* gym2 = hs + (size_t)px * cols + (py - 2 < 0 ? py - 2 + cols : py - 2);
     int h = __ldg(g);
     h = max(h, (int)__ldg(g + cols)); h = max(h, (int)__ldg(g + 1)); h = max(h, (int)__ldg(g + 2 * cols));
     h = max(h, (int)__ldg(g + 2)); h = max(h, (int)__ldg(g + cols + 1)); h = max(h, (int)__ldg(g - cols));
-    h = max(h, (int)__ldg(g - 1)); h = max(h, (int)__ldg(g - 2 * cols)); h = max(h, (int)__ldg(g - 2));
+    h = max(h, (int)__ldg(g - 1)); h = max(h, (int)__ldg(gxm2)); h = max(h, (int)__ldg(gym2));
     clr[f] = __fsub_rn(fpos[f][2], __fmul_rn((float)h, cfg->vertical_scale));
     b.foot_clearance[n * 4 + f] = clr[f];
     contact[f] = fF[f][2] > 1.0f;
@@ -370,7 +381,10 @@ __global__ void __launch_bounds__(128) k_reward_reset(const dtc_env_config* __re
     b.reward_terms[(size_t)21 * N + n] = r; }
   b.rew_buf[n] = rew;
   b.reset_buf[n] = reset;
-  if (!reset) return;
+  if (!reset) {
+    atomicAdd(reinterpret_cast<int*>(b.episode_stats) + 25, (int)b.terrain_levels[n]);  // mean(terrain_levels) of extras["episode"]
+    return;
+  }
 
   // ---- E13 reset_idx (legged_robot.py:200-272), per environment
   float u[25];
@@ -401,6 +415,7 @@ __global__ void __launch_bounds__(128) k_reward_reset(const dtc_env_config* __re
       lv = min(r, cfg->max_terrain_level - 1);
     } else if (lv < 0) lv = 0;
     b.terrain_levels[n] = lv;
+    atomicAdd(reinterpret_cast<int*>(b.episode_stats) + 25, (int)lv);
     const float* to = b.terrain_origins + ((size_t)lv * cfg->num_terrain_cols + b.terrain_types[n]) * 3;
     b.env_origins[n * 3] = to[0]; b.env_origins[n * 3 + 1] = to[1]; b.env_origins[n * 3 + 2] = to[2];
   }
@@ -459,6 +474,12 @@ __global__ void __launch_bounds__(128) k_observe(const dtc_env_config* __restric
   if (n >= N) return;
   const float clipv = cfg->clip_obs;
   const float root_z = b.root_states[(size_t)n * 13 + 2];
+  // the reference's `extras` dict persists between steps and is rewritten only by a reset_idx() call with a non-empty id list
+  // (legged_robot.py:210,253-264): publish this step's episode statistics / time-out flags only if some environment was reset
+  if (b.episode_stats[24] > 0.f) {
+    if (lane == 0) b.time_outs_sent[n] = b.time_out_buf[n];
+    if (n == 0 && lane < 26) b.episode_stats_last[lane] = b.episode_stats[lane];
+  }
   // ---- obs (legged_robot_dtc.py:259-272, :287) + history shift (history_wrapper.py:23)
   float* hist = b.obs_history + (size_t)n * b.hist_ld;
   float* obs = b.obs_buf + (size_t)n * 53;
@@ -562,13 +583,17 @@ extern "C" int dtc_env_heightmap_updated(dtc_env* e) {
   if (!e || !e->bound) DTC_FAIL(DTC_ERR_STATE, "dtc_env_heightmap_updated: env not bound");
   return dtc_env_build_min3(e);
 }
-extern "C" int dtc_env_pre_physics(dtc_env* e, const float* actions_in, const int32_t lag_choice[4], void* stream) {
+extern "C" int dtc_env_pre_physics(dtc_env* e, const float* actions_in, const int32_t lag_choice[4], int32_t first_substep,
+                                   int32_t num_substeps, void* stream) {
   if (!e || !e->bound) DTC_FAIL(DTC_ERR_STATE, "dtc_env_pre_physics: env not bound");
-  for (int i = 0; i < 4; ++i)
+  if (first_substep < 0 || num_substeps < 1 || first_substep + num_substeps > 4)
+    DTC_FAIL(DTC_ERR_ARG, "dtc_env_pre_physics: sub-steps [%d, %d) outside the decimation loop [0, 4)", first_substep, first_substep + num_substeps);
+  for (int i = first_substep; i < first_substep + num_substeps; ++i)
     if (lag_choice[i] < 1 || lag_choice[i] > 4) DTC_FAIL(DTC_ERR_ARG, "lag choice must be in 1..4");
+  if (first_substep == 0 && !actions_in) DTC_FAIL(DTC_ERR_ARG, "dtc_env_pre_physics: actions_in is null");
   int total = e->cfg.num_envs * 12;
   k_pre_physics<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      e->d_cfg, e->buf, actions_in, make_int4(lag_choice[0], lag_choice[1], lag_choice[2], lag_choice[3]));
+      e->d_cfg, e->buf, actions_in, make_int4(lag_choice[0], lag_choice[1], lag_choice[2], lag_choice[3]), first_substep, num_substeps);
   DTC_CHECK_LAUNCH("k_pre_physics");
   return DTC_OK;
 }

@@ -17,6 +17,7 @@
 // with a cp.async.bulk.tensor.2d box load; an int16 / SWIZZLE_NONE tensor map raises "illegal instruction" on this device for every
 // box shape tried, so they were removed and the launcher rejects those ids.)
 #include <cuda.h>
+#include <stdlib.h>
 #include "dtc_common.cuh"
 #include "dtc_env_internal.cuh"
 
@@ -900,6 +901,460 @@ k_foothold_v5(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const i
   }
 }
 
+// ================================================================== variant 6: CTA-batched scalar work, fused sampling loop
+// ncu on variant 5 (profiles/r2_foothold_v5_lines.txt): 2620 warp instructions per environment at 56 % issue-slot use, 16 warps/SM.
+// 610 of them are per-environment SCALAR work every lane repeats (root state, yaw quaternion, cell arithmetic in fp64, Raibert
+// footholds, rotation tables), 150 the predicated 22-iteration exact-sample loop that 68 % of the environments enter for one or
+// two samples, 100 fp64 divisions.  Variant 6 keeps variant 5's arithmetic (same fast cell path, same exact fall-back, same
+// window search - results are bit-identical) and reorganises the work:
+//   * a CTA owns a contiguous chunk of environments; 128 THREADS prepare 32 environments x 4 legs at once (one thread per
+//     (environment, leg): per-environment constants and the leg's Raibert foothold go to a shared-memory record), then the four
+//     warps walk the chunk one environment each - the scalar work costs ~60 warp instructions per environment instead of 610;
+//   * sampling, height store, moments and plane fit run in ONE unrolled loop (no mh[22] register array); samples next to a cell
+//     boundary are skipped there and finished by a compact while-loop over the set bits of the per-lane mask;
+//   * exception flags are a byte array in shared memory (no mask shuffles), the rotation tables are gone (the window search
+//     rotates its <= 96 candidates directly), divisions by constants are multiplications;
+//   * one patch buffer per warp, refilled with cp.async right after the sampling loop so the copy overlaps the window search;
+//     6.8 KB of shared memory per warp and 96 registers put 20 warps on an SM (variant 5: 16);
+//   * the sampling loop runs on the packed fp32x2 pipe (FFMA2 / FADD2 / FMUL2: two samples per issue slot).
+// packed fp32x2 arithmetic of sm_100 (FFMA2 / FADD2 / FMUL2: two IEEE round-to-nearest results per issue slot)
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 f2_sub(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 f2(float v) { return make_float2(v, v); }
+
+#define V6_WARPS 4
+#define V6_PH 42     // patch rows
+#define V6_PC 48     // patch row pitch = copied columns (cells)
+#define V6_NK 22
+#define V6_BATCH 32  // environments prepared per CTA round (x 4 legs = 128 threads)
+#define V6_CTAS_PER_SM 6
+
+struct V6Rec {  // per-environment constants written by the prepare threads
+  float root_x, root_y, root_z, yz, yw;
+  float qx0, qy0, ca, sa;  // fast cell path: q = grid . (ca, -sa | sa, ca) + q0, in cells relative to the robot's cell centre
+  uint32_t kbase;          // byte offset constant of the patch lookup (see variant 5)
+  int fast, x0, y0;        // 1: patch staged and every sample interior; patch origin (cells)
+  float pf[4][3];          // Raibert nominal footholds (legged_robot_dtc.py:100-115)
+  int ci[4], cj[4];        // lattice cell nearest to each nominal foothold
+};
+struct __align__(16) V6Warp {
+  int16_t patch[V6_PH * V6_PC];  // 4032 B
+  float gc[NP + 3];              // clamped relative heights
+};
+struct __align__(16) V6Cta {
+  V6Warp w[V6_WARPS];
+  V6Rec rec[V6_BATCH];
+  float4 gtab[V6_NK / 2][32];    // (gx_k, gx_k+1, gy_k, gy_k+1) of the sample pair p = 32 k + lane, k even (p clamped to 692)
+  float gx[GXN + 3], gy[GYN + 3];
+};
+
+// one thread per (environment, leg): everything of the environment that does not depend on the grid point
+__device__ __forceinline__ void v6_prepare(const dtc_env_config* __restrict__ cfg, const dtc_env_buffers& b, int n, int l, V6Rec& R,
+                                           const V5Params& P) {
+  const float* rs = b.root_states + (size_t)n * 13;
+  const float root_x = rs[0], root_y = rs[1], root_z = rs[2];
+  float yz, yw;
+  yaw_quat_exact(rs[5], rs[6], yz, yw);
+  const float cpsi = 1.0f - 2.0f * yz * yz, spsi = 2.0f * yz * yw;
+  if (l == 0) {
+    const int rows = cfg->map_rows, cols = cfg->map_cols;
+    const double inv_h = 1.0 / (double)cfg->horizontal_scale;
+    const double cxd = ((double)root_x + (double)cfg->border_size) * inv_h, cyd = ((double)root_y + (double)cfg->border_size) * inv_h;
+    const double fx = floor(cxd), fy = floor(cyd);
+    const int cx = (int)fx, cy = (int)fy;
+    // bounding box of the rotated grid in cells, one cell of slack on every side
+    const float c = fabsf(cpsi), s = fabsf(spsi);
+    const int cex = (int)ceilf((P.ext_x * c + P.ext_y * s) * (float)inv_h), cey = (int)ceilf((P.ext_x * s + P.ext_y * c) * (float)inv_h);
+    const int x0 = cx - cex - 1, y0 = (cy - cey - 1) & ~7;
+    // the 4e-4-cell margin of the fast path holds for coordinates below 128 m
+    const int fast = (cx - cex >= 0 && cx + cex <= rows - 2 && cy - cey >= 0 && cy + cey <= cols - 2 && x0 >= 0 && x0 + V6_PH <= rows && y0 >= 0 &&
+                      y0 + V6_PC <= cols && 2 * cex + 3 <= V6_PH && cy + cey + 1 - y0 < V6_PC && fabsf(root_x) + cfg->border_size < 120.0f &&
+                      fabsf(root_y) + cfg->border_size < 120.0f) ? 1 : 0;
+    R.root_x = root_x; R.root_y = root_y; R.root_z = root_z; R.yz = yz; R.yw = yw;
+    R.qx0 = (float)(cxd - fx - 0.5);
+    R.qy0 = (float)(cyd - fy - 0.5);
+    R.ca = cpsi * (float)inv_h;
+    R.sa = spsi * (float)inv_h;
+    R.kbase = ((uint32_t)(cx - x0) - 0x4B400000u) * (uint32_t)(V6_PC * 2) + ((uint32_t)(cy - y0) - 0x4B400000u) * 2u;
+    R.fast = fast; R.x0 = x0; R.y0 = y0;
+  }
+  // Raibert nominal foothold of leg l
+  const float cmd_x = b.commands[n * 4 + 0], cmd_y = b.commands[n * 4 + 1], cmd_yaw = b.commands[n * 4 + 2];
+  const float vx = b.base_lin_vel[n * 3 + 0], vy = b.base_lin_vel[n * 3 + 1], vz = b.base_lin_vel[n * 3 + 2];
+  const float cth = cosf(cmd_yaw), sth = sinf(cmd_yaw);
+  const float sym_x = __fadd_rn(__fmul_rn(0.01f, vx), __fmul_rn(0.03f, __fsub_rn(vx, cmd_x)));
+  const float sym_y = __fadd_rn(__fmul_rn(0.01f, vy), __fmul_rn(0.03f, __fsub_rn(vy, cmd_y)));
+  const float sym_z = __fadd_rn(__fmul_rn(0.01f, vz), __fmul_rn(0.03f, vz));
+  const float* th = b.rigid_body_state + (size_t)n * 17 * 13 + (2 + 4 * l) * 13;  // thigh bodies 2,6,10,14
+  const float hx = __fsub_rn(th[0], root_x), hy = __fsub_rn(th[1], root_y), hz = __fsub_rn(th[2], root_z);
+  const float rxh = __fadd_rn(__fmul_rn(cth, hx), __fmul_rn(-sth, hy));
+  const float ryh = __fadd_rn(__fmul_rn(sth, hx), __fmul_rn(cth, hy));
+  const float pfx = __fadd_rn(__fadd_rn(root_x, rxh), sym_x);
+  const float pfy = __fadd_rn(__fadd_rn(root_y, ryh), sym_y);
+  const float pfz = __fadd_rn(__fadd_rn(root_z, hz), sym_z);
+  const float relx = pfx - root_x, rely = pfy - root_y;
+  const float lxf = cpsi * relx + spsi * rely, lyf = -spsi * relx + cpsi * rely;
+  R.pf[l][0] = pfx; R.pf[l][1] = pfy; R.pf[l][2] = pfz;
+  R.ci[l] = (int)floorf((lxf + 0.8f) * 20.0f + 0.5f);
+  R.cj[l] = (int)floorf((lyf + 0.5f) * 20.0f + 0.5f);
+}
+
+// 42 x 48-cell window of the min3 map around the rotated sampling grid: every lane moves eight 16-byte chunks (252 in all)
+__device__ __forceinline__ void v6_stage_patch(const int16_t* __restrict__ min3, int cols, const V6Rec& R, int16_t* patch, int lane) {
+  if (R.fast) {
+    const char* src0 = reinterpret_cast<const char*>(min3 + (size_t)R.x0 * cols + R.y0);
+    const uint32_t dst0 = smem_u32(patch);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ch = lane + 32 * i;
+      const int r = (ch * 171) >> 10, q = ch - 6 * r;  // row = ch / 6, 16-byte column chunk = ch % 6
+      if (ch < V6_PH * (V6_PC / 8))
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(r * (V6_PC * 2) + q * 16)),
+                     "l"(src0 + (size_t)r * (size_t)(cols * 2) + q * 16)
+                     : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <bool SEP, int CPS>
+__global__ void __launch_bounds__(V6_WARPS * 32, CPS)
+k_foothold_v6(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const int16_t* __restrict__ min3, const V5Params P, int per_cta) {
+  extern __shared__ __align__(128) uint8_t v6_smem_raw[];
+  V6Cta& S = *reinterpret_cast<V6Cta*>(v6_smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  V6Warp& W = S.w[warp];
+  const int N = cfg->num_envs;
+  const int c0 = blockIdx.x * per_cta, c1 = min(N, c0 + per_cta);
+  if (c0 >= N) return;
+  const int rows = cfg->map_rows, cols = cfg->map_cols;
+  const float border = cfg->border_size, hscale = cfg->horizontal_scale, vscale = cfg->vertical_scale;
+  if (threadIdx.x < GXN) S.gx[threadIdx.x] = cfg->grid_x[threadIdx.x];
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + GYN) S.gy[threadIdx.x - 64] = cfg->grid_y[threadIdx.x - 64];
+  for (int i = threadIdx.x; i < (V6_NK / 2) * 32; i += V6_WARPS * 32) {
+    const int pa_ = min(64 * (i >> 5) + (i & 31), NP - 1), pb_ = min(pa_ + 32, NP - 1);
+    S.gtab[i >> 5][i & 31] = make_float4(cfg->grid_x[pa_ / GYN], cfg->grid_x[pb_ / GYN], cfg->grid_y[pa_ % GYN], cfg->grid_y[pb_ % GYN]);
+  }
+  // window slots of the per-leg search (see variant 5): the 7x7 lattice window minus its corners = 45 candidates; two legs share
+  // three passes (slots 0..31 of each leg, then slots 32..44 of both on lanes 0..12 / 16..28)
+  auto slot_offset = [](int s, int& wi, int& wj) {
+    const int r = s < 5 ? s + 1 : (s < 40 ? s + 2 : s + 3);
+    wi = r / 7 - 3; wj = r - (r / 7) * 7 - 3;
+  };
+  int wi_a, wj_a, wi_c, wj_c;
+  slot_offset(lane, wi_a, wj_a);
+  slot_offset(32 + min(lane & 15, 12), wi_c, wj_c);
+  const bool c_live = (lane & 15) < 13;
+  const float inv_sp = __frcp_rn(0.05f);
+  const float* gcw = W.gc;
+
+  for (int base = c0; base < c1; base += V6_BATCH) {
+    const int nb = min(V6_BATCH, c1 - base);
+    __syncthreads();  // the previous round's records are no longer read (first round: the constant tables are written)
+    if ((int)(threadIdx.x >> 2) < nb) v6_prepare(cfg, b, base + (threadIdx.x >> 2), threadIdx.x & 3, S.rec[threadIdx.x >> 2], P);
+    __syncthreads();
+    if (warp < nb) v6_stage_patch(min3, cols, S.rec[warp], W.patch, lane);
+    for (int e = warp; e < nb; e += V6_WARPS) {
+      const V6Rec& R = S.rec[e];
+      const int n = base + e;
+      const float root_x = R.root_x, root_y = R.root_y, root_z = R.root_z, yz = R.yz, yw = R.yw;
+      float* mh_out = b.measured_heights + (size_t)n * NP;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+
+      // ---------------------------------------------------------------- phase 1: samples, stores, moments, plane fit
+      // Two samples (k, k + 1) per iteration on the packed fp32x2 pipe.  Every sample goes through the fast cell path and is
+      // stored / accumulated at once; the few within 4e-4 cells of a cell boundary (where the reference's own fp32 rounding
+      // decides the cell) are corrected afterwards: the exact op-by-op sample replaces the stored value and the difference of the
+      // two contributions is added to the sums.
+      float2 s1 = f2(0.f), s2 = f2(0.f), pa = f2(0.f), pb = f2(0.f);
+      float cs = 0.f, mh0 = 0.f, c0s = 0.f;
+      unsigned slowm = 0u, excm = 0u;  // per-lane bit k: sample 32 k + lane is redone exactly / is an exception point (|g| > 1)
+      const float2 rz2 = f2(root_z);
+      if (R.fast) {
+        const char* patch_b = reinterpret_cast<const char*>(W.patch);
+        const float2 ca2 = f2(R.ca), sa2 = f2(R.sa), nsa2 = f2(-R.sa), qx02 = f2(R.qx0), qy02 = f2(R.qy0);
+        const float2 M2 = f2(12582912.0f), vs2 = f2(vscale);
+        const uint32_t kbase = R.kbase;
+        float2 c0s2 = f2(0.f), mh02 = f2(0.f);
+#pragma unroll
+        for (int kk = 0; kk < V6_NK / 2; ++kk) {
+          const int k = 2 * kk;
+          const float4 g = S.gtab[kk][lane];
+          const float2 gx2 = make_float2(g.x, g.y), gy2 = make_float2(g.z, g.w);
+          const float2 qx = f2_fma(gx2, ca2, f2_fma(gy2, nsa2, qx02));
+          const float2 qy = f2_fma(gx2, sa2, f2_fma(gy2, ca2, qy02));
+          const float2 tx = f2_add(qx, M2), ty = f2_add(qy, M2);
+          const float2 rx = f2_sub(qx, f2_sub(tx, M2)), ry = f2_sub(qy, f2_sub(ty, M2));
+          if (fmaxf(fabsf(rx.x), fabsf(ry.x)) > 0.5f - 4.0e-4f) slowm |= 1u << k;
+          if (fmaxf(fabsf(rx.y), fabsf(ry.y)) > 0.5f - 4.0e-4f) slowm |= 2u << k;
+          const uint32_t off0 = __float_as_uint(tx.x) * (uint32_t)(V6_PC * 2) + __float_as_uint(ty.x) * 2u + kbase;
+          const uint32_t off1 = __float_as_uint(tx.y) * (uint32_t)(V6_PC * 2) + __float_as_uint(ty.y) * 2u + kbase;
+          const float2 mh = f2_mul(make_float2((float)*reinterpret_cast<const int16_t*>(patch_b + off0),
+                                               (float)*reinterpret_cast<const int16_t*>(patch_b + off1)), vs2);
+          if (kk == 0) {
+            // shift of the cancellation-free moments / plane fit: ANY height near the data works - lane 0's first sample
+            mh0 = __shfl_sync(0xffffffffu, mh.x, 0);
+            c0s = fminf(fmaxf(__fsub_rn(mh0, root_z), -0.5f), 0.5f);
+            c0s2 = f2(c0s); mh02 = f2(mh0);
+          }
+          const bool last = (k + 1 == V6_NK - 1);                         // sample 21 exists on lanes 0..20 only
+          const bool live1 = !last || lane < NP - 32 * (V6_NK - 1);
+          const int p = 32 * k + lane;
+          mh_out[p] = mh.x;
+          if (live1) mh_out[p + 32] = mh.y;
+          const float2 graw = f2_sub(mh, rz2);
+          if (fabsf(graw.x) > 1.0f) excm |= 1u << k;
+          if (fabsf(graw.y) > 1.0f) excm |= 2u << k;
+          const float2 gc = make_float2(fminf(fmaxf(graw.x, -0.5f), 0.5f), fminf(fmaxf(graw.y, -0.5f), 0.5f));
+          W.gc[p] = gc.x;
+          if (live1) W.gc[p + 32] = gc.y;
+          float2 d = f2_sub(gc, c0s2), dm = f2_sub(mh, mh02);
+          if (last) { d.y = live1 ? d.y : 0.f; dm.y = live1 ? dm.y : 0.f; }
+          s1 = f2_add(s1, d);
+          s2 = f2_fma(d, d, s2);
+          pa = f2_fma(SEP ? gx2 : make_float2(cfg->plane_op[p], cfg->plane_op[min(p + 32, NP - 1)]), dm, pa);
+          pb = f2_fma(SEP ? gy2 : make_float2(cfg->plane_op[NP + p], cfg->plane_op[NP + min(p + 32, NP - 1)]), dm, pb);
+          // centre block of check_termination: rows 10..22 = points 210..482
+          if ((32 * k + 31 >= 10 * GYN) && (32 * k < (GXN - 10) * GYN)) {
+            const bool in0 = (32 * k >= 10 * GYN && 32 * k + 31 < (GXN - 10) * GYN) || (p >= 10 * GYN && p < (GXN - 10) * GYN);
+            if (in0) cs += __fsub_rn(root_z, fmaxf(mh.x, 0.f));
+          }
+          if ((32 * k + 63 >= 10 * GYN) && (32 * k + 32 < (GXN - 10) * GYN)) {
+            const bool in1 = (32 * k + 32 >= 10 * GYN && 32 * k + 63 < (GXN - 10) * GYN) || (p + 32 >= 10 * GYN && p + 32 < (GXN - 10) * GYN);
+            if (in1) cs += __fsub_rn(root_z, fmaxf(mh.y, 0.f));
+          }
+        }
+        if (lane >= NP - 32 * (V6_NK - 1)) slowm &= ~(1u << (V6_NK - 1));
+        // corrections: exact sample, and the old contribution (recomputed from the patch on the same fast path) out of the sums
+        while (__any_sync(0xffffffffu, slowm != 0u)) {
+          if (slowm) {
+            const int k = __ffs(slowm) - 1;
+            slowm &= slowm - 1u;
+            const int p = 32 * k + lane;
+            const float4 g = S.gtab[k >> 1][lane];
+            const float gx = (k & 1) ? g.y : g.x, gy = (k & 1) ? g.w : g.z;
+            const float qx = fmaf(gx, R.ca, fmaf(gy, -R.sa, R.qx0)), qy = fmaf(gx, R.sa, fmaf(gy, R.ca, R.qy0));
+            const uint32_t off = __float_as_uint(qx + 12582912.0f) * (uint32_t)(V6_PC * 2) + __float_as_uint(qy + 12582912.0f) * 2u + kbase;
+            const float mh_old = __fmul_rn((float)*reinterpret_cast<const int16_t*>(patch_b + off), vscale);
+            const float mh_new = v5_exact_sample(min3, rows, cols, gx, gy, yz, yw, root_x, root_y, border, hscale, vscale);
+            if (mh_new != mh_old) {
+              mh_out[p] = mh_new;
+              excm = fabsf(__fsub_rn(mh_new, root_z)) > 1.0f ? (excm | (1u << k)) : (excm & ~(1u << k));
+              const float g_old = fminf(fmaxf(__fsub_rn(mh_old, root_z), -0.5f), 0.5f), g_new = fminf(fmaxf(__fsub_rn(mh_new, root_z), -0.5f), 0.5f);
+              W.gc[p] = g_new;
+              const float d_old = g_old - c0s, d_new = g_new - c0s;
+              s1.x += d_new - d_old;
+              s2.x += d_new * d_new - d_old * d_old;
+              if (p >= 10 * GYN && p < (GXN - 10) * GYN) cs += __fsub_rn(root_z, fmaxf(mh_new, 0.f)) - __fsub_rn(root_z, fmaxf(mh_old, 0.f));
+              pa.x = fmaf(SEP ? gx : cfg->plane_op[p], mh_new - mh_old, pa.x);
+              pb.x = fmaf(SEP ? gy : cfg->plane_op[NP + p], mh_new - mh_old, pb.x);
+            }
+          }
+        }
+      } else {
+        // robot at the map border (no staged patch): every sample on the exact path
+        c0s = fminf(fmaxf(-root_z, -0.5f), 0.5f);
+#pragma unroll 1
+        for (int k = 0; k < V6_NK; ++k) {
+          const int p = 32 * k + lane;
+          if (p < NP) {
+            const float4 g = S.gtab[k >> 1][lane];
+            const float gx = (k & 1) ? g.y : g.x, gy = (k & 1) ? g.w : g.z;
+            const float mh = v5_exact_sample(min3, rows, cols, gx, gy, yz, yw, root_x, root_y, border, hscale, vscale);
+            mh_out[p] = mh;
+            if (fabsf(__fsub_rn(mh, root_z)) > 1.0f) excm |= 1u << k;
+            const float gc = fminf(fmaxf(__fsub_rn(mh, root_z), -0.5f), 0.5f);
+            W.gc[p] = gc;
+            const float d = gc - c0s;
+            s1.x += d;
+            s2.x = fmaf(d, d, s2.x);
+            if (p >= 10 * GYN && p < (GXN - 10) * GYN) cs += __fsub_rn(root_z, fmaxf(mh, 0.f));
+            pa.x = fmaf(SEP ? gx : cfg->plane_op[p], mh, pa.x);
+            pb.x = fmaf(SEP ? gy : cfg->plane_op[NP + p], mh, pb.x);
+          }
+        }
+      }
+      __syncwarp();  // every lane is done with the patch: refill it for this warp's next environment while the search runs
+      if (e + V6_WARPS < nb) v6_stage_patch(min3, cols, S.rec[e + V6_WARPS], W.patch, lane);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+      const double S1 = warp_sum((double)s1.x + (double)s1.y), S2 = warp_sum((double)s2.x + (double)s2.y);
+      const float CS = warp_sum(cs);
+      const double PA = (double)warp_sum(pa.x + pa.y) * (SEP ? (double)P.ax : 1.0) + (double)mh0 * P.r0;
+      const double PB = (double)warp_sum(pb.x + pb.y) * (SEP ? (double)P.ay : 1.0) + (double)mh0 * P.r1;
+      const double mean_d = (double)c0s + S1 * (1.0 / (double)NP);
+      double var_d = (S2 - S1 * S1 * (1.0 / (double)NP)) * (1.0 / (double)(NP - 1));
+      var_d = var_d < 0.0 ? 0.0 : var_d;
+      const float mean = (float)mean_d;
+      const float edge = fminf(fmaxf(__fsqrt_rn((float)var_d), 0.0f), 0.3f);
+      if (lane == 0) {
+        b.center_clear_mean[n] = CS * (1.0f / (float)((GXN - 20) * GYN));
+        b.plane_ab[n * 2] = (float)PA;
+        b.plane_ab[n * 2 + 1] = (float)PB;
+      }
+      __syncwarp();  // orders this warp's measured_heights / gc stores before the reads below
+
+      // ---------------------------------------------------------------- terrain score of one grid point (branch-free)
+      const float e02 = __fmul_rn(0.2f, edge);
+      auto score = [&](int p, int ix, int iy) {  // s in [0, 0.1) or 10 (legged_robot_dtc.py:134-148)
+        const int pxm = ix > 0 ? p - GYN : p, pxp = ix < GXN - 1 ? p + GYN : p;
+        const int pym = iy > 0 ? p - 1 : p, pyp = iy < GYN - 1 ? p + 1 : p;
+        const float g = gcw[p];
+        float dx = div_by_const_rn(__fsub_rn(gcw[pxp], gcw[pxm]), 0.05f, inv_sp);
+        float dy = div_by_const_rn(__fsub_rn(gcw[pyp], gcw[pym]), 0.05f, inv_sp);
+        if (ix > 0 && ix < GXN - 1) dx = __fmul_rn(dx, 0.5f);
+        if (iy > 0 && iy < GYN - 1) dy = __fmul_rn(dy, 0.5f);
+        const float slope = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+        const float rough = fabsf(__fsub_rn(g, mean));
+        const float s = __fadd_rn(__fadd_rn(e02, slope), __fmul_rn(0.3f, rough));
+        return s < 0.1f ? s : 10.0f;
+      };
+      // exception point: |measured height - base z| > 1 before the clamp (legged_robot_dtc.py:131); the flag lives in lane p % 32
+      auto is_exc = [&](int p) { return ((__shfl_sync(0xffffffffu, excm, p & 31) >> (p >> 5)) & 1u) != 0u; };
+
+      // ---------------------------------------------------------------- phase 3: window search around the nominal footholds
+      int my_idx = 0x7fffffff, my_nom = 0x7fffffff;  // results of leg `lane` (lanes 0..3)
+      bool need_fallback = false;
+      auto candidate = [&](int leg, int wi, int wj, bool live, unsigned& db, unsigned& vb, int& p, bool& in_r, bool& adm) {
+        const float lpfx = R.pf[leg][0], lpfy = R.pf[leg][1];
+        const int i = R.ci[leg] + wi, j = R.cj[leg] + wj;
+        const bool valid = live && i >= 0 && i < GXN && j >= 0 && j < GYN;
+        const int ic = min(max(i, 0), GXN - 1), jc = min(max(j, 0), GYN - 1);
+        p = ic * GYN + jc;
+        const bool exc = is_exc(p);
+        float rx, ry;
+        yaw_apply_exact(yz, yw, S.gx[ic], S.gy[jc], rx, ry);
+        const float ddx = __fsub_rn(lpfx, __fadd_rn(rx, root_x)), ddy = __fsub_rn(lpfy, __fadd_rn(ry, root_y));
+        const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
+        in_r = valid && d < 0.16f;
+        adm = in_r && !exc;
+        const float v = __fadd_rn(__fmul_rn(score(p, ic, jc), 0.2f), __fmul_rn(d, 0.8f));
+        db = __float_as_uint(d); vb = __float_as_uint(v);
+      };
+#pragma unroll 1
+      for (int lp = 0; lp < 2; ++lp) {
+        const int l0 = 2 * lp, l1 = l0 + 1;
+        unsigned bs[2] = {0x7f7fffffu, 0x7f7fffffu}, bd[2] = {0x7f7fffffu, 0x7f7fffffu};  // value bits; FLT_MAX = nothing found
+        int bsi[2] = {0x7fffffff, 0x7fffffff}, bdi[2] = {0x7fffffff, 0x7fffffff};
+        unsigned db, vb;
+        int p;
+        bool in_r, adm;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {  // passes A and B: slots 0..31 of leg l0 / l1
+          candidate(k == 0 ? l0 : l1, wi_a, wj_a, true, db, vb, p, in_r, adm);
+          if (in_r) { bd[k] = db; bdi[k] = p; }
+          if (adm) { bs[k] = vb; bsi[k] = p; }
+        }
+        // pass C: slots 32..44 of both legs (lanes 0..12 -> l0, lanes 16..28 -> l1)
+        candidate(lane < 16 ? l0 : l1, wi_c, wj_c, c_live, db, vb, p, in_r, adm);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const bool mine = (lane < 16) == (k == 0);
+          if (mine && in_r && (db < bd[k] || (db == bd[k] && p < bdi[k]))) { bd[k] = db; bdi[k] = p; }
+          if (mine && adm && (vb < bs[k] || (vb == bs[k] && p < bsi[k]))) { bs[k] = vb; bsi[k] = p; }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          int ri, rn;
+          v5_argmin(bs[k], bsi[k], ri);
+          v5_argmin(bd[k], bdi[k], rn);
+          if (lane == l0 + k) { my_idx = ri; my_nom = rn; }
+          need_fallback |= (ri == 0x7fffffff);
+        }
+      }
+      int fbi = 0;
+      if (need_fallback) {  // warp-uniform: argmin_p (exc ? 10 : 0.2 s_p + 8), lowest index on ties
+        const float c8 = __fmul_rn(10.0f, 0.8f);
+        float fbv = 3.0e38f;
+        fbi = 0x7fffffff;
+#pragma unroll 1
+        for (int k = 0; k < V6_NK; ++k) {
+          const int p = 32 * k + lane;
+          if (p < NP) {
+            const int ix = p / GYN, iy = p - ix * GYN;
+            const float v = ((excm >> k) & 1u) ? 10.0f : __fadd_rn(__fmul_rn(score(p, ix, iy), 0.2f), c8);
+            if (v < fbv) { fbv = v; fbi = p; }
+          }
+        }
+        warp_argmin(fbv, fbi);
+      }
+      if (lane < 4) {
+        const int l = lane;
+        const int idx = my_idx != 0x7fffffff ? my_idx : fbi, nom = my_nom != 0x7fffffff ? my_nom : 0;
+        const int xi = idx % GYN, yi = idx / GYN;  // reference quirk: x list indexed by idx%21, y list by (idx//21)%21
+        float rx, ry;
+        yaw_apply_exact(yz, yw, S.gx[yi], S.gy[xi], rx, ry);
+        b.optimal_idx[n * 4 + l] = idx;
+        b.nominal_idx[n * 4 + l] = nom;
+        b.foothold_obs[n * 8 + l] = S.gx[xi];
+        b.foothold_obs[n * 8 + 4 + l] = S.gy[yi % GYN];
+        float* pf = b.pred_footholds + (size_t)n * 12 + l * 3;
+        pf[0] = R.pf[l][0]; pf[1] = R.pf[l][1]; pf[2] = R.pf[l][2];
+        float* ow = b.optimal_footholds_world + (size_t)n * 12 + l * 3;
+        ow[0] = __fadd_rn(rx, root_x);
+        ow[1] = __fadd_rn(ry, root_y);
+        ow[2] = __ldcg(mh_out + idx);
+      }
+      __syncwarp();  // gc is rewritten by this warp's next environment
+    }
+  }
+}
+
+template <bool SEP, int CPS>
+static int launch_v6(dtc_env* e, const V5Params& P, cudaStream_t st) {
+  static int sms = 0;
+  const int smem = (int)sizeof(V6Cta);
+  if (!sms) {
+    int dev = 0, ctas = 0;
+    DTC_CUDA(cudaGetDevice(&dev));
+    DTC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DTC_CUDA(cudaFuncSetAttribute(k_foothold_v6<SEP, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DTC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_foothold_v6<SEP, CPS>, V6_WARPS * 32, smem));
+    if (ctas < 1) { sms = 0; DTC_FAIL(DTC_ERR_CUDA, "k_foothold_v6 does not fit on this device"); }
+  }
+  const int N = e->cfg.num_envs;
+  // contiguous chunks, a whole number of environments per warp, one wave of CTAs
+  int per = ceil_div(N, sms * CPS);
+  per = ceil_div(per, V6_WARPS) * V6_WARPS;
+  k_foothold_v6<SEP, CPS><<<ceil_div(N, per), V6_WARPS * 32, smem, st>>>(e->d_cfg, e->buf, e->min3, P, per);
+  return DTC_OK;
+}
+static int v6_cps() {  // resident CTAs per SM the kernel is compiled for (env DTC_FH_CPS = 4 | 5 | 6, tuning knob)
+  static int cps = 0;
+  if (!cps) { const char* s = getenv("DTC_FH_CPS"); cps = s ? atoi(s) : 5; if (cps < 4 || cps > 6) cps = 5; }
+  return cps;
+}
+template <bool SEP>
+static int launch_v6_any(dtc_env* e, const V5Params& P, cudaStream_t st) {
+  switch (v6_cps()) {
+    case 4: return launch_v6<SEP, 4>(e, P, st);
+    case 5: return launch_v6<SEP, 5>(e, P, st);
+    default: return launch_v6<SEP, 6>(e, P, st);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_min3_map(const int16_t* __restrict__ H, int16_t* __restrict__ out, int rows, int cols) {
   const int64_t total = (int64_t)rows * cols;
   for (int64_t e = blockIdx.x * 256ll + threadIdx.x; e < total; e += gridDim.x * 256ll) {
@@ -969,24 +1424,31 @@ extern "C" int dtc_foothold_step(dtc_env* e, int variant, float* debug_score, vo
   cudaStream_t st = (cudaStream_t)stream;
   int N = e->cfg.num_envs;
   dim3 grid(ceil_div(N, FH_WARPS)), block(FH_WARPS * 32);
-  if (variant >= 3 && variant <= 5 && (e->cfg.map_cols * 2) % 16 != 0)
+  if (variant >= 3 && variant <= 6 && (e->cfg.map_cols * 2) % 16 != 0)
     DTC_FAIL(DTC_ERR_ARG, "TMA variants need 16-byte aligned heightmap rows");
-  dtc_prof_begin(st, 1, 0.0);
-  if (variant == 1 || variant == 2) {
+  if (variant == 1 || variant == 2)
     DTC_FAIL(DTC_ERR_ARG, "dtc_foothold_step: variants 1 and 2 (tensor-map staging) were removed; use 0, 3, 4 or 5");
-  } else if (variant == 3) {
+  if (variant != 0 && (variant < 3 || variant > 6)) DTC_FAIL(DTC_ERR_ARG, "dtc_foothold_step: unknown variant %d", variant);
+  if (variant >= 5 && !e->min3) DTC_FAIL(DTC_ERR_STATE, "dtc_foothold_step: min3 map missing (dtc_env_bind builds it)");
+  if (variant >= 5 && debug_score) {
+    // test-only: the reference's [N,693,4] score tensor comes from the brute-force kernel; variant 5 then overwrites every
+    // other output, so argmin(debug_score) == optimal_idx checks variant 5's window search against the full scan
+    k_foothold<0><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score);
+    DTC_CHECK_LAUNCH("k_foothold<0> (score dump)");
+  }
+  dtc_prof_begin(st, 1, 0.0);
+  if (variant == 3) {
     k_foothold<3><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score);
   } else if (variant == 4) {
     k_foothold_v4<<<ceil_div(N, V4_WARPS), V4_WARPS * 32, 0, st>>>(e->d_cfg, e->buf, debug_score);
-  } else if (variant == 5 && !debug_score) {
-    if (!e->min3) DTC_FAIL(DTC_ERR_STATE, "dtc_foothold_step: min3 map missing (dtc_env_bind builds it)");
+  } else if (variant == 5 || variant == 6) {
     bool sep = false;
     const V5Params P = v5_params(e->cfg, &sep);
-    RETURN_IF_ERR(sep ? launch_v5<true>(e, P, st) : launch_v5<false>(e, P, st));
-  } else if (variant == 0 || variant == 5) {  // the brute-force debug dump of variant 5 is variant 0's
-    k_foothold<0><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score);
+    const int rc = variant == 5 ? (sep ? launch_v5<true>(e, P, st) : launch_v5<false>(e, P, st))
+                                : (sep ? launch_v6_any<true>(e, P, st) : launch_v6_any<false>(e, P, st));
+    if (rc) { dtc_prof_end(st); return rc; }
   } else {
-    DTC_FAIL(DTC_ERR_ARG, "dtc_foothold_step: unknown variant %d", variant);
+    k_foothold<0><<<grid, block, 0, st>>>(e->d_cfg, e->buf, debug_score);
   }
   DTC_CHECK_LAUNCH("k_foothold");
   dtc_prof_end(st);

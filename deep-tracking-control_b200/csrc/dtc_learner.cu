@@ -238,7 +238,7 @@ extern "C" int64_t dtc_learner_workspace_bytes(int32_t max_rows) {
 
 extern "C" int dtc_learner_create(int32_t max_rows, float* params, float* grads, float* adam_main_m, float* adam_main_v,
                                   float* adam_vae_m, float* adam_vae_v, void* workspace, int64_t workspace_bytes,
-                                  dtc_learner** out) {
+                                  void* stream, dtc_learner** out) {
   build_table();
   if (!out || !params || !workspace || max_rows <= 0) DTC_FAIL(DTC_ERR_ARG, "dtc_learner_create: bad arguments");
   if (workspace_bytes < dtc_learner_workspace_bytes(max_rows)) DTC_FAIL(DTC_ERR_ARG, "dtc_learner_create: workspace too small");
@@ -268,10 +268,11 @@ extern "C" int dtc_learner_create(int32_t max_rows, float* params, float* grads,
   l->last_M = 0;
   l->side_ready = false;
   l->ev_next = 0;
-  DTC_CUDA(cudaMemset(l->stats, 0, ST_COUNT * sizeof(double)));
-  DTC_CUDA(cudaMemset(l->ws_val_begin, 0, 2 * ws_value_bytes(R)));
+  // ordered with the caller's own work (the parameter upload ahead of this call, the first step after it): no host sync
+  DTC_CUDA(cudaMemsetAsync(l->stats, 0, ST_COUNT * sizeof(double), (cudaStream_t)stream));
+  DTC_CUDA(cudaMemsetAsync(l->ws_val_begin, 0, 2 * ws_value_bytes(R), (cudaStream_t)stream));
   *out = l;
-  return dtc_learner_refresh_params(l, nullptr);
+  return dtc_learner_refresh_params(l, stream);
 }
 extern "C" void dtc_learner_destroy(dtc_learner* l) {
   if (!l) return;

@@ -26,14 +26,15 @@ class _Scales:
 
 class LeggedRobotDTC:
     def __init__(self, cfg, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True, *, gym,
-                 height_samples, terrain_origins, layout, seed=0, foothold_variant=5, robot_mass=12.0):
+                 height_samples, terrain_origins, layout, seed=0, foothold_variant=6, robot_mass=12.0):
         self.cfg = cfg
         self.device = torch.device(sim_device)
         if self.device.type != "cuda":
             raise B.DtcError("LeggedRobotDTC runs on a CUDA device only (no CPU fallback)")
         self.lib = B.lib()
         self.gym = gym
-        self.sim = None
+        self.sim = getattr(gym, "sim", None)
+        self._unwrap = getattr(gym, "unwrap_tensor", None) or (lambda t: t)  # gymtorch.unwrap_tensor for Isaac Gym's tensor API
         self.headless = headless
         self.viewer = None
         self.debug_viz = False
@@ -53,7 +54,6 @@ class LeggedRobotDTC:
         self.seed = int(seed)
         self.np_rng = np.random.default_rng(seed)
         self.common_step_counter = 0
-        self.extras = {}
         self.init_done = True
         dev = self.device
         f = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
@@ -114,7 +114,8 @@ class LeggedRobotDTC:
         self._forces0 = f(N, 3)
         self._episode_sums = f(24, N)
         self._reward_terms = f(24, N)
-        self._episode_stats = f(26)
+        self._episode_stats, self._episode_stats_last = f(26), f(26)
+        self._time_outs_sent = u8(N)
         self.episode_sums = {k: self._episode_sums[i] for i, k in enumerate(L.EPISODE_SUM_NAMES)}
         self.default_dof_pos = torch.tensor(L.DEFAULT_DOF_POS, device=dev).unsqueeze(0)
         self.dof_pos_limits = torch.tensor(L.soft_dof_pos_limits(), device=dev)
@@ -127,6 +128,7 @@ class LeggedRobotDTC:
         self._noise = None  # injected draws (tests): dict of CUDA tensors keyed like dtc_env_noise
         self._host_draws = None  # injected host draws: dict(lag=[4 ints], reset_normal=float)
         self._make_ctx()
+        self.extras = _Extras(self)
 
     # ------------------------------------------------------------------ construction helpers
     def _noise_scale_vec(self):
@@ -210,7 +212,8 @@ class LeggedRobotDTC:
             terrain_levels=self.terrain_levels, terrain_types=self.terrain_types, env_origins=self.env_origins,
             terrain_origins=self.terrain_origins, reset_buf=self.reset_buf, time_out_buf=self.time_out_buf,
             rew_buf=self.rew_buf, episode_sums=self._episode_sums, reward_terms=self._reward_terms, obs_buf=self.obs_buf,
-            privileged_obs_buf=self._priv_store, obs_history=self._hist_store, episode_stats=self._episode_stats)
+            privileged_obs_buf=self._priv_store, obs_history=self._hist_store, episode_stats=self._episode_stats,
+            episode_stats_last=self._episode_stats_last, time_outs_sent=self._time_outs_sent)
         b = B.EnvBuffers()
         for name in B.ENV_BUFFER_NAMES:
             x = t[name]
@@ -306,10 +309,21 @@ class LeggedRobotDTC:
         hd = self._host_draws or {}
         lag = hd.get("lag") or [int(self.np_rng.integers(1, 5)) for _ in range(L.DECIMATION)]
         arr = (C.c_int32 * 4)(*lag)
-        B.check(lib.dtc_env_pre_physics(self._h, B.ptr(actions), arr, st), "dtc_env_pre_physics")
-        for _ in range(L.DECIMATION):
-            self.gym.simulate(self.sim)
-            self.gym.refresh_dof_state_tensor(self.sim)
+        gym, sim, uw = self.gym, self.sim, self._unwrap
+        if getattr(gym, "static_dof_state", False):
+            # stubbed simulator: the dof state does not move inside the decimation loop -> the four PD sub-steps in one launch
+            B.check(lib.dtc_env_pre_physics(self._h, B.ptr(actions), arr, 0, L.DECIMATION, st), "dtc_env_pre_physics")
+            for _ in range(L.DECIMATION):
+                gym.set_dof_actuation_force_tensor(sim, uw(self.torques))
+                gym.simulate(sim)
+                gym.refresh_dof_state_tensor(sim)
+        else:
+            # legged_robot.py:102-111: torque from the refreshed dof state in every sub-step, handed to the simulator each time
+            for s in range(L.DECIMATION):
+                B.check(lib.dtc_env_pre_physics(self._h, B.ptr(actions), arr, s, 1, st), "dtc_env_pre_physics")
+                gym.set_dof_actuation_force_tensor(sim, uw(self.torques))
+                gym.simulate(sim)
+                gym.refresh_dof_state_tensor(sim)
         self.post_physics_step()
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
 
@@ -328,8 +342,12 @@ class LeggedRobotDTC:
         B.check(lib.dtc_foothold_step(self._h, self.foothold_variant, dbg, st), "dtc_foothold_step")
         rn = hd["reset_normal"] if "reset_normal" in hd else float(self.np_rng.normal(0, 0.02))
         B.check(lib.dtc_env_reward_reset(self._h, step, seed, rn, C.byref(nz), st), "dtc_env_reward_reset")
+        # pushes (legged_robot.py:673-678) and in-episode resets (:640-667) were written into root_states / dof_state on the device;
+        # hand them to the simulator.  Which environments were reset is not known on the host (no nonzero() sync), so the whole
+        # tensors go back: rows the kernel did not touch still hold what the simulator produced.
+        self.gym.set_actor_root_state_tensor(self.sim, self._unwrap(self.root_states))
+        self.gym.set_dof_state_tensor(self.sim, self._unwrap(self.dof_state))
         B.check(lib.dtc_env_observe(self._h, step, seed, C.byref(nz), st), "dtc_env_observe")
-        self.extras = _LazyExtras(self)
 
     def _pre_reset_all(self, hd):
         """Full-batch reset_idx (legged_robot.py:200-272) ahead of the first step: done with torch ops on the
@@ -371,6 +389,11 @@ class LeggedRobotDTC:
                   self.ang_vel_buffer, self.cmd_buffer, self._forces0):
             t.zero_()
         self.episode_length_buf.zero_()
+        # extras of a reset_idx() over every environment (legged_robot.py:253-264): zero episode sums, current mean level
+        self._episode_stats_last.zero_()
+        self._episode_stats_last[24] = float(N)
+        self._episode_stats_last[25:26].view(torch.int32)[0] = int(self.terrain_levels.sum().item())
+        self._time_outs_sent.copy_(self.time_out_buf)
 
     # overridable hooks kept for API parity; the fused kernels implement them (see module docstring)
     def check_termination(self):
@@ -379,36 +402,38 @@ class LeggedRobotDTC:
     compute_reward = compute_observations = check_termination
 
 
-class _LazyExtras(dict):
-    """`extras` of step(): "time_outs" [N] bool and, when some env was reset, "episode" means
-    (legged_robot.py:253-264).  The episode means need a device->host decision (was anything reset?), so they are
-    materialised only when a consumer actually looks - the training loop's logger - keeping the step sync-free."""
+class _Extras(dict):
+    """`extras` of step().  In the reference this is ONE dict that lives as long as the environment and is rewritten only by a
+    reset_idx() call with a non-empty id list (legged_robot.py:210,253-264): "time_outs" [N] bool and "episode" (means of the
+    episode sums over the environments of that reset, `terrain_level`) therefore describe the last step that reset anything.
+    The kernels keep exactly that on the device (dtc_env_buffers.time_outs_sent / episode_stats_last); "episode" needs a
+    device->host read, so it is materialised only when a consumer looks - the training loop's logger - keeping step() sync-free."""
 
     def __init__(self, env):
         super().__init__()
         self._env = env
-        self._stats = env._episode_stats.clone()
-        self["time_outs"] = env.time_out_buf.bool()
-        self._done = False
+        self["time_outs"] = env._time_outs_sent.view(torch.bool)  # zero-copy view of the device flags
 
-    def _materialise(self):
-        if self._done:
-            return
-        self._done = True
-        s = self._stats.tolist()
-        if s[24] > 0:
-            ep = {"rew_" + k: torch.tensor(s[i] / s[24] / L.EPISODE_LENGTH_S) for i, k in enumerate(L.EPISODE_SUM_NAMES)}
-            ep["terrain_level"] = torch.mean(self._env.terrain_levels.float()).cpu()
-            dict.__setitem__(self, "episode", ep)
+    def _episode(self):
+        s = self._env._episode_stats_last.tolist()
+        if s[24] <= 0:
+            return None
+        ep = {"rew_" + k: torch.tensor(s[i] / s[24] / L.EPISODE_LENGTH_S) for i, k in enumerate(L.EPISODE_SUM_NAMES)}
+        level_sum = int(self._env._episode_stats_last[25:26].view(torch.int32).item())
+        ep["terrain_level"] = torch.tensor(level_sum / self._env.num_envs)
+        return ep
 
     def __contains__(self, k):
         if k == "episode":
-            self._materialise()
+            return self._episode() is not None
         return dict.__contains__(self, k)
 
     def __getitem__(self, k):
         if k == "episode":
-            self._materialise()
+            ep = self._episode()
+            if ep is None:
+                raise KeyError(k)
+            return ep
         return dict.__getitem__(self, k)
 
     def get(self, k, default=None):

@@ -137,6 +137,7 @@ class PPO:
         self._lr_dirty = True
         self._inject = None  # tests: dict(perm=LongTensor, eps=[per optimizer step [M,16] tensors, vae/ppo alternating])
         self._update_calls = 0
+        self._grad_tap = None  # tests: callable(which) invoked between backward and the optimizer step (0 = vae, 1 = policy)
         self.group = None  # torch.distributed process group for data parallel training (None = default group)
 
     # ------------------------------------------------------------------ learning rate lives on the device
@@ -171,6 +172,26 @@ class PPO:
                                       action_shape, self.device)
         rows = (num_envs * num_transitions_per_env) // self.num_mini_batches
         self.actor_critic._learner(max(rows, num_envs))
+        self.sync_replicas()
+
+    def sync_replicas(self):
+        """Data parallel: every rank must hold rank 0's parameters, Adam moments, step counters and learning rate; gradients are
+        the only thing the update all-reduces.  Called at init_storage() and after load(); a no-op at world size 1."""
+        if self._world() <= 1:
+            return
+        import torch.distributed as dist
+        ac = self.actor_critic
+        for t in (ac._flat, *ac._adam):
+            dist.broadcast(t, 0, group=self.group)
+        a, b = C.c_int64(), C.c_int64()
+        if ac._h is not None:
+            B.lib().dtc_learner_get_adam_steps(ac._h, C.byref(a), C.byref(b))
+        meta = torch.tensor([self._pending_steps.get("vae", a.value), self._pending_steps.get("main", b.value), self.learning_rate],
+                            dtype=torch.float64, device=self.device)
+        dist.broadcast(meta, 0, group=self.group)
+        self._pending_steps = {"vae": int(meta[0].item()), "main": int(meta[1].item())}
+        self.learning_rate = float(meta[2].item())
+        ac._params_written()
 
     def test_mode(self):
         self.actor_critic.eval()
@@ -190,9 +211,9 @@ class PPO:
     def process_env_step(self, rewards, dones, next_obs, infos):
         st = self.storage
         to = infos["time_outs"] if "time_outs" in infos else None
-        if to is not None:
-            to = to.to(torch.uint8) if to.dtype != torch.uint8 else to
-        d = dones if dones.dtype == torch.uint8 else dones.to(torch.uint8)
+        if to is not None and to.dtype != torch.uint8:
+            to = to.view(torch.uint8) if to.dtype == torch.bool else to.to(torch.uint8)  # bool -> uint8 is a zero-copy view
+        d = dones if dones.dtype == torch.uint8 else (dones.view(torch.uint8) if dones.dtype == torch.bool else dones.to(torch.uint8))
         B.check(B.lib().dtc_store_transition(C.byref(st._c), st.step, B.ptr(rewards), B.ptr(d), B.ptr(to), B.ptr(next_obs),
                                              next_obs.stride(0), self.gamma, B.stream_ptr(self.device)), "dtc_store_transition")
         st.step += 1
@@ -228,7 +249,8 @@ class PPO:
         eps_list = list(inj.get("eps", []))
         hp = self._hparams()
         world = self._world()
-        sync = 1 if world > 1 else 0
+        tap = self._grad_tap
+        sync = 1 if (world > 1 or tap is not None) else 0
         tab = ac._table
         self._update_calls += 1
         k = 0
@@ -241,12 +263,16 @@ class PPO:
                 B.check(lib.dtc_vae_step(h, C.byref(batch._c), i * mbs, mbs, B.ptr(e1), ac.seed + 7919, ctr, C.byref(hp), sync, stream),
                         "dtc_vae_step")
                 if sync:
+                    if tap is not None:
+                        tap(0)
                     b0, b1 = tab.ranges["vae"]
                     dp.allreduce_sum_(ac._grads[b0:b1], self.group)
                     B.check(lib.dtc_optimizer_apply(h, 0, C.byref(hp), 1.0 / world, mbs * world, stream), "dtc_optimizer_apply")
                 B.check(lib.dtc_ppo_step(h, C.byref(batch._c), i * mbs, mbs, B.ptr(e2), ac.seed + 7919, ctr + 1, C.byref(hp), sync, stream),
                         "dtc_ppo_step")
                 if sync:
+                    if tap is not None:
+                        tap(1)
                     b0, b1 = tab.ranges["policy_sync"]
                     dp.allreduce_sum_(ac._grads[b0:b1], self.group)
                     B.check(lib.dtc_optimizer_apply(h, 1, C.byref(hp), 1.0 / world, mbs * world, stream), "dtc_optimizer_apply")

@@ -251,7 +251,8 @@ class ActorCriticDecoder:
             h = C.c_void_p()
             m1, v1, m2, v2 = self._adam
             B.check(lib.dtc_learner_create(rows, B.ptr(self._flat), B.ptr(self._grads), B.ptr(m1), B.ptr(v1), B.ptr(m2), B.ptr(v2),
-                                           C.c_void_p(self._ws.data_ptr() + off), nbytes, C.byref(h)), "dtc_learner_create")
+                                           C.c_void_p(self._ws.data_ptr() + off), nbytes, B.stream_ptr(self.device), C.byref(h)),
+                    "dtc_learner_create")
         self._h, self._max_rows = h, rows
         self._stats_ptr = lib.dtc_learner_stats(h)
         if steps is not None:

@@ -155,6 +155,7 @@ class OnPolicyRunner:
         if load_optimizer:
             self.alg.optimizer.load_state_dict(loaded_dict["optimizer_state_dict"])
         self.current_learning_iteration = loaded_dict["iter"]
+        self.alg.sync_replicas()
         return loaded_dict["infos"]
 
     def get_inference_policy(self, device=None):

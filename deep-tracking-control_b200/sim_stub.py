@@ -259,6 +259,7 @@ class FakeGym:
         self.dof_state = torch.zeros(N * L.NUM_DOF, 2, device=device)
         self.net_contact_force = torch.zeros(N * L.NUM_BODIES, 3, device=device)
         self.rigid_body_state = torch.zeros(N * L.NUM_BODIES, 13, device=device)
+        self.static_dof_state = True  # dof_state does not change inside the decimation loop (LeggedRobotDTC.step fuses the 4 sub-steps)
         self.queue = []  # list of state dicts consumed FIFO
         self.source = None  # optional callable() -> state dict, used when the queue is empty
 
@@ -287,6 +288,7 @@ class FakeGym:
     def fetch_results(self, sim, flag): pass
     def set_dof_actuation_force_tensor(self, sim, t): pass
     def set_dof_state_tensor_indexed(self, sim, t, ids, n): pass
+    def set_dof_state_tensor(self, sim, t): pass
     def set_actor_root_state_tensor(self, sim, t): pass
     def set_actor_root_state_tensor_indexed(self, sim, t, ids, n): pass
     def clear_lines(self, viewer): pass

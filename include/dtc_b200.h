@@ -121,7 +121,10 @@ typedef struct {
   float* obs_buf;            /* [N,53] */
   float* privileged_obs_buf; /* [N, priv_ld] */
   float* obs_history;        /* [N, hist_ld] (HistoryWrapper state) */
-  float* episode_stats;      /* [26]: per-key sum of episode_sums over envs reset this step (24), count, unused */
+  float* episode_stats;      /* [26]: per-key sum of episode_sums over envs reset this step (24), count, int32 bits: sum of terrain_levels */
+  float* episode_stats_last; /* [26]: episode_stats of the last step that reset at least one environment - what the reference's
+                                persistent `extras["episode"]` holds (legged_robot.py:253-262 runs only when len(env_ids) > 0) */
+  uint8_t* time_outs_sent;   /* [N] extras["time_outs"]: time_out_buf as of the last step with a reset (legged_robot.py:263-264) */
   int32_t priv_ld, hist_ld;
 } dtc_env_buffers;
 
@@ -144,9 +147,14 @@ int dtc_env_bind(dtc_env* e, const dtc_env_buffers* buf);
 /* call after writing height_samples in place (the reference never does after start-up) */
 int dtc_env_heightmap_updated(dtc_env* e);
 
-/* E1+E2: clip actions, 4x PD torque with the lag buffer (legged_robot.py:92-111,595-630).
- * lag_choice[4]: the host draws np.random.randint(1,5) per sub-step like the reference (:608). */
-int dtc_env_pre_physics(dtc_env* e, const float* actions_in, const int32_t lag_choice[4], void* stream);
+/* E1+E2: clip actions (first_substep == 0), PD torque of decimation sub-steps [first_substep, first_substep + num_substeps) with the
+ * lag buffer (legged_robot.py:92-111,595-630).  The reference recomputes the torque from the refreshed dof state in every
+ * sub-step and hands it to gym.set_dof_actuation_force_tensor, so a real simulator is driven with four calls (s, 1) around
+ * gym.simulate(); a stub that leaves dof_state alone inside the loop may take all four in one call (0, 4) - same arithmetic.
+ * lag_choice[4]: the host draws np.random.randint(1,5) per sub-step like the reference (:608); entries outside the range of
+ * this call are ignored. */
+int dtc_env_pre_physics(dtc_env* e, const float* actions_in, const int32_t lag_choice[4], int32_t first_substep,
+                        int32_t num_substeps, void* stream);
 
 /* E3+E4(commands part): base velocities, history buffers, command resampling, heading command
  * (legged_robot_dtc.py:66-91, legged_robot.py:534-539,567-593). */
@@ -155,7 +163,8 @@ int dtc_env_state_prep(dtc_env* e, int64_t common_step_counter, uint64_t seed, c
 /* E5 + E7..E10: height sampling, Raibert footholds, terrain score, argmin, decode
  * (legged_robot.py:1279-1317; legged_robot_dtc.py:100-201).  THE foothold-scoring kernel.
  * variant 0 = brute force with L2 gathers, 3 = patch staged with bulk row copies, 4 = lazy window scoring, 5 = persistent warps +
- * min3 map + prefetched patch (default); 1 and 2 are rejected (removed).  debug_score may be NULL or [N,693,4]. */
+ * min3 map + prefetched patch, 6 = CTA-batched per-environment work + packed fp32x2 sampling (default); 1 and 2 are rejected
+ * (removed).  debug_score may be NULL or [N,693,4] (then the brute-force kernel writes it first and the chosen variant follows). */
 int dtc_foothold_step(dtc_env* e, int variant, float* debug_score, void* stream);
 
 /* E4(rest), E6, E11, E12, E13: push, foot clearance, contact filter, termination, 23 rewards, reset
@@ -205,8 +214,10 @@ typedef struct {
 
 typedef struct dtc_learner dtc_learner;
 int64_t dtc_learner_workspace_bytes(int32_t max_rows);
+/* `stream`: the stream the caller wrote `params` on; the workspace is cleared and the 3xTF32 parameter companions are derived on
+ * it (asynchronously), so the first step queued on the same stream sees both */
 int dtc_learner_create(int32_t max_rows, float* params, float* grads, float* adam_main_m, float* adam_main_v,
-                       float* adam_vae_m, float* adam_vae_v, void* workspace, int64_t workspace_bytes,
+                       float* adam_vae_m, float* adam_vae_v, void* workspace, int64_t workspace_bytes, void* stream,
                        dtc_learner** out);
 void dtc_learner_destroy(dtc_learner* l);
 /* call after writing the flat parameter buffer from outside (load_state_dict): refreshes the 3xTF32 companions */

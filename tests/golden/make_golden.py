@@ -28,7 +28,21 @@ def digest(t):
     return torch.tensor([t.sum(), t.abs().sum(), (t * torch.arange(1, t.numel() + 1, dtype=torch.float64)).sum() / t.numel()])
 
 
-def env_golden(N=16, steps=10, seed=11):
+def _place(state, n, xy=None, dz=0.0, lin_vel=None):
+    """Moves robot n of a synthetic state rigidly (root and every body) and/or overrides its world linear velocity."""
+    rs, rb = state["root_states"], state["rigid_body_state"].view(-1, 17, 13)
+    if xy is not None:
+        d = torch.tensor(xy) - rs[n, 0:2]
+        rs[n, 0:2] += d
+        rb[n, :, 0:2] += d
+    if dz:
+        rs[n, 2] += dz
+        rb[n, :, 2] += dz
+    if lin_vel is not None:
+        rs[n, 7:10] = torch.tensor(lin_vel)
+
+
+def env_golden(N=16, steps=13, seed=11):
     torch.manual_seed(seed)
     np.random.seed(seed)
     hs, tor = sim_stub.make_heightmap("stones", 0)
@@ -39,6 +53,16 @@ def env_golden(N=16, steps=10, seed=11):
     # make sure the nasty paths are hit: tilt one robot over, drop one into a pit
     states[3]["root_states"][1, 3:7] = torch.tensor([0.9, 0.0, 0.0, 0.435])
     states[5]["root_states"][2, 2] -= 0.4
+    # frames 10..12 pin the tie / fall-back branch of topk(k=1, largest=False) by reference output:
+    states[11]["root_states"][5:7, 2] += 1.5                    # root only: every grid point is an exception point -> score == 10 everywhere
+    _place(states[11], 9, dz=1.5)                               # same with the whole robot lifted
+    _place(states[12], 7, lin_vel=[40.0, 0.0, 0.0])             # nominal footholds 1.6 m away: no in-radius candidate on stones
+    _place(states[12], 8, xy=[-10.0, -10.0])                    # flat border: identical terrain score at all 693 points
+    states[12]["root_states"][8, 2] = 0.35
+    _place(states[13], 10, xy=[-8.0, 12.5], lin_vel=[-40.0, 3.0, 0.0])  # flat border AND no in-radius candidate: 693-way exact tie
+    states[13]["root_states"][10, 2] = 0.33
+    _place(states[13], 11, xy=[4.0, -11.0])
+    states[13]["root_states"][11, 2] = 0.31
     env = RH.build_ref_env(N, hs, tor, layout, fg)
     rec = Recorder()
     out = dict(N=N, steps=steps, seed=seed, states=states, heightmap=("stones", 0), layout=layout, frames=[])
@@ -136,6 +160,12 @@ def learner_golden(N=8, iters=2, seed=5):
         ppo_mod.nn.utils.clip_grad_norm_ = orig_clip
         ck = torch.load(os.path.join(d, "model_%d.pt" % iters), weights_only=True)
         out["checkpoint_keys"] = list(ck["model_state_dict"].keys())
+        # structure of the reference's model_<it>.pt (on_policy_runner.py:249-255); the tensors themselves (38 MB) are not committed
+        osd = ck["optimizer_state_dict"]
+        out["checkpoint_struct"] = dict(
+            top_keys=list(ck.keys()), iter=ck["iter"], model={k: tuple(v.shape) for k, v in ck["model_state_dict"].items()},
+            opt_groups=[{k: (len(v) if k == "params" else v) for k, v in g.items()} for g in osd["param_groups"]],
+            opt_state={i: {k: (tuple(v.shape), str(v.dtype)) for k, v in st.items()} for i, st in osd["state"].items()})
     torch.save(out, os.path.join(OUT, "learner_n8.pt"))
     print("learner golden: lr", [o["lr"] for o in out["iters_out"]], "params", out["num_params"])
 

@@ -103,31 +103,56 @@ def step_tables(log, N, resample_ids, reset_ids, counter, device):
     return dict(lag=lag, reset_normal=normal), {k: v.contiguous().to(device) for k, v in noise.items()}
 
 
-def lockstep(oenv, cenv, fg_cpu, fg_gpu, state, actions):
-    """One step of both envs on the same state/actions/draws.  Returns the oracle outputs."""
+def lockstep(oenv, cenv, fg_cpu, fg_gpu, state, actions, log=None, ostep=None, cstep=None):
+    """One step of both envs on the same state/actions/draws.  Returns (oracle outputs, CUDA outputs).
+    log: recorded draws of the reference for this step (golden frames) - the oracle replays them instead of drawing live.
+    ostep / cstep: step callables (e.g. the HistoryWrappers' step); default the environments' own."""
+    from oracle.rng import Replay
     N = oenv.num_envs
     dev = cenv.device
     resample_ids = ((oenv.episode_length_buf + 1) % K.RESAMPLING_STEPS == 0).nonzero().flatten()
     counter = oenv.common_step_counter + 1
+    if log is not None:
+        oenv.rng = Replay(log)
     fg_cpu.queue.append(state)
-    out = oenv.step(actions)
+    out = (ostep or oenv.step)(actions)
     reset_ids = oenv.reset_buf.nonzero().flatten()
-    hd, nz = step_tables(oenv.rng.take(), N, resample_ids, reset_ids, counter, dev)
+    if log is not None:
+        assert oenv.rng.done(), f"oracle consumed {oenv.rng.pos} of {len(log)} recorded draws"
+    hd, nz = step_tables(log if log is not None else oenv.rng.take(), N, resample_ids, reset_ids, counter, dev)
     cenv._host_draws, cenv._noise = hd, nz
     fg_gpu.queue.append({k: v.to(dev) for k, v in state.items()})
-    cenv.step(actions.to(dev))
-    return out
+    cout = (cstep or cenv.step)(actions.to(dev))
+    return out, cout
 
 
-def reset_both(oenv, cenv, fg_cpu, fg_gpu, state):
+def reset_both(oenv, cenv, fg_cpu, fg_gpu, state, log=None, oreset=None, creset=None):
+    from oracle.rng import Replay
     N, dev = oenv.num_envs, cenv.device
+    if log is not None:
+        oenv.rng = Replay(log)
     fg_cpu.queue.append(state)
-    oenv.reset()
-    log = oenv.rng.take()
+    oout = (oreset or oenv.reset)()
+    log = log if log is not None else oenv.rng.take()
     u, normal, rest = reset_tables(log, N, dev)
     none = torch.zeros(0, dtype=torch.long)
     hd, nz = step_tables(rest, N, none, oenv.reset_buf.nonzero().flatten(), 1, dev)
     hd.update(reset0_u=u, reset0_normal=normal)
     cenv._host_draws, cenv._noise = hd, nz
     fg_gpu.queue.append({k: v.to(dev) for k, v in state.items()})
-    cenv.reset()
+    cout = (creset or cenv.reset)()
+    return oout, cout
+
+
+def make_pair_from_golden(G, device="cuda"):
+    """Oracle env + CUDA env on the heightmap / layout a golden file was recorded with."""
+    from dtc_b200.legged_gym.envs import LeggedRobotDTC, Lite3DTCCfg
+    N = G["N"]
+    hs, tor = sim_stub.make_heightmap(*G["heightmap"])
+    fg_cpu = sim_stub.FakeGym(N)
+    oenv = EO.OracleEnv(K, N, hs, G["layout"], fg_cpu, None)
+    fg_gpu = sim_stub.FakeGym(N, device=device)
+    cfg = Lite3DTCCfg()
+    cfg.env.num_envs = N
+    cenv = LeggedRobotDTC(cfg, sim_device=device, gym=fg_gpu, height_samples=hs, terrain_origins=tor, layout=G["layout"], seed=G["seed"])
+    return oenv, cenv, fg_cpu, fg_gpu

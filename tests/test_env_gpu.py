@@ -9,6 +9,7 @@ from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-5
+FLIPS = {"pairs": 0, "optimal": 0, "nominal": 0}  # observed near-tie index differences, printed per test (run with -s)
 
 
 def _close(a, b, name, rtol=RTOL, atol=1e-6):
@@ -31,14 +32,21 @@ def _compare_step(o, c, tag, sel=None):
     _close(c.pred_footholds, o.pred_footholds, tag + "pred_footholds")
     ci, oi = c.optimal_foothold_indice.squeeze(1).cpu(), o.optimal_foothold_indice.squeeze(1)
     bad = (ci != oi).nonzero().tolist()
-    if bad:
-        # an index may differ only at a score near-tie (1-ulp transcendental differences upstream)
-        for n, l in bad:
-            s = sel["score"][n, :, l]
-            assert abs(float(s[ci[n, l]] - s[oi[n, l]])) < 1e-6, (tag, "optimal idx", n, l, int(ci[n, l]), int(oi[n, l]))
+    # an index may differ only at a near-tie: the per-env mean / variance of the 693 heights is an fp32 reduction whose order
+    # the reference does not define (ATen cascade sum on the CPU, tree on CUDA); every difference is verified to be one
+    for n, l in bad:
+        s = sel["score"][n, :, l]
+        assert abs(float(s[ci[n, l]] - s[oi[n, l]])) < 1e-6, (tag, "optimal idx", n, l, int(ci[n, l]), int(oi[n, l]))
     assert len(bad) <= max(1, ci.numel() // 2000), (tag, "too many near-tie flips", len(bad))
-    ni = c.nominal_footholds_indice.cpu()
-    assert (ni != o.nominal_footholds_indice).sum() <= max(1, ni.numel() // 2000), tag + "nominal idx"
+    ni, on = c.nominal_footholds_indice.cpu(), o.nominal_footholds_indice
+    bad_n = (ni != on).nonzero().tolist()
+    for n, l in bad_n:
+        d = (o.pred_footholds[n, l, :2][None] - o.heights_world[n, :, :2]).norm(dim=1)
+        assert abs(float(d[ni[n, l]] - d[on[n, l]])) < 1e-6, (tag, "nominal idx", n, l, int(ni[n, l]), int(on[n, l]))
+    assert len(bad_n) <= max(1, ni.numel() // 2000), (tag, "too many nominal near-tie flips", len(bad_n))
+    FLIPS["pairs"] += ci.numel()
+    FLIPS["optimal"] += len(bad)
+    FLIPS["nominal"] += len(bad_n)
     same = (ci == oi).all(dim=1)
     _close(c.foothold_obs[same.to(c.device)], o.foothold_obs[same], tag + "foothold_obs")
     _close(c.optimal_footholds_world[same.to(c.device)], o.optimal_footholds_world[same], tag + "optimal_footholds_world")
@@ -46,6 +54,11 @@ def _compare_step(o, c, tag, sel=None):
     _close(c.measured_foot_clearance, o.measured_foot_clearance, tag + "clearance")
     assert torch.equal(c.reset_buf.bool().cpu(), o.reset_buf.bool()), tag + "reset_buf"
     assert torch.equal(c.time_out_buf.bool().cpu(), o.time_out_buf), tag + "time_out_buf"
+    if "time_outs" in o.extras:  # persistent dict: the flags of the last step that reset anything (legged_robot.py:263-264)
+        assert torch.equal(c.extras["time_outs"].cpu(), o.extras["time_outs"]), tag + "extras[time_outs]"
+    if "episode" in o.extras:
+        for k, v in o.extras["episode"].items():
+            _close(torch.as_tensor(c.extras["episode"][k]).reshape(()), torch.as_tensor(v).float().reshape(()), tag + "extras." + k, atol=5e-6)
     for i, k in enumerate(K.EPISODE_SUM_NAMES):
         if k in o.reward_terms:
             _close(c._reward_terms[i][same.to(c.device)], o.reward_terms[k][same], tag + "reward." + k, atol=2e-6)
@@ -73,7 +86,8 @@ def _compare_step(o, c, tag, sel=None):
 @pytest.mark.parametrize("N,kind,variant", [(64, "stones", 0), (64, "flat", 4), (256, "curriculum", 3), (4096, "stones", 4),
                                             (1000, "stones", 3), (256, "curriculum", 4), (1000, "stones", 4), (64, "stones", 4),
                                             (64, "stones", 5), (256, "curriculum", 5), (4096, "stones", 5), (64, "flat", 5),
-                                            (1000, "curriculum", 5)])
+                                            (1000, "curriculum", 5), (64, "stones", 6), (256, "curriculum", 6), (4096, "stones", 6),
+                                            (64, "flat", 6), (1000, "curriculum", 6), (37, "stones", 6)])
 def test_env_step_parity(N, kind, variant):
     from oracle import env_oracle as EO
     oenv, cenv, fg_cpu, fg_gpu = H.make_pair(N, kind, seed=3)
@@ -84,6 +98,10 @@ def test_env_step_parity(N, kind, variant):
     states[2]["root_states"][1, 3:7] = torch.tensor([0.9, 0.0, 0.0, 0.435])  # flipped robot -> termination
     states[2]["root_states"][2, 2] -= 0.4                                    # sunk robot -> termination
     states[1]["root_states"][3, 0:2] = torch.tensor([-25.0, 70.0])           # outside the map -> index clipping
+    rb1 = states[1]["rigid_body_state"].view(N, 17, 13)
+    rb1[3, :, 0:2] = torch.tensor([-25.0, 70.0])                             # ... feet too: clearance stencil clipped to cell 1 / dim-3
+    rb1[6, 4, 0:2] = torch.tensor([-19.93, 3.0])                             # foot in cell row 1: height_samples[px-2] wraps to the LAST row
+    rb1[6, 8, 0:2] = torch.tensor([3.0, -19.93])                             # foot in cell column 1: [py-2] wraps to the last column
     H.reset_both(oenv, cenv, fg_cpu, fg_gpu, states[0])
     _close(cenv.obs_buf, oenv.obs_buf, "reset obs")
     _close(cenv.commands, oenv.commands, "reset commands")
@@ -104,9 +122,10 @@ def test_env_step_parity(N, kind, variant):
             if (ci != oi).any():
                 sel = EO.foothold_select(states[t + 1]["root_states"], oenv.measured_heights, oenv.pred_footholds, oenv.grid, K, debug=True)
         _compare_step(oenv, cenv, f"N{N} {kind} v{variant} step{t} ", sel)
+    print(f"[index parity] N={N} {kind} v{variant}: cumulative {FLIPS}")
 
 
-@pytest.mark.parametrize("variant", [0, 4, 5])
+@pytest.mark.parametrize("variant", [0, 4, 5, 6])
 def test_debug_score_matches_bruteforce(variant):
     """The windowed argmin equals the reference's brute-force 693x4 scan: dump the full score tensor from the kernel
     and check argmin(score) == optimal_idx, plus the tensor itself against the oracle."""
@@ -129,8 +148,9 @@ def test_debug_score_matches_bruteforce(variant):
     assert 0.0 < frac_fallback < 0.5  # the tie / fall-back path is exercised (SURVEY: ~8 % of pairs)
 
 
-@pytest.mark.parametrize("N,kind", [(16384, "stones"), (8192, "curriculum")])
-def test_foothold_variants_agree(N, kind):
+@pytest.mark.parametrize("N,kind,variant", [(16384, "stones", 5), (8192, "curriculum", 5), (16384, "stones", 6), (8192, "curriculum", 6),
+                                            (4099, "stones", 6)])
+def test_foothold_variants_agree(N, kind, variant):
     """Every output of the default kernel (variant 5: min3 map, fast cell arithmetic with the exact path near cell boundaries,
     persistent warps with a prefetched patch) against the brute-force variant 0 at BASELINE.json's microbench size, including
     robots at / outside the map border and robots whose whole window is exception points.  Heights, Raibert footholds and
@@ -158,14 +178,14 @@ def test_foothold_variants_agree(N, kind):
         st["root_states"][8:40, 2] += 1.5   # all exception points -> fall-back argmin
         fg.load(st)
         out = {}
-        for v in (0, 5):
+        for v in (0, variant):
             for nme in names:
                 env._keep[nme].zero_()
             B.check(env.lib.dtc_foothold_step(env._h, v, C.c_void_p(0), stp), "foothold")
             torch.cuda.synchronize()
             out[v] = {nme: env._keep[nme].clone() for nme in names}
         for nme in names:
-            a, b = out[0][nme], out[5][nme]
+            a, b = out[0][nme], out[variant][nme]
             if nme in ("plane_ab", "center_clear_mean"):
                 # reductions: v0 sums in fp64, v5 in fp32 lane partials (same tolerance class as the oracle comparison)
                 assert torch.allclose(a, b, rtol=1e-5, atol=5e-6), f"{nme} rep{rep}: {(a - b).abs().max()}"
@@ -260,3 +280,52 @@ def test_philox_noise_statistics():
     # adjacent columns / envs are uncorrelated
     c = torch.corrcoef(torch.stack([noise[:, 0], noise[:, 1], noise[:, 4]]))
     assert float((c - torch.eye(3, device=c.device)).abs().max()) < 0.1
+
+
+def test_decimation_substeps_drive_a_moving_simulator():
+    """legged_robot.py:102-111: with a simulator whose dof state changes inside the decimation loop the PD torque is recomputed
+    from the refreshed state in every sub-step and handed to gym.set_dof_actuation_force_tensor each time; pushes / resets
+    written on the device go back through set_actor_root_state_tensor / set_dof_state_tensor."""
+    N = 64
+
+    class MovingGym(sim_stub.FakeGym):
+        def __init__(self, n, device="cpu"):
+            super().__init__(n, device)
+            self.static_dof_state = False
+            self.k = 0
+            self.torque_log, self.root_sets, self.dof_sets = [], 0, 0
+            g = torch.Generator().manual_seed(11)
+            self.deltas = [torch.randn(n * 12, 2, generator=g).to(device) * 0.05 for _ in range(16)]
+
+        def refresh_dof_state_tensor(self, sim):
+            self.dof_state += self.deltas[self.k % 16]
+            self.k += 1
+
+        def set_dof_actuation_force_tensor(self, sim, t): self.torque_log.append(t.clone())
+        def set_actor_root_state_tensor(self, sim, t): self.root_sets += 1
+        def set_dof_state_tensor(self, sim, t): self.dof_sets += 1
+
+    from dtc_b200.legged_gym.envs import LeggedRobotDTC, Lite3DTCCfg
+    from oracle import env_oracle as EO
+    hs, tor = sim_stub.make_heightmap("stones", 0)
+    layout = sim_stub.initial_env_layout(N, tor, 3)
+    rng = H.TapRng(3)
+    fg_cpu, fg_gpu = MovingGym(N), MovingGym(N, "cuda")
+    oenv = EO.OracleEnv(K, N, hs, layout, fg_cpu, rng)
+    cfg = Lite3DTCCfg()
+    cfg.env.num_envs = N
+    cenv = LeggedRobotDTC(cfg, sim_device="cuda", gym=fg_gpu, height_samples=hs, terrain_origins=tor, layout=layout, seed=3)
+    g = torch.Generator().manual_seed(7)
+    states = [sim_stub.synth_state(N, oenv.env_origins, g) for _ in range(4)]
+    H.reset_both(oenv, cenv, fg_cpu, fg_gpu, states[0])
+    ag = torch.Generator().manual_seed(9)
+    for t in range(3):
+        fg_gpu.torque_log.clear()
+        H.lockstep(oenv, cenv, fg_cpu, fg_gpu, states[t + 1], torch.randn(N, 12, generator=ag))
+        assert len(fg_gpu.torque_log) == 4
+        assert not torch.equal(fg_gpu.torque_log[0], fg_gpu.torque_log[3]), "sub-steps must see the refreshed dof state"
+        _close(cenv.torques, oenv.torques, f"step{t} torques (last sub-step)", atol=1e-5)
+        _close(fg_gpu.torque_log[3], oenv.torques, f"step{t} torque handed to the simulator", atol=1e-5)
+        _close(cenv.dof_state, oenv.dof_state, f"step{t} dof_state")
+        _close(cenv.rew_buf, oenv.rew_buf, f"step{t} rew", atol=5e-6)
+    assert fg_gpu.root_sets == fg_gpu.dof_sets == 4  # reset()'s step + 3 steps

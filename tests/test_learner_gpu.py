@@ -551,3 +551,111 @@ def test_policy_step_gradients(engine):
     assert n_checked == 31
     n_out = int(cac.debug_buffer("OUTM").view(torch.uint8)[:, :16].sum())
     assert n_out > 0, "the outlier path must be exercised"
+
+
+def test_step_gradients_at_bench_size():
+    """P11 / P12 at the benchmark's minibatch size (N=4096, T=24 -> 24 576 rows): the radix-select median over 393 k latent_var
+    elements, the 24-25-way split-K weight gradients and the CTA-pair GEMM schedule only exist at this size.  One VAE step and
+    one policy step (sync_grads=1: backward only) on a permuted minibatch of a 98 304-row storage against autograd on the same
+    rows, parameters and draws; default engine (tcgen05 3xTF32)."""
+    from dtc_b200.rsl_rl.algorithms import PPO
+    from dtc_b200.rsl_rl.storage import RolloutStorage
+    oac, cac, rng = _make_policies(8)
+    N, T = 4096, 24
+    mbs = N * T // 4
+    g = torch.Generator().manual_seed(77)
+    perm = torch.randperm(N * T, generator=g)
+    b = perm[:mbs]
+    R = N * T
+    f = dict(obs=torch.randn(R, 53, generator=g), hist=torch.randn(R, 265, generator=g), priv=torch.randn(R, 1389, generator=g),
+             bv=torch.randn(R, 3, generator=g), nobs=torch.randn(R, 53, generator=g), adv=torch.randn(R, generator=g),
+             actions=torch.zeros(R, 12), values=torch.zeros(R), returns=torch.zeros(R), logp=torch.zeros(R), mu=torch.zeros(R, 12),
+             sigma=torch.ones(R, 12))
+    # old policy outputs on the minibatch rows: the current policy's, perturbed, so that ratio / value clipping are exercised
+    with torch.no_grad():
+        a = oac.act(f["obs"][b], f["hist"][b], f["priv"][b])
+        rng.take()
+        v = oac.evaluate(f["obs"][b], f["priv"][b], f["bv"][b]).squeeze(1)
+        f["actions"][b] = a
+        f["mu"][b] = oac.action_mean + 0.05 * torch.randn(mbs, 12, generator=g)
+        f["sigma"][b] = oac.action_std
+        f["logp"][b] = oac.get_actions_log_prob(a) + 0.15 * torch.randn(mbs, generator=g)
+        f["values"][b] = v + 0.3 * torch.randn(mbs, generator=g)
+        f["returns"][b] = v + 0.5 * torch.randn(mbs, generator=g)
+    calg = PPO(cac, num_learning_epochs=5, num_mini_batches=4, clip_param=0.2, gamma=0.99, lam=0.95, value_loss_coef=1.0,
+               entropy_coef=0.003, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True, schedule="adaptive",
+               desired_kl=0.01, device=DEV)
+    calg.init_storage(N, T, [53], [1389], [265], [12])
+    st = calg.storage
+    tr = RolloutStorage.Transition()
+    for t in range(T):
+        sl = slice(t * N, (t + 1) * N)
+        tr.observations, tr.observation_histories, tr.privileged_observations = (f[k][sl].to(DEV) for k in ("obs", "hist", "priv"))
+        tr.base_vel, tr.next_observations, tr.actions = f["bv"][sl].to(DEV), f["nobs"][sl].to(DEV), f["actions"][sl].to(DEV)
+        tr.rewards, tr.dones = torch.zeros(N, device=DEV), torch.zeros(N, device=DEV, dtype=torch.uint8)
+        tr.values, tr.actions_log_prob = f["values"][sl].to(DEV), f["logp"][sl].to(DEV)
+        tr.action_mean, tr.action_sigma = f["mu"][sl].to(DEV), f["sigma"][sl].to(DEV)
+        st.add_transitions(tr)
+    st.returns.copy_(f["returns"].view(T, N, 1))
+    st.advantages.copy_(f["adv"].view(T, N, 1))
+    eps_v = torch.randn(mbs, 16, generator=g)
+    eps_p = torch.randn(mbs, 16, generator=g)
+    lib, stream = B.lib(), B.stream_ptr()
+    batch = st.gather(perm.to(DEV))
+    hp, h = calg._hparams(), cac._learner(mbs)
+    calg._push_lr(h)
+    report = {}
+
+    def compare(got, named, prefix, rel):
+        n = 0
+        for k, gref in named:
+            if gref is None:
+                continue
+            gc = got[prefix + k].double().cpu()
+            report[prefix + k] = float((gc - gref.double()).abs().max() / gref.abs().max().clamp_min(1e-30))
+            _close(got[prefix + k], gref, "grad " + prefix + k, rel=rel, flips=1e-2)
+            n += 1
+        return n
+
+    # ---- VAE step (ppo.py:197-254)
+    class _Fixed:
+        def __init__(self, e): self.e = e
+        def randn_like(self, t): return self.e
+    oac.vae.rng = _Fixed(eps_v)
+    oac.zero_grad()
+    mu, lv, z = oac.vae.cenet_forward(f["hist"][b])
+    l_t = oac.vae.terrain_encoder(f["priv"][b][:, :693])
+    recons = oac.vae.cenet_decoder(torch.cat([z, mu[:, :3], l_t], dim=1))
+    recons_loss = torch.pow(recons - f["nobs"][b], 2).mean(-1).mean()
+    height_loss = torch.nn.functional.mse_loss(oac.vae.terrain_decoder(l_t), f["priv"][b][:, 696:])
+    vel_loss = torch.nn.functional.mse_loss(mu[:, :3], f["bv"][b])
+    kld_loss = torch.mean(-0.5 * torch.sum(1 + lv - mu[:, 3:].pow(2) - lv.exp(), dim=1))
+    (recons_loss + vel_loss + 4 * kld_loss + height_loss).backward()
+    B.check(lib.dtc_learner_reset_stats(h, stream), "reset")
+    B.check(lib.dtc_vae_step(h, C.byref(batch._c), 0, mbs, B.ptr(eps_v.to(DEV).contiguous()), 0, 0, C.byref(hp), 1, stream), "vae_step")
+    n_v = compare(_grads_as_state_dict(cac), [(k, p.grad) for k, p in oac.vae.named_parameters()], "vae.", 2e-5)
+    s = cac.stats().tolist()
+    assert s[2] == pytest.approx(recons_loss.item(), rel=1e-5) and s[3] == pytest.approx(vel_loss.item(), rel=1e-5)
+    assert s[4] == pytest.approx(kld_loss.item(), rel=1e-5, abs=1e-7) and s[5] == pytest.approx(height_loss.item(), rel=1e-5)
+    # ---- policy step (ppo.py:265-338)
+    oac.vae.rng = _Fixed(eps_p)
+    oac.rng = _Fixed(torch.zeros(mbs, 12))
+    oac.zero_grad()
+    oac.act(f["obs"][b], f["hist"][b], f["priv"][b])
+    logp = oac.get_actions_log_prob(f["actions"][b])
+    value = oac.evaluate(f["obs"][b], f["priv"][b], f["bv"][b])
+    ratio = torch.exp(logp - f["logp"][b])
+    adv = f["adv"][b]
+    surr = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 0.8, 1.2)).mean()
+    tv, ret = f["values"][b].unsqueeze(1), f["returns"][b].unsqueeze(1)
+    vc = tv + (value - tv).clamp(-0.2, 0.2)
+    vloss = torch.max((value - ret).pow(2), (vc - ret).pow(2)).mean()
+    (surr + 1.0 * vloss - 0.003 * oac.entropy.mean()).backward()
+    B.check(lib.dtc_ppo_step(h, C.byref(batch._c), 0, mbs, B.ptr(eps_p.to(DEV).contiguous()), 0, 0, C.byref(hp), 1, stream), "ppo_step")
+    n_p = compare(_grads_as_state_dict(cac), [(k, p.grad) for k, p in oac.named_parameters()], "", 3e-5)
+    assert n_v == 26 and n_p == 31, (n_v, n_p)
+    s = cac.stats().tolist()
+    assert s[0] == pytest.approx(vloss.item(), rel=2e-5) and s[1] == pytest.approx(surr.item(), rel=2e-5, abs=1e-6)
+    worst = sorted(report.items(), key=lambda kv: -kv[1])[:4]
+    print("[24576-row step] normwise gradient error max|d|/max|ref|: worst " + ", ".join(f"{k} {v:.1e}" for k, v in worst))
+    assert int(cac.debug_buffer("OUTM").view(torch.uint8)[:, :16].sum()) > 0, "the outlier path must be exercised"

@@ -51,7 +51,7 @@ def test_env_step_matches_reference(env_gold):
     env.episode_length_buf[0:4] = 498
     env.episode_length_buf[4:6] = 999
     env.common_step_counter = 747
-    n_idx_diff = 0
+    n_idx_diff = n_nom_diff = n_fallback = n_exact_tie = 0
     for t, fr in enumerate(G["frames"]):
         rng = env.rng = Replay(fr["log"])
         fg.queue.append(G["states"][t + 1])
@@ -64,14 +64,22 @@ def test_env_step_matches_reference(env_gold):
         _close(env.commands, fr["commands"], tag + "commands")
         _close(env.torques, fr["torques"], tag + "torques", atol=1e-5)
         _close(env.measured_foot_clearance, fr["clearance"], tag + "clearance")
-        # indices: exact up to score near-ties
-        for name, mine, ref in (("optimal", env.optimal_foothold_indice.squeeze(1), fr["optimal_idx"]),):
-            bad = (mine != ref).nonzero()
-            for n, l in bad.tolist():
-                sc = fr["foothold_score"][n, :, l]
-                assert abs(sc[mine[n, l]] - sc[ref[n, l]]) < 1e-6, (tag, name, n, l)
-                n_idx_diff += 1
-        assert torch.equal(env.nominal_footholds_indice, fr["nominal_idx"]) or n_idx_diff >= 0
+        # indices: exact; a difference is tolerated only where the two candidates tie to < 1e-6 in the reference's own score
+        # (optimal) or distance (nominal) - the reference's fp32 cascade mean/var is not reproduced bit for bit (module docstring)
+        mine, ref = env.optimal_foothold_indice.squeeze(1), fr["optimal_idx"]
+        for n, l in (mine != ref).nonzero().tolist():
+            sc = fr["foothold_score"][n, :, l]
+            assert abs(sc[mine[n, l]] - sc[ref[n, l]]) < 1e-6, (tag, "optimal", n, l)
+            n_idx_diff += 1
+        mine_n, ref_n = env.nominal_footholds_indice, fr["nominal_idx"]
+        for n, l in (mine_n != ref_n).nonzero().tolist():
+            xy = env.heights_world[n, :, :2]
+            d = (env.pred_footholds[n, l, :2][None] - xy).norm(dim=1)
+            assert abs(d[mine_n[n, l]] - d[ref_n[n, l]]) < 1e-6, (tag, "nominal", n, l)
+            n_nom_diff += 1
+        smin = fr["foothold_score"].min(dim=1)[0]                      # [N,4]
+        n_fallback += int((smin >= 8).sum())
+        n_exact_tie += int(((fr["foothold_score"] == smin[:, None, :]).sum(dim=1) > 1).sum())
         same = (env.optimal_foothold_indice.squeeze(1) == fr["optimal_idx"]).all(dim=1)
         _close(env.foothold_obs[same], fr["foothold_obs"][same], tag + "foothold_obs")
         _close(env.optimal_footholds_world[same], fr["optimal_footholds_world"][same], tag + "opt world")
@@ -95,7 +103,12 @@ def test_env_step_matches_reference(env_gold):
         for k, v in fr["extras_episode"].items():
             _close(torch.as_tensor(extras["episode"][k]).float().reshape(()), torch.as_tensor(v).float().reshape(()),
                    tag + "extras." + k, atol=2e-6)
-    assert n_idx_diff <= 2, f"too many near-tie index differences: {n_idx_diff}"
+    n_pairs = len(G["frames"]) * G["N"] * 4
+    print(f"golden index parity: {n_idx_diff} optimal / {n_nom_diff} nominal near-tie differences of {n_pairs} (env, leg) pairs; "
+          f"{n_fallback} pairs on the fall-back branch (min score >= 8), {n_exact_tie} with an exact tie at the minimum")
+    assert n_idx_diff == 0 and n_nom_diff == 0, (n_idx_diff, n_nom_diff)
+    # the goldens must exercise the reference's topk tie-break: fall-back argmin and exact multi-way ties
+    assert n_fallback >= 12 and n_exact_tie >= 8, (n_fallback, n_exact_tie)
 
 
 def test_known_answers():
@@ -157,6 +170,22 @@ def test_learner_matches_reference(learner_gold):
         assert rng.done()
         st = alg.storage
         tag = f"iter{it} "
+        # per-minibatch gradient digests recorded at the reference's clip_grad_norm_ calls (vae, policy alternating)
+        ref_d = out["grad_digests"]
+        assert len(ref_d) == 2 * len(alg.debug["vae_grads"]) == 40
+        errs = []
+        for k in range(len(ref_d)):
+            gd = alg.debug["vae_grads" if k % 2 == 0 else "ppo_grads"][k // 2]
+            d = _digest(torch.cat([g.flatten() for g in gd.values()]))
+            errs.append(float((d - ref_d[k]).abs().max() / ref_d[k][1]))
+        print(f"{tag}gradient digests vs reference, |diff| / sum|g|: first pair {errs[0]:.1e} {errs[1]:.1e}, median "
+              f"{sorted(errs)[20]:.1e}, worst {max(errs):.1e}")
+        if it == 0:
+            # minibatch 0 starts from bit-identical parameters; later steps inherit the Adam amplification described below, and
+            # the latent_var outlier repair is discontinuous at its 2-sigma threshold (one step of the 40 lands on it: 0.12)
+            assert max(errs[:6]) <= 1e-6 and sorted(errs)[-3] <= 1e-4 and max(errs) <= 0.5, errs
+        else:
+            assert sorted(errs)[20] <= 5e-2, errs
         # iteration 0 starts from bit-identical parameters -> tight; iteration 1 starts from post-Adam
         # parameters that legitimately differ by ~1e-5 (see below) -> structural check at 3e-3
         f = 1.0 if it == 0 else 300.0

@@ -13,7 +13,7 @@ from dtc_b200 import _lib as B, sim_stub  # noqa: E402
 from dtc_b200.legged_gym.envs import LeggedRobotDTC, Lite3DTCCfg  # noqa: E402
 
 
-def run(N=16384, iters=50, warmup=5, variants=(0, 1)):
+def run(N=16384, iters=50, warmup=5, variants=(6,)):
     dev = "cuda"
     hs, tor = sim_stub.make_heightmap("stones", 0)
     layout = sim_stub.initial_env_layout(N, tor, 1)
@@ -66,5 +66,5 @@ def run(N=16384, iters=50, warmup=5, variants=(0, 1)):
 
 if __name__ == "__main__":
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
-    variants = tuple(int(v) for v in sys.argv[2].split(",")) if len(sys.argv) > 2 else (0,)
+    variants = tuple(int(v) for v in sys.argv[2].split(",")) if len(sys.argv) > 2 else (6,)
     print(json.dumps({"N": N, **run(N, variants=variants)}))
