@@ -606,13 +606,14 @@ def test_step_gradients_at_bench_size():
     calg._push_lr(h)
     report = {}
 
-    def compare(got, named, prefix, rel):
+    def compare(got, named, prefix, rel, tag):
         n = 0
         for k, gref in named:
             if gref is None:
                 continue
             gc = got[prefix + k].double().cpu()
-            report[prefix + k] = float((gc - gref.double()).abs().max() / gref.abs().max().clamp_min(1e-30))
+            report[tag + prefix + k] = (float((gc - gref.double()).abs().max() / gref.abs().max().clamp_min(1e-30)),
+                                        float((gc - gref.double()).norm() / gref.double().norm().clamp_min(1e-30)))
             _close(got[prefix + k], gref, "grad " + prefix + k, rel=rel, flips=1e-2)
             n += 1
         return n
@@ -633,7 +634,7 @@ def test_step_gradients_at_bench_size():
     (recons_loss + vel_loss + 4 * kld_loss + height_loss).backward()
     B.check(lib.dtc_learner_reset_stats(h, stream), "reset")
     B.check(lib.dtc_vae_step(h, C.byref(batch._c), 0, mbs, B.ptr(eps_v.to(DEV).contiguous()), 0, 0, C.byref(hp), 1, stream), "vae_step")
-    n_v = compare(_grads_as_state_dict(cac), [(k, p.grad) for k, p in oac.vae.named_parameters()], "vae.", 2e-5)
+    n_v = compare(_grads_as_state_dict(cac), [(k, p.grad) for k, p in oac.vae.named_parameters()], "vae.", 2e-5, "VAE:")
     s = cac.stats().tolist()
     assert s[2] == pytest.approx(recons_loss.item(), rel=1e-5) and s[3] == pytest.approx(vel_loss.item(), rel=1e-5)
     assert s[4] == pytest.approx(kld_loss.item(), rel=1e-5, abs=1e-7) and s[5] == pytest.approx(height_loss.item(), rel=1e-5)
@@ -652,10 +653,19 @@ def test_step_gradients_at_bench_size():
     vloss = torch.max((value - ret).pow(2), (vc - ret).pow(2)).mean()
     (surr + 1.0 * vloss - 0.003 * oac.entropy.mean()).backward()
     B.check(lib.dtc_ppo_step(h, C.byref(batch._c), 0, mbs, B.ptr(eps_p.to(DEV).contiguous()), 0, 0, C.byref(hp), 1, stream), "ppo_step")
-    n_p = compare(_grads_as_state_dict(cac), [(k, p.grad) for k, p in oac.named_parameters()], "", 3e-5)
+    n_p = compare(_grads_as_state_dict(cac), [(k, p.grad) for k, p in oac.named_parameters()], "", 3e-5, "PPO:")
     assert n_v == 26 and n_p == 31, (n_v, n_p)
     s = cac.stats().tolist()
     assert s[0] == pytest.approx(vloss.item(), rel=2e-5) and s[1] == pytest.approx(surr.item(), rel=2e-5, abs=1e-6)
-    worst = sorted(report.items(), key=lambda kv: -kv[1])[:4]
-    print("[24576-row step] normwise gradient error max|d|/max|ref|: worst " + ", ".join(f"{k} {v:.1e}" for k, v in worst))
+    worst = sorted(report.items(), key=lambda kv: -kv[1][0])[:6]
+    print("[24576-row step] gradient error (max|d|/max|ref|, |d|_F/|ref|_F): worst " + ", ".join(f"{k} {v[0]:.1e}/{v[1]:.1e}" for k, v in worst))
+    print("[24576-row step] median over tensors: %.1e / %.1e" % (sorted(v[0] for v in report.values())[len(report) // 2],
+                                                                   sorted(v[1] for v in report.values())[len(report) // 2]))
+    # 57 gradient tensors: the typical one agrees to < 1e-5 (measured 8e-6, both norms).  The 512-wide ReLU layers of the terrain
+    # encoder see 12.6 M pre-activations per layer at this size; the dozen within fp32 round-off of zero land on either side on
+    # two correct implementations, and one flipped unit of one sample moves that unit's weight-gradient row by 1/sqrt(24576) =
+    # 6e-3 of its norm (measured worst tensor: 1.0e-2 max-norm, 9e-4 Frobenius) - the `flips` allowance of _close covers exactly that
+    med = sorted(v[0] for v in report.values())[len(report) // 2]
+    assert med <= 2e-5, med
+    assert max(v[1] for v in report.values()) <= 2e-3
     assert int(cac.debug_buffer("OUTM").view(torch.uint8)[:, :16].sum()) > 0, "the outlier path must be exercised"
