@@ -36,7 +36,7 @@ class EnvConfig(C.Structure):
 
 ENV_BUFFER_NAMES = [
     "root_states", "dof_state", "contact_forces", "rigid_body_state", "height_samples",
-    "actions", "torques", "lag_buffer", "base_lin_vel", "base_ang_vel", "projected_gravity", "commands",
+    "actions", "torques", "lag_buffer", "base_lin_vel", "base_vel_scaled", "base_ang_vel", "projected_gravity", "commands",
     "cmd_buffer", "lin_vel_buffer", "ang_vel_buffer", "measured_heights", "pred_footholds", "optimal_idx",
     "nominal_idx", "foothold_obs", "optimal_footholds_world", "center_clear_mean", "plane_ab", "foot_clearance",
     "contact_filt", "last_contacts", "stumb_buffer", "feet_air_time", "pitch_est", "last_actions", "last_actions_2",
@@ -99,7 +99,7 @@ def lib():
     L.dtc_env_destroy.argtypes = [vp]
     L.dtc_env_destroy.restype = None
     L.dtc_env_bind.argtypes = [vp, C.POINTER(EnvBuffers)]
-    L.dtc_env_pre_physics.argtypes = [vp, vp, C.POINTER(C.c_int32), C.c_int32, C.c_int32, vp]
+    L.dtc_env_pre_physics.argtypes = [vp, vp, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int64, C.c_uint64, vp]
     L.dtc_env_state_prep.argtypes = [vp, C.c_int64, C.c_uint64, C.POINTER(EnvNoise), vp]
     L.dtc_foothold_step.argtypes = [vp, C.c_int, vp, vp]
     L.dtc_env_reward_reset.argtypes = [vp, C.c_int64, C.c_uint64, C.c_float, C.POINTER(EnvNoise), vp]

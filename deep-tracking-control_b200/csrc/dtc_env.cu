@@ -4,7 +4,12 @@
 #include "dtc_env_internal.cuh"
 
 // ------------------------------------------------------------------ RNG slots (one Philox stream per env per step)
-enum { SLOT_RESAMPLE = 0, SLOT_PUSH = 1, SLOT_RESET = 2, SLOT_PRIV = 16, SLOT_OBS = 400 };
+enum { SLOT_RESAMPLE = 0, SLOT_PUSH = 1, SLOT_RESET = 2, SLOT_LAG = 10, SLOT_RESET_NORMAL = 11, SLOT_PRIV = 16, SLOT_OBS = 400 };
+// draws the reference makes ONCE per step for all environments (np.random.randint lag choice, np.random.normal reset offset):
+// env index 0xffffffff keeps them apart from every per-environment stream
+__device__ __forceinline__ Philox step_rng(uint64_t seed, int64_t step, int slot) {
+  return Philox(seed, (uint64_t)step, ((uint64_t)0xffffffffu << 32) | ((uint64_t)slot << 8));
+}
 __device__ __forceinline__ Philox env_rng(uint64_t seed, int64_t step, int env, int slot) {
   return Philox(seed, (uint64_t)step, ((uint64_t)(uint32_t)env << 32) | ((uint64_t)slot << 8));
 }
@@ -15,7 +20,8 @@ __device__ __forceinline__ Philox env_rng(uint64_t seed, int64_t step, int env, 
 // around gym.simulate(); when the simulator is a stub that leaves the dof state alone inside the loop the four sub-steps run
 // back to back in one launch (count = 4) - the same arithmetic either way.
 __global__ void __launch_bounds__(256) k_pre_physics(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b,
-                                                     const float* __restrict__ actions_in, int4 choice, int first, int count) {
+                                                     const float* __restrict__ actions_in, int4 choice, int first, int count,
+                                                     int64_t step, uint64_t seed) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int N = cfg->num_envs;
   if (i >= N * 12) return;
@@ -34,6 +40,14 @@ __global__ void __launch_bounds__(256) k_pre_physics(const dtc_env_config* __res
   float q = b.dof_state[2 * i], qd = b.dof_state[2 * i + 1];
   float ms = b.motor_strengths[i];
   int ch[4] = {choice.x, choice.y, choice.z, choice.w};
+  if (ch[0] == 0 || ch[1] == 0 || ch[2] == 0 || ch[3] == 0) {
+    // np.random.randint(1, 5) of legged_robot.py:608, one value per sub-step shared by all environments, drawn on the device
+    const uint4 r = step_rng(seed, step, SLOT_LAG).next();
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+      if (ch[s] == 0) ch[s] = 1 + (int)(w[s] >> 30);
+  }
   float tq = 0.f;
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
@@ -95,6 +109,7 @@ __global__ void __launch_bounds__(128) k_state_prep(const dtc_env_config* __rest
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     b.base_lin_vel[n * 3 + i] = blv[i];
+    b.base_vel_scaled[n * 3 + i] = __fmul_rn(blv[i], cfg->obs_scale_lin_vel);  // get_base_vel() (legged_robot.py:1429-1431)
     b.base_ang_vel[n * 3 + i] = bav[i];
     b.projected_gravity[n * 3 + i] = pg[i];
   }
@@ -436,6 +451,11 @@ __global__ void __launch_bounds__(128) k_reward_reset(const dtc_env_config* __re
   { float ms = __fadd_rn(__fmul_rn(u[24], cfg->motor_strength[1]), cfg->motor_strength[0]);
 #pragma unroll
     for (int j = 0; j < 12; ++j) b.motor_strengths[n * 12 + j] = ms; }
+  if (reset_normal != reset_normal) {
+    // np.random.normal(0, 0.02) of legged_robot.py:230: one value per reset_idx() call, shared by the environments it resets
+    const uint4 r = step_rng(seed, step, SLOT_RESET_NORMAL).next();
+    reset_normal = 0.02f * box_muller(r.x, r.y).x;
+  }
   b.height_noise_offset[n] = __fadd_rn(__fmul_rn(b.height_noise_offset[n], 0.0f), reset_normal);
 #pragma unroll
   for (int j = 0; j < 12; ++j) {
@@ -584,16 +604,17 @@ extern "C" int dtc_env_heightmap_updated(dtc_env* e) {
   return dtc_env_build_min3(e);
 }
 extern "C" int dtc_env_pre_physics(dtc_env* e, const float* actions_in, const int32_t lag_choice[4], int32_t first_substep,
-                                   int32_t num_substeps, void* stream) {
+                                   int32_t num_substeps, int64_t step, uint64_t seed, void* stream) {
   if (!e || !e->bound) DTC_FAIL(DTC_ERR_STATE, "dtc_env_pre_physics: env not bound");
   if (first_substep < 0 || num_substeps < 1 || first_substep + num_substeps > 4)
     DTC_FAIL(DTC_ERR_ARG, "dtc_env_pre_physics: sub-steps [%d, %d) outside the decimation loop [0, 4)", first_substep, first_substep + num_substeps);
   for (int i = first_substep; i < first_substep + num_substeps; ++i)
-    if (lag_choice[i] < 1 || lag_choice[i] > 4) DTC_FAIL(DTC_ERR_ARG, "lag choice must be in 1..4");
+    if (lag_choice[i] < 0 || lag_choice[i] > 4) DTC_FAIL(DTC_ERR_ARG, "lag choice must be in 1..4 (or 0: drawn on the device)");
   if (first_substep == 0 && !actions_in) DTC_FAIL(DTC_ERR_ARG, "dtc_env_pre_physics: actions_in is null");
   int total = e->cfg.num_envs * 12;
   k_pre_physics<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      e->d_cfg, e->buf, actions_in, make_int4(lag_choice[0], lag_choice[1], lag_choice[2], lag_choice[3]), first_substep, num_substeps);
+      e->d_cfg, e->buf, actions_in, make_int4(lag_choice[0], lag_choice[1], lag_choice[2], lag_choice[3]), first_substep, num_substeps,
+      step, seed);
   DTC_CHECK_LAUNCH("k_pre_physics");
   return DTC_OK;
 }

@@ -26,7 +26,7 @@ class _Scales:
 
 class LeggedRobotDTC:
     def __init__(self, cfg, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True, *, gym,
-                 height_samples, terrain_origins, layout, seed=0, foothold_variant=6, robot_mass=12.0):
+                 height_samples, terrain_origins, layout, seed=0, foothold_variant=6, robot_mass=12.0, host_rng=False):
         self.cfg = cfg
         self.device = torch.device(sim_device)
         if self.device.type != "cuda":
@@ -52,6 +52,10 @@ class LeggedRobotDTC:
         self.reward_names = list(L.REWARD_NAMES)
         self.command_ranges = {k: list(v) for k, v in L.CMD_RANGES.items()}
         self.seed = int(seed)
+        # the reference draws two numbers per step on the HOST (np.random.randint lag choice, np.random.normal reset offset,
+        # legged_robot.py:608,230).  host_rng=False (default): both come from the kernels' Philox streams, step() touches no host
+        # generator (CUDA-graph capturable); host_rng=True: a seeded numpy generator, consumed exactly where the reference does
+        self.host_rng = bool(host_rng)
         self.np_rng = np.random.default_rng(seed)
         self.common_step_counter = 0
         self.init_done = True
@@ -94,6 +98,7 @@ class LeggedRobotDTC:
         self.actions, self.torques = f(N, 12), f(N, 12)
         self._lag = f(6, N, 12)
         self.base_lin_vel, self.base_ang_vel, self.projected_gravity = f(N, 3), f(N, 3), f(N, 3)
+        self._base_vel = f(N, 3)
         self.commands = f(N, 4)
         self.cmd_buffer, self.lin_vel_buffer, self.ang_vel_buffer = f(10, N, 4), f(10, N, 2), f(10, N, 1)
         self.measured_heights = f(N, L.NUM_POINTS)
@@ -198,7 +203,8 @@ class LeggedRobotDTC:
         t = dict(
             root_states=self.root_states, dof_state=self.dof_state, contact_forces=self.contact_forces,
             rigid_body_state=self.rigid_body_state, height_samples=self.height_samples, actions=self.actions,
-            torques=self.torques, lag_buffer=self._lag, base_lin_vel=self.base_lin_vel, base_ang_vel=self.base_ang_vel,
+            torques=self.torques, lag_buffer=self._lag, base_lin_vel=self.base_lin_vel, base_vel_scaled=self._base_vel,
+            base_ang_vel=self.base_ang_vel,
             projected_gravity=self.projected_gravity, commands=self.commands, cmd_buffer=self.cmd_buffer,
             lin_vel_buffer=self.lin_vel_buffer, ang_vel_buffer=self.ang_vel_buffer, measured_heights=self.measured_heights,
             pred_footholds=self.pred_footholds, optimal_idx=self._optimal_idx, nominal_idx=self._nominal_idx,
@@ -274,7 +280,7 @@ class LeggedRobotDTC:
         return self.rew_buf
 
     def get_base_vel(self):
-        return self.base_lin_vel * self.obs_scales.lin_vel
+        return self._base_vel  # base_lin_vel * obs_scales.lin_vel, written by dtc_env_state_prep (legged_robot.py:1429-1431)
 
     def reset(self):
         """base_task.py:115-119: reset every robot, then one zero-action step."""
@@ -307,12 +313,13 @@ class LeggedRobotDTC:
         B.require_cuda(actions, "actions")
         actions = actions.contiguous().float()
         hd = self._host_draws or {}
-        lag = hd.get("lag") or [int(self.np_rng.integers(1, 5)) for _ in range(L.DECIMATION)]
+        lag = hd.get("lag") or ([int(self.np_rng.integers(1, 5)) for _ in range(L.DECIMATION)] if self.host_rng else [0] * L.DECIMATION)
         arr = (C.c_int32 * 4)(*lag)
+        nstep, seed = self.common_step_counter + 1, self.seed
         gym, sim, uw = self.gym, self.sim, self._unwrap
         if getattr(gym, "static_dof_state", False):
             # stubbed simulator: the dof state does not move inside the decimation loop -> the four PD sub-steps in one launch
-            B.check(lib.dtc_env_pre_physics(self._h, B.ptr(actions), arr, 0, L.DECIMATION, st), "dtc_env_pre_physics")
+            B.check(lib.dtc_env_pre_physics(self._h, B.ptr(actions), arr, 0, L.DECIMATION, nstep, seed, st), "dtc_env_pre_physics")
             for _ in range(L.DECIMATION):
                 gym.set_dof_actuation_force_tensor(sim, uw(self.torques))
                 gym.simulate(sim)
@@ -320,7 +327,7 @@ class LeggedRobotDTC:
         else:
             # legged_robot.py:102-111: torque from the refreshed dof state in every sub-step, handed to the simulator each time
             for s in range(L.DECIMATION):
-                B.check(lib.dtc_env_pre_physics(self._h, B.ptr(actions), arr, s, 1, st), "dtc_env_pre_physics")
+                B.check(lib.dtc_env_pre_physics(self._h, B.ptr(actions), arr, s, 1, nstep, seed, st), "dtc_env_pre_physics")
                 gym.set_dof_actuation_force_tensor(sim, uw(self.torques))
                 gym.simulate(sim)
                 gym.refresh_dof_state_tensor(sim)
@@ -340,7 +347,7 @@ class LeggedRobotDTC:
         B.check(lib.dtc_env_state_prep(self._h, step, seed, C.byref(nz), st), "dtc_env_state_prep")
         dbg = B.ptr(self._debug_score) if self._debug_score is not None else C.c_void_p(0)
         B.check(lib.dtc_foothold_step(self._h, self.foothold_variant, dbg, st), "dtc_foothold_step")
-        rn = hd["reset_normal"] if "reset_normal" in hd else float(self.np_rng.normal(0, 0.02))
+        rn = hd["reset_normal"] if "reset_normal" in hd else (float(self.np_rng.normal(0, 0.02)) if self.host_rng else math.nan)
         B.check(lib.dtc_env_reward_reset(self._h, step, seed, rn, C.byref(nz), st), "dtc_env_reward_reset")
         # pushes (legged_robot.py:673-678) and in-episode resets (:640-667) were written into root_states / dof_state on the device;
         # hand them to the simulator.  Which environments were reset is not known on the host (no nonzero() sync), so the whole

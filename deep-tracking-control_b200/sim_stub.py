@@ -262,12 +262,49 @@ class FakeGym:
         self.static_dof_state = True  # dof_state does not change inside the decimation loop (LeggedRobotDTC.step fuses the 4 sub-steps)
         self.queue = []  # list of state dicts consumed FIFO
         self.source = None  # optional callable() -> state dict, used when the queue is empty
+        self._pf = None     # host->device double buffering (enable_prefetch)
 
     def load(self, st):
         self.root_states.copy_(st["root_states"], non_blocking=True)
         self.dof_state.copy_(st["dof_state"], non_blocking=True)
         self.net_contact_force.copy_(st["net_contact_force"], non_blocking=True)
         self.rigid_body_state.copy_(st["rigid_body_state"], non_blocking=True)
+
+    def enable_prefetch(self, on=True):
+        """States arriving from PINNED HOST memory through `source`: copy step t+1's four tensors host->device on a copy stream
+        into a staging set while step t's kernels run; refresh() then only waits for the staging set and moves it into the
+        simulator tensors device-to-device.  Same bytes over PCIe per step, off the compute stream's critical path."""
+        if not on:
+            self._pf = None
+            return
+        dev = self.root_states.device
+        self._pf = dict(stream=torch.cuda.Stream(dev), ready=torch.cuda.Event(), free=torch.cuda.Event(), staged=False,
+                        buf={k: torch.empty_like(v) for k, v in self._tensors().items()})
+        self._pf["free"].record(torch.cuda.current_stream(dev))
+
+    def _tensors(self):
+        return {"root_states": self.root_states, "dof_state": self.dof_state, "net_contact_force": self.net_contact_force,
+                "rigid_body_state": self.rigid_body_state}
+
+    def _prefetch_next(self):
+        pf, st = self._pf, self.source()
+        with torch.cuda.stream(pf["stream"]):
+            pf["stream"].wait_event(pf["free"])  # the previous device-to-device move out of the staging set has been queued
+            for k, v in pf["buf"].items():
+                v.copy_(st[k], non_blocking=True)
+            pf["ready"].record(pf["stream"])
+        pf["staged"] = True
+
+    def _take_prefetched(self):
+        pf = self._pf
+        if not pf["staged"]:
+            self._prefetch_next()
+        cur = torch.cuda.current_stream(self.root_states.device)
+        cur.wait_event(pf["ready"])
+        for k, v in self._tensors().items():
+            v.copy_(pf["buf"][k], non_blocking=True)
+        pf["free"].record(cur)
+        self._prefetch_next()  # the next step's state starts flowing while this step's kernels run
 
     # --- tensor API
     def acquire_actor_root_state_tensor(self, sim): return self.root_states
@@ -279,7 +316,10 @@ class FakeGym:
         if self.queue:
             self.load(self.queue.pop(0))
         elif self.source is not None:
-            self.load(self.source())
+            if self._pf is not None:
+                self._take_prefetched()
+            else:
+                self.load(self.source())
 
     def refresh_dof_state_tensor(self, sim): pass
     def refresh_net_contact_force_tensor(self, sim): pass

@@ -79,6 +79,7 @@ typedef struct {
   float* torques;            /* [N,12] */
   float* lag_buffer;         /* [6,N,12] */
   float* base_lin_vel;       /* [N,3] */
+  float* base_vel_scaled;    /* [N,3] base_lin_vel * obs_scales.lin_vel = get_base_vel() (legged_robot.py:1429-1431) */
   float* base_ang_vel;       /* [N,3] */
   float* projected_gravity;  /* [N,3] */
   float* commands;           /* [N,4] */
@@ -151,10 +152,11 @@ int dtc_env_heightmap_updated(dtc_env* e);
  * lag buffer (legged_robot.py:92-111,595-630).  The reference recomputes the torque from the refreshed dof state in every
  * sub-step and hands it to gym.set_dof_actuation_force_tensor, so a real simulator is driven with four calls (s, 1) around
  * gym.simulate(); a stub that leaves dof_state alone inside the loop may take all four in one call (0, 4) - same arithmetic.
- * lag_choice[4]: the host draws np.random.randint(1,5) per sub-step like the reference (:608); entries outside the range of
- * this call are ignored. */
+ * lag_choice[4]: np.random.randint(1,5) per sub-step (:608), ONE value for all environments: 1..4 = the caller's draw (tests,
+ * seeded numpy parity), 0 = drawn inside the kernel from Philox(seed, step) so the step needs no host randomness (CUDA graphs);
+ * entries outside the range of this call are ignored.  step: the common_step_counter this step will have in post_physics_step. */
 int dtc_env_pre_physics(dtc_env* e, const float* actions_in, const int32_t lag_choice[4], int32_t first_substep,
-                        int32_t num_substeps, void* stream);
+                        int32_t num_substeps, int64_t step, uint64_t seed, void* stream);
 
 /* E3+E4(commands part): base velocities, history buffers, command resampling, heading command
  * (legged_robot_dtc.py:66-91, legged_robot.py:534-539,567-593). */
@@ -169,7 +171,8 @@ int dtc_foothold_step(dtc_env* e, int variant, float* debug_score, void* stream)
 
 /* E4(rest), E6, E11, E12, E13: push, foot clearance, contact filter, termination, 23 rewards, reset
  * (legged_robot.py:546-564,1443-1472,274-291,200-272; legged_robot_dtc.py:229-245,522-586).
- * reset_normal: the host's np.random.normal(0,0.02) of legged_robot.py:230. */
+ * reset_normal: np.random.normal(0,0.02) of legged_robot.py:230 (one value per step for all environments reset in it): the
+ * caller's draw, or NaN = drawn inside the kernel from Philox(seed, step). */
 int dtc_env_reward_reset(dtc_env* e, int64_t common_step_counter, uint64_t seed, float reset_normal,
                          const dtc_env_noise* noise, void* stream);
 
