@@ -24,7 +24,8 @@ class EnvConfig(C.Structure):
         ("base_height_target", C.c_float), ("tracking_sigma", C.c_float), ("max_acc", C.c_float),
         ("terrain_length", C.c_float), ("max_terrain_level", C.c_int32), ("num_terrain_cols", C.c_int32),
         ("episode_length_s", C.c_float),
-        ("p_gain", C.c_float), ("d_gain", C.c_float), ("action_scale", C.c_float), ("torque_limit", C.c_float),
+        ("p_gains", C.c_float * 12), ("d_gains", C.c_float * 12), ("action_scale", C.c_float), ("torque_limit", C.c_float),
+        ("terrain_curriculum", C.c_int32), ("push_robots", C.c_int32),
         ("default_dof_pos", C.c_float * 12), ("dof_pos_lower", C.c_float * 12), ("dof_pos_upper", C.c_float * 12),
         ("base_init_state", C.c_float * 13), ("grid_x", C.c_float * 33), ("grid_y", C.c_float * 21),
         ("plane_op", C.c_float * (2 * 693)), ("reward_scale", C.c_float * 24), ("noise_scale_vec", C.c_float * 53),
@@ -75,7 +76,7 @@ class ParamInfo(C.Structure):
 
 
 # every entry point include/dtc_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
-EXPORTED_SYMBOLS = ['dtc_env_bind', 'dtc_env_create', 'dtc_env_destroy', 'dtc_env_heightmap_updated', 'dtc_env_observe', 'dtc_env_pre_physics', 'dtc_env_reward_reset', 'dtc_env_state_prep', 'dtc_foothold_step', 'dtc_gae', 'dtc_gae_normalize', 'dtc_gather_minibatch', 'dtc_gemm_debug', 'dtc_get_gemm_mode', 'dtc_get_gemm_pair', 'dtc_get_overlap', 'dtc_gru_forward', 'dtc_gru_param_floats', 'dtc_gru_reset', 'dtc_last_error', 'dtc_launch_count', 'dtc_learner_create', 'dtc_learner_debug_buffer', 'dtc_learner_destroy', 'dtc_learner_get_adam_steps', 'dtc_learner_refresh_params', 'dtc_learner_reset_stats', 'dtc_learner_set_adam_steps', 'dtc_learner_set_lr', 'dtc_learner_stats', 'dtc_learner_workspace_bytes', 'dtc_linear_forward', 'dtc_optimizer_apply', 'dtc_param_count', 'dtc_param_get', 'dtc_param_range', 'dtc_param_total_floats', 'dtc_policy_act', 'dtc_policy_act_teacher', 'dtc_policy_evaluate', 'dtc_ppo_step', 'dtc_profile_enable', 'dtc_profile_kind', 'dtc_profile_read', 'dtc_set_gemm_mode', 'dtc_set_gemm_pair', 'dtc_set_overlap', 'dtc_store_transition', 'dtc_struct_size', 'dtc_terrain_rasterize', 'dtc_vae_step', 'dtc_version']
+EXPORTED_SYMBOLS = ['dtc_env_bind', 'dtc_env_create', 'dtc_env_destroy', 'dtc_env_heightmap_updated', 'dtc_env_observe', 'dtc_env_pre_physics', 'dtc_env_reward_reset', 'dtc_env_state_prep', 'dtc_foothold_step', 'dtc_gae', 'dtc_gae_normalize', 'dtc_gather_minibatch', 'dtc_gemm_debug', 'dtc_get_gemm_mode', 'dtc_get_gemm_pair', 'dtc_get_overlap', 'dtc_gru_forward', 'dtc_gru_param_floats', 'dtc_gru_reset', 'dtc_last_error', 'dtc_launch_count', 'dtc_learner_create', 'dtc_learner_debug_buffer', 'dtc_learner_destroy', 'dtc_learner_get_adam_steps', 'dtc_learner_grad_bucket', 'dtc_learner_wait_bucket', 'dtc_learner_refresh_params', 'dtc_learner_reset_stats', 'dtc_learner_set_adam_steps', 'dtc_learner_set_lr', 'dtc_learner_stats', 'dtc_learner_workspace_bytes', 'dtc_linear_forward', 'dtc_optimizer_apply', 'dtc_param_count', 'dtc_param_get', 'dtc_param_range', 'dtc_param_total_floats', 'dtc_policy_act', 'dtc_policy_act_teacher', 'dtc_policy_evaluate', 'dtc_ppo_step', 'dtc_profile_enable', 'dtc_profile_kind', 'dtc_profile_read', 'dtc_set_gemm_mode', 'dtc_set_gemm_pair', 'dtc_set_overlap', 'dtc_store_transition', 'dtc_struct_size', 'dtc_terrain_rasterize', 'dtc_vae_step', 'dtc_version']
 
 
 class DtcError(RuntimeError):
@@ -117,6 +118,8 @@ def lib():
     L.dtc_learner_destroy.argtypes = [vp]
     L.dtc_learner_destroy.restype = None
     L.dtc_learner_refresh_params.argtypes = [vp, vp]
+    L.dtc_learner_grad_bucket.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.dtc_learner_wait_bucket.argtypes = [vp, C.c_int, C.c_int, vp]
     i32, u64, SP = C.c_int32, C.c_uint64, C.POINTER(Storage)
     L.dtc_policy_act.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, u64, u64, SP, i32, vp, vp, vp, vp, vp, vp]
     L.dtc_policy_evaluate.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp, vp]

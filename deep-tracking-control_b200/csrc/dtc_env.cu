@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) k_pre_physics(const dtc_env_config* __res
     for (int k = 2; k < 5; ++k) sel = (ch[s] == k) ? lag[k] : sel;
     float goal = fminf(fmaxf(sel + cfg->default_dof_pos[j], cfg->dof_pos_lower[j]), cfg->dof_pos_upper[j]);
     // p_gains*Kp(=1) * (goal - q + offsets(=0)) - d_gains*Kd(=1) * qd
-    tq = __fsub_rn(__fmul_rn(cfg->p_gain, __fsub_rn(goal, q)), __fmul_rn(cfg->d_gain, qd));
+    tq = __fsub_rn(__fmul_rn(cfg->p_gains[j], __fsub_rn(goal, q)), __fmul_rn(cfg->d_gains[j], qd));
     tq = __fmul_rn(tq, ms);
     tq = fminf(fmaxf(tq, -cfg->torque_limit), cfg->torque_limit);
   }
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(128) k_reward_reset(const dtc_env_config* __re
   // ---- push (legged_robot.py:546-556): counter % interval in {0,1} -> random xy base velocity
   {
     int64_t m = step % cfg->push_interval;
-    if (m == 0 || m == 1) {
+    if (cfg->push_robots && (m == 0 || m == 1)) {
       float u0, u1;
       if (nz.push_u) { u0 = nz.push_u[n * 2]; u1 = nz.push_u[n * 2 + 1]; }
       else { Philox p = env_rng(seed, step, n, SLOT_PUSH); uint4 r = p.next(); u0 = u01(r.x); u1 = u01(r.y); }
@@ -417,8 +417,10 @@ __global__ void __launch_bounds__(128) k_reward_reset(const dtc_env_config* __re
       if (k + 3 < 25) u[k + 3] = u01(r.w);
     }
   }
-  // terrain curriculum (:690-711)
-  {
+  // terrain curriculum (:690-711), only with cfg.terrain.curriculum (:216-217)
+  if (!cfg->terrain_curriculum) {
+    atomicAdd(reinterpret_cast<int*>(b.episode_stats) + 25, (int)b.terrain_levels[n]);
+  } else {
     float dx = rs[0] - b.env_origins[n * 3], dy = rs[1] - b.env_origins[n * 3 + 1];
     float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
     bool up = dist > cfg->terrain_length * 0.6f;

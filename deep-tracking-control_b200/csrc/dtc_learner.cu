@@ -193,6 +193,9 @@ struct dtc_learner {
   cudaStream_t side[2];
   cudaEvent_t ev[DTC_NEV];
   int ev_next;
+  // data parallel: gradient buckets of the last step, [which][bucket] (see dtc_learner_wait_bucket)
+  bool bucket_ready;
+  cudaEvent_t bucket_ev[2][2];
 };
 
 static const float* lo_of(const dtc_learner* l, const float* p) {
@@ -267,6 +270,7 @@ extern "C" int dtc_learner_create(int32_t max_rows, float* params, float* grads,
   l->vae_steps = l->main_steps = 0;
   l->last_M = 0;
   l->side_ready = false;
+  l->bucket_ready = false;
   l->ev_next = 0;
   // ordered with the caller's own work (the parameter upload ahead of this call, the first step after it): no host sync
   DTC_CUDA(cudaMemsetAsync(l->stats, 0, ST_COUNT * sizeof(double), (cudaStream_t)stream));
@@ -280,6 +284,8 @@ extern "C" void dtc_learner_destroy(dtc_learner* l) {
     for (int i = 0; i < 2; ++i) cudaStreamDestroy(l->side[i]);
     for (int i = 0; i < DTC_NEV; ++i) cudaEventDestroy(l->ev[i]);
   }
+  if (l->bucket_ready)
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(l->bucket_ev[i >> 1][i & 1]);
   delete l;
 }
 
@@ -1041,6 +1047,38 @@ static int grid1d(long long n, int threads, int cap = 148 * 8) {
 }
 
 // cenet encoder + latent heads + outlier statistics (stream c) | terrain encoder (main) -> latent kernel; X receives l_t | z | mu[:3]
+// ------------------------------------------------------------------ data-parallel gradient buckets
+// With sync_grads the caller all-reduces the step's flat gradient range before dtc_optimizer_apply.  Backward produces that
+// range back to front: in the VAE step the decoders' weight gradients are complete while the encoders' backward still runs, in
+// the policy step the actor / critic ones.  Each step therefore publishes TWO buckets with an event each, so the caller can
+// start the all-reduce of the early one on a communication stream underneath the rest of the backward pass:
+//   which 0 (VAE step)   : bucket 0 = decoders (ready on stream w after the last decoder wgrad), bucket 1 = shared encoders (end of call)
+//   which 1 (policy step): bucket 0 = actor, critic, std, piggy-back scalars,                   bucket 1 = shared encoders (end of call)
+// Ranges are contiguous in the flat layout, so a bucket is one all-reduce.
+static int record_bucket(dtc_learner* l, int which, int bucket, cudaStream_t st) {
+  if (!l->bucket_ready) {
+    for (int i = 0; i < 4; ++i) DTC_CUDA(cudaEventCreateWithFlags(&l->bucket_ev[i >> 1][i & 1], cudaEventDisableTiming));
+    l->bucket_ready = true;
+  }
+  DTC_CUDA(cudaEventRecord(l->bucket_ev[which][bucket], st));
+  return DTC_OK;
+}
+extern "C" int dtc_learner_grad_bucket(int which, int bucket, int64_t* begin, int64_t* end) {
+  build_table();
+  if ((which != 0 && which != 1) || (bucket != 0 && bucket != 1) || !begin || !end) DTC_FAIL(DTC_ERR_ARG, "dtc_learner_grad_bucket: bad arguments");
+  // VAE step: [0, g_vae_end) = decoders | shared encoders; the shared encoders finish last -> bucket 1
+  // policy step: [g_pol_begin, piggy end) = shared encoders | actor, critic, std, piggy; the shared encoders finish last -> bucket 1
+  if (which == 0) { *begin = bucket == 0 ? 0 : g_pol_begin; *end = bucket == 0 ? g_pol_begin : g_vae_end; }
+  else { *begin = bucket == 0 ? g_vae_end : g_pol_begin; *end = bucket == 0 ? g_off_piggy + NPIGGY : g_vae_end; }
+  return DTC_OK;
+}
+extern "C" int dtc_learner_wait_bucket(dtc_learner* l, int which, int bucket, void* stream) {
+  if (!l || (which != 0 && which != 1) || (bucket != 0 && bucket != 1)) DTC_FAIL(DTC_ERR_ARG, "dtc_learner_wait_bucket: bad arguments");
+  if (!l->bucket_ready) DTC_FAIL(DTC_ERR_STATE, "dtc_learner_wait_bucket: no step with sync_grads has run yet");
+  DTC_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, l->bucket_ev[which][bucket], 0));
+  return DTC_OK;
+}
+
 static int encode(dtc_learner* l, int M, const float* hist, const float* priv_a, const float* xc, int mode, const float* eps,
                   uint64_t seed, uint64_t counter, const StepStreams& S) {
   float* X = mode == 0 ? l->XA : l->XD;
@@ -1357,13 +1395,14 @@ extern "C" int dtc_vae_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
   RET_IF(dgrad(l, TD2, l->dU2, 512, l->dU1, 512, 512, l->U1, 512, EPI_DRELU, false, M, st, TD0, 0));
   RET_IF(chain(l, st, sw));
   RET_IF(wgrad(l, TD0, l->dU1, 512, l->XD, LD_XD, M, sw));
+  if (sync_grads) RET_IF(record_bucket(l, 0, 0, sw));  // every decoder gradient is complete on stream w
   RET_IF(dgrad(l, CD0, l->dD1, 64, l->dX, LD_XD, LD_XD, nullptr, 0, EPI_STORE, false, M, sc));
   // fan-in into d l_t: the terrain decoder's input gradient accumulates onto the CENet decoder's (dML comes from stream c too)
   RET_IF(chain(l, sc, st));
   RET_IF(dgrad(l, TD0, l->dU1, 512, l->dX, LD_XD, 512, nullptr, 0, EPI_STORE, true, M, st, TE4, 0));
   RET_IF(encode_bwd(l, M, hist, priv_a, 1, 1, S));
   RET_IF(streams_end(l, S));
-  if (sync_grads) return DTC_OK;
+  if (sync_grads) return record_bucket(l, 0, 1, st);
   return optimizer_apply(l, 0, hp, 1.0f, M, st);
 }
 
@@ -1421,10 +1460,11 @@ extern "C" int dtc_ppo_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
   RET_IF(dgrad(l, CB2, l->dC2, 256, l->dC1, 512, 512, l->C1, 512, EPI_DELU, false, M, sc, CB0, 1));
   RET_IF(chain(l, sc, sw));
   RET_IF(wgrad(l, CB0, l->dC1, 512, xc, LD_XC, M, sw));
+  if (sync_grads) RET_IF(record_bucket(l, 1, 0, sw));  // actor, critic, std and the piggy-back scalars are complete on stream w
   RET_IF(dgrad(l, AB0, l->dA1, 512, l->dX, LD_XA, LD_XA, nullptr, 0, EPI_STORE, false, M, st, TE4, 0));
   RET_IF(encode_bwd(l, M, hist, priv_a, 0, 0, S));
   RET_IF(streams_end(l, S));
-  if (sync_grads) return DTC_OK;
+  if (sync_grads) return record_bucket(l, 1, 1, st);
   return optimizer_apply(l, 1, hp, 1.0f, M, st);
 }
 

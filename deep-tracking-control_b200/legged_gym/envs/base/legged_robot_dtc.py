@@ -17,6 +17,7 @@ import torch
 
 from .... import _lib as B
 from .... import lite3 as L
+from .cfg_resolve import resolve
 
 
 class _Scales:
@@ -39,18 +40,21 @@ class LeggedRobotDTC:
         self.viewer = None
         self.debug_viz = False
         self.foothold_variant = foothold_variant
-        N = self.num_envs = int(cfg.env.num_envs)
+        # every number below comes from the configuration object, the way _parse_cfg / _prepare_reward_function read it
+        # (legged_robot.py:1230-1240, 929-952); settings the fused kernels cannot honour raise CfgError
+        R = self._rc = resolve(cfg, sim_dt=getattr(sim_params, "dt", None))
+        N = self.num_envs = R.num_envs
         if gym.num_envs != N:
             raise ValueError("gym.num_envs != cfg.env.num_envs")
         self.num_obs, self.num_privileged_obs, self.num_actions = L.NUM_OBS, L.NUM_PRIV, L.NUM_ACTIONS
         self.num_bodies, self.num_dof = L.NUM_BODIES, L.NUM_DOF
-        self.dt = L.DT
-        self.max_episode_length_s = L.EPISODE_LENGTH_S
-        self.max_episode_length = float(L.MAX_EPISODE_LENGTH)
-        self.obs_scales = _Scales(L.OBS_SCALES)
-        self.reward_scales = {k: v * self.dt for k, v in L.REWARD_SCALES.items()}
-        self.reward_names = list(L.REWARD_NAMES)
-        self.command_ranges = {k: list(v) for k, v in L.CMD_RANGES.items()}
+        self.dt = R.dt
+        self.max_episode_length_s = R.episode_length_s
+        self.max_episode_length = float(R.max_episode_length)
+        self.obs_scales = _Scales(R.obs_scales)
+        self.reward_scales = dict(R.reward_scales)  # non-zero scales x dt (legged_robot.py:934-940)
+        self.reward_names = [k for k in L.REWARD_NAMES if k in R.reward_scales]
+        self.command_ranges = {k: list(v) for k, v in R.command_ranges.items()}
         self.seed = int(seed)
         # the reference draws two numbers per step on the HOST (np.random.randint lag choice, np.random.normal reset offset,
         # legged_robot.py:608,230).  host_rng=False (default): both come from the kernels' Philox streams, step() touches no host
@@ -76,14 +80,15 @@ class LeggedRobotDTC:
         self.base_pos = self.root_states[:, :3]
         # numpy (host generator) or a tensor, e.g. straight from sim_stub.make_heightmap_device / dtc_terrain_rasterize
         hs_t = height_samples if torch.is_tensor(height_samples) else torch.as_tensor(np.asarray(height_samples))
-        self.height_samples = hs_t.to(dev).view(L.MAP_ROWS, L.MAP_COLS).contiguous()
-        assert self.height_samples.dtype == torch.int16
+        if hs_t.dim() != 2 or hs_t.dtype != torch.int16:
+            raise ValueError("height_samples must be an int16 [rows, cols] heightfield (legged_gym/utils/terrain.py:26-30)")
+        self.height_samples = hs_t.to(dev).contiguous()
         levels, types, origins, tor = layout
         self.terrain_levels = levels.to(dev).clone()
         self.terrain_types = types.to(dev).clone()
         self.env_origins = origins.to(dev).float().contiguous().clone()
         self.terrain_origins = tor.to(dev).float().contiguous().clone()
-        self.max_terrain_level = L.NUM_ROWS
+        self.max_terrain_level = R.num_rows
         self.custom_origins = True
         # buffers (base_task.py:41-52; legged_robot.py:788-846)
         self.priv_ld, self.hist_ld = 1392, 268
@@ -122,13 +127,14 @@ class LeggedRobotDTC:
         self._episode_stats, self._episode_stats_last = f(26), f(26)
         self._time_outs_sent = u8(N)
         self.episode_sums = {k: self._episode_sums[i] for i, k in enumerate(L.EPISODE_SUM_NAMES)}
-        self.default_dof_pos = torch.tensor(L.DEFAULT_DOF_POS, device=dev).unsqueeze(0)
-        self.dof_pos_limits = torch.tensor(L.soft_dof_pos_limits(), device=dev)
-        self.torque_limits = torch.full((12,), L.TORQUE_LIMIT, device=dev)
+        self.default_dof_pos = torch.tensor(R.default_dof_pos, device=dev).unsqueeze(0)
+        self.dof_pos_limits = torch.tensor(R.dof_pos_limits, device=dev)
+        self.torque_limits = torch.full((12,), R.torque_limit, device=dev)
+        self.p_gains, self.d_gains = torch.tensor(R.p_gains, device=dev), torch.tensor(R.d_gains, device=dev)
         self.feet_indices = torch.tensor(L.FEET_INDICES, device=dev)
         self.thigh_indices = torch.tensor(L.THIGH_INDICES, device=dev)
-        self.noise_scale_vec = self._noise_scale_vec().to(dev)
-        self.add_noise = True
+        self.noise_scale_vec = torch.tensor(R.noise_scale_vec, device=dev)
+        self.add_noise = R.add_noise
         self._debug_score = None
         self._noise = None  # injected draws (tests): dict of CUDA tensors keyed like dtc_env_noise
         self._host_draws = None  # injected host draws: dict(lag=[4 ints], reset_normal=float)
@@ -136,62 +142,54 @@ class LeggedRobotDTC:
         self.extras = _Extras(self)
 
     # ------------------------------------------------------------------ construction helpers
-    def _noise_scale_vec(self):
-        ns, os_ = L.NOISE_SCALES, L.OBS_SCALES
-        v = torch.zeros(L.NUM_OBS)
-        v[:3] = ns["ang_vel"] * 1.0 * os_["ang_vel"]
-        v[3:6] = ns["gravity"] * 1.0
-        v[9:21] = ns["dof_pos"] * 1.0 * os_["dof_pos"]
-        v[21:33] = ns["dof_vel"] * 1.0 * os_["dof_vel"]
-        return v
-
     def _plane_op(self):
         # constant (A^T A)^-1 A^T of get_plane_norm (legged_robot.py:1541-1546); same torch ops, batch of one
-        x = torch.tensor(L.MEASURED_POINTS_X)
-        y = torch.tensor(L.MEASURED_POINTS_Y)
+        x = torch.tensor(self._rc.grid_x)
+        y = torch.tensor(self._rc.grid_y)
         gx, gy = torch.meshgrid(x, y, indexing="ij")
         A = torch.stack([gx.flatten(), gy.flatten(), torch.ones(L.NUM_POINTS)], dim=1)[None]
         return torch.bmm(torch.linalg.inv(torch.bmm(A.transpose(1, 2), A)), A.transpose(1, 2))[0]
 
     def _make_ctx(self):
-        c = B.EnvConfig()
-        c.num_envs, c.map_rows, c.map_cols = self.num_envs, L.MAP_ROWS, L.MAP_COLS
-        c.horizontal_scale, c.vertical_scale, c.border_size = L.HORIZONTAL_SCALE, L.VERTICAL_SCALE, L.BORDER_SIZE
-        c.dt = L.DT
-        c.max_episode_length, c.resampling_steps, c.push_interval = L.MAX_EPISODE_LENGTH, L.RESAMPLING_STEPS, L.PUSH_INTERVAL
-        c.max_push_vel_xy = L.MAX_PUSH_VEL_XY
+        R, c = self._rc, B.EnvConfig()
+        c.num_envs, c.map_rows, c.map_cols = self.num_envs, int(self.height_samples.shape[0]), int(self.height_samples.shape[1])
+        c.horizontal_scale, c.vertical_scale, c.border_size = R.horizontal_scale, R.vertical_scale, R.border_size
+        c.dt = R.dt
+        c.max_episode_length, c.resampling_steps, c.push_interval = R.max_episode_length, R.resampling_steps, R.push_interval
+        c.max_push_vel_xy, c.push_robots = R.max_push_vel_xy, int(R.push_robots)
         for name, key in (("cmd_lin_x", "lin_vel_x"), ("cmd_lin_y", "lin_vel_y"), ("cmd_heading", "heading")):
-            lo, hi = L.CMD_RANGES[key]
+            lo, hi = R.command_ranges[key]
             getattr(c, name)[0], getattr(c, name)[1] = lo, hi - lo
-        lo, hi = L.MOTOR_STRENGTH_RANGE
+        lo, hi = R.motor_strength
         c.motor_strength[0], c.motor_strength[1] = lo, hi - lo
-        c.cmd_lin_x_max, c.cmd_ang_yaw_max = L.CMD_RANGES["lin_vel_x"][1], L.CMD_RANGES["ang_vel_yaw"][1]
-        c.base_height_target, c.tracking_sigma, c.max_acc = L.BASE_HEIGHT_TARGET, L.TRACKING_SIGMA, L.MAX_ACC
-        c.terrain_length, c.max_terrain_level, c.num_terrain_cols = L.TERRAIN_LENGTH, L.NUM_ROWS, L.NUM_COLS
-        c.episode_length_s = L.EPISODE_LENGTH_S
-        c.p_gain, c.d_gain, c.action_scale, c.torque_limit = L.P_GAIN, L.D_GAIN, L.ACTION_SCALE, L.TORQUE_LIMIT
-        lim = L.soft_dof_pos_limits()
+        c.cmd_lin_x_max, c.cmd_ang_yaw_max = R.command_ranges["lin_vel_x"][1], R.command_ranges["ang_vel_yaw"][1]
+        c.base_height_target, c.tracking_sigma, c.max_acc = R.base_height_target, R.tracking_sigma, R.max_acc
+        c.terrain_length, c.max_terrain_level, c.num_terrain_cols = R.terrain_length, R.num_rows, R.num_cols
+        c.terrain_curriculum = int(R.terrain_curriculum)
+        c.episode_length_s = R.episode_length_s
+        c.action_scale, c.torque_limit = R.action_scale, R.torque_limit
         for j in range(12):
-            c.default_dof_pos[j] = L.DEFAULT_DOF_POS[j]
-            c.dof_pos_lower[j], c.dof_pos_upper[j] = lim[j]
+            c.p_gains[j], c.d_gains[j] = R.p_gains[j], R.d_gains[j]
+            c.default_dof_pos[j] = R.default_dof_pos[j]
+            c.dof_pos_lower[j], c.dof_pos_upper[j] = R.dof_pos_limits[j]
         for j in range(13):
-            c.base_init_state[j] = L.BASE_INIT_STATE[j]
+            c.base_init_state[j] = R.base_init_state[j]
         for j in range(33):
-            c.grid_x[j] = L.MEASURED_POINTS_X[j]
+            c.grid_x[j] = R.grid_x[j]
         for j in range(21):
-            c.grid_y[j] = L.MEASURED_POINTS_Y[j]
+            c.grid_y[j] = R.grid_y[j]
         po = self._plane_op()
         flat = po[:2].contiguous().flatten().tolist()
         for j, v in enumerate(flat):
             c.plane_op[j] = v
         for j, k in enumerate(L.EPISODE_SUM_NAMES):
-            c.reward_scale[j] = self.reward_scales[k]
-        for j, v in enumerate(self.noise_scale_vec.cpu().tolist()):
+            c.reward_scale[j] = R.reward_scales.get(k, 0.0)  # a zero scale drops the term, as legged_robot.py:936-938 does
+        for j, v in enumerate(R.noise_scale_vec):
             c.noise_scale_vec[j] = v
-        s = L.OBS_SCALES
+        s = R.obs_scales
         c.obs_scale_lin_vel, c.obs_scale_ang_vel, c.obs_scale_dof_pos = s["lin_vel"], s["ang_vel"], s["dof_pos"]
         c.obs_scale_dof_vel, c.obs_scale_height, c.obs_scale_force = s["dof_vel"], s["height_measurements"], s["force"]
-        c.clip_obs, c.clip_actions = L.CLIP_OBS, L.CLIP_ACTIONS
+        c.clip_obs, c.clip_actions = R.clip_obs, R.clip_actions
         self._cfg_struct = c
         h = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -289,13 +287,13 @@ class LeggedRobotDTC:
         return obs, priv
 
     def reset_idx(self, env_ids):
-        """Host-driven reset; only the full-batch call of reset() goes through here.  In-episode resets happen on
-        the device inside dtc_env_reward_reset (no nonzero()/len() host sync)."""
-        if len(env_ids) == 0:
+        """legged_robot.py:200-272 for an explicit id list (host-driven: reset(), user scripts).  In-episode resets inside
+        step() happen on the device in dtc_env_reward_reset (no nonzero()/len() host sync); this path
+        does the same arithmetic with torch ops on the selected rows."""
+        env_ids = torch.as_tensor(env_ids, device=self.device, dtype=torch.long).flatten()
+        if env_ids.numel() == 0:
             return
-        if len(env_ids) != self.num_envs:
-            raise NotImplementedError("host-side reset_idx supports the full-batch reset of reset() only")
-        self._pre_reset_all(self._host_draws or {})
+        self._reset_ids(env_ids, self._host_draws or {})
 
     def _noise_struct(self):
         nz = B.EnvNoise()
@@ -356,57 +354,78 @@ class LeggedRobotDTC:
         self.gym.set_dof_state_tensor(self.sim, self._unwrap(self.dof_state))
         B.check(lib.dtc_env_observe(self._h, step, seed, C.byref(nz), st), "dtc_env_observe")
 
-    def _pre_reset_all(self, hd):
-        """Full-batch reset_idx (legged_robot.py:200-272) ahead of the first step: done with torch ops on the
-        device (init-time plumbing, not the hot path)."""
-        N, dev = self.num_envs, self.device
-        g = torch.Generator(device=dev).manual_seed(self.seed + 12345)
+    def _reset_ids(self, ids, hd):
+        """reset_idx (legged_robot.py:200-272) on the rows `ids`: init-time / user-script plumbing, not the hot path."""
+        R, dev, n = self._rc, self.device, int(ids.numel())
+        full = n == self.num_envs
         r = hd.get("reset0_u")
         if r is None:
-            r = torch.rand(N, 25, generator=g, device=dev)
-        # curriculum at init: distance from origin vs command norm (all zero commands -> no move_down unless distance<0)
-        dxy = self.root_states[:, :2] - self.env_origins[:, :2]
-        dist = torch.linalg.vector_norm(dxy, dim=1)
-        up = dist > L.TERRAIN_LENGTH * 0.6
-        cn = torch.linalg.vector_norm(self.commands[:, :2], dim=1)
-        down = (dist < cn * L.EPISODE_LENGTH_S * 0.5) & ~up
-        lv = self.terrain_levels + up.long() - down.long()
-        rnd = torch.clamp((r[:, 0] * L.NUM_ROWS).long(), max=L.NUM_ROWS - 1)
-        lv = torch.where(lv >= self.max_terrain_level, rnd, torch.clip(lv, 0))
-        self.terrain_levels.copy_(lv)
-        self.env_origins.copy_(self.terrain_origins[self.terrain_levels, self.terrain_types])
-        self.dof_pos[:] = self.default_dof_pos * (1.0 * r[:, 1:13] + 0.5)
-        self.dof_vel[:] = 0.0
-        self.root_states[:] = torch.tensor(L.BASE_INIT_STATE, device=dev)
-        self.root_states[:, :3] += self.env_origins
-        self.root_states[:, :2] += 1.0 * r[:, 13:15] + -0.5
-        self.root_states[:, 7:13] = 1.0 * r[:, 15:21] + -0.5
-        R = L.CMD_RANGES
+            g = torch.Generator(device=dev).manual_seed(self.seed + 12345 + self.common_step_counter)
+            r = torch.rand(n, 25, generator=g, device=dev)
+        # terrain curriculum (:690-711)
+        if R.terrain_curriculum:
+            dxy = self.root_states[ids, :2] - self.env_origins[ids, :2]
+            dist = torch.linalg.vector_norm(dxy, dim=1)
+            up = dist > R.terrain_length * 0.6
+            cn = torch.linalg.vector_norm(self.commands[ids, :2], dim=1)
+            down = (dist < cn * R.episode_length_s * 0.5) & ~up
+            lv = self.terrain_levels[ids] + up.long() - down.long()
+            rnd = torch.clamp((r[:, 0] * R.num_rows).long(), max=R.num_rows - 1)
+            lv = torch.where(lv >= self.max_terrain_level, rnd, torch.clip(lv, 0))
+            self.terrain_levels[ids] = lv
+            self.env_origins[ids] = self.terrain_origins[lv, self.terrain_types[ids]]
+        # _reset_dofs (:640), _reset_root_states (dtc:299-311)
+        dof = self.dof_state.view(self.num_envs, L.NUM_DOF, 2)
+        dof[ids, :, 0] = self.default_dof_pos * (1.0 * r[:, 1:13] + 0.5)
+        dof[ids, :, 1] = 0.0
+        root = torch.tensor(R.base_init_state, device=dev).repeat(n, 1)
+        root[:, :3] += self.env_origins[ids]
+        root[:, :2] += 1.0 * r[:, 13:15] + -0.5
+        root[:, 7:13] = 1.0 * r[:, 15:21] + -0.5
+        self.root_states[ids] = root
+        cmd = self.commands[ids]
         for col, key, k in ((0, "lin_vel_x", 21), (1, "lin_vel_y", 22), (3, "heading", 23)):
-            lo, hi = R[key]
-            self.commands[:, col] = (hi - lo) * r[:, k] + lo
-        nrm = torch.linalg.vector_norm(self.commands[:, :2], dim=1)
-        self.commands[:, :2] *= (nrm > 0.1).unsqueeze(1)
-        lo, hi = L.MOTOR_STRENGTH_RANGE
-        self.motor_strengths[:] = (r[:, 24] * (hi - lo) + lo).unsqueeze(1)
+            lo, hi = R.command_ranges[key]
+            cmd[:, col] = (hi - lo) * r[:, k] + lo
+        cmd[:, :2] *= (torch.linalg.vector_norm(cmd[:, :2], dim=1) > 0.1).unsqueeze(1)
+        self.commands[ids] = cmd
+        self._forces0[ids] = 0.0
+        lo, hi = R.motor_strength
+        self.motor_strengths[ids] = (r[:, 24] * (hi - lo) + lo).unsqueeze(1).expand(n, 12)
         rn0 = hd["reset0_normal"] if "reset0_normal" in hd else float(self.np_rng.normal(0, 0.02))
-        self._height_noise_offset[:] = self._height_noise_offset * 0.0 + rn0
-        for t in (self.last_actions, self.last_actions_2, self.last_dof_vel, self.feet_air_time, self.pitch_est, self._lag,
-                  self._stumb, self._episode_sums, self._contact_filt, self._last_contacts, self.lin_vel_buffer,
-                  self.ang_vel_buffer, self.cmd_buffer, self._forces0):
-            t.zero_()
-        self.episode_length_buf.zero_()
-        # extras of a reset_idx() over every environment (legged_robot.py:253-264): zero episode sums, current mean level
-        self._episode_stats_last.zero_()
-        self._episode_stats_last[24] = float(N)
+        self._height_noise_offset[ids] = self._height_noise_offset[ids] * 0.0 + rn0
+        for t in (self.last_actions, self.last_actions_2, self.last_dof_vel, self.feet_air_time, self.pitch_est, self._contact_filt,
+                  self._last_contacts):
+            t[ids] = 0
+        for t in (self._lag, self._stumb, self.lin_vel_buffer, self.ang_vel_buffer, self.cmd_buffer):
+            t[:, ids] = 0
+        # extras of this reset_idx() call (legged_robot.py:253-264): episode means over the rows reset, current mean level
+        sums = self._episode_sums[:, ids].sum(dim=1)
+        self._episode_stats_last[:24] = sums
+        self._episode_stats_last[24] = float(n)
         self._episode_stats_last[25:26].view(torch.int32)[0] = int(self.terrain_levels.sum().item())
+        self._episode_sums[:, ids] = 0.0
         self._time_outs_sent.copy_(self.time_out_buf)
+        self.episode_length_buf[ids] = 0
+        self.reset_buf[ids] = 1
+        # hand the new state to the simulator (legged_robot.py:643-667)
+        self.gym.set_actor_root_state_tensor(self.sim, self._unwrap(self.root_states))
+        self.gym.set_dof_state_tensor(self.sim, self._unwrap(self.dof_state))
 
-    # overridable hooks kept for API parity; the fused kernels implement them (see module docstring)
+    # The reference calls these three inside post_physics_step (legged_robot_dtc.py:205-213).  Here they are fused into
+    # dtc_env_reward_reset / dtc_env_observe, so a call returns what the fused launch of the CURRENT step produced; a subclass
+    # that wants different arithmetic has to supply a kernel, not a Python override.
     def check_termination(self):
-        raise NotImplementedError("fused into dtc_env_reward_reset; subclass hooks are not supported on the CUDA path")
+        """reset_buf / time_out_buf of the current step (legged_robot_dtc.py:229-245)."""
+        return self.reset_buf
 
-    compute_reward = compute_observations = check_termination
+    def compute_reward(self):
+        """rew_buf of the current step; per-term values in `_reward_terms`, running sums in `episode_sums` (legged_robot.py:274-291)."""
+        return self.rew_buf
+
+    def compute_observations(self):
+        """obs_buf / privileged_obs_buf of the current step (legged_robot_dtc.py:254-287)."""
+        return self.obs_buf, self.privileged_obs_buf
 
 
 class _Extras(dict):
@@ -425,7 +444,8 @@ class _Extras(dict):
         s = self._env._episode_stats_last.tolist()
         if s[24] <= 0:
             return None
-        ep = {"rew_" + k: torch.tensor(s[i] / s[24] / L.EPISODE_LENGTH_S) for i, k in enumerate(L.EPISODE_SUM_NAMES)}
+        ep = {"rew_" + k: torch.tensor(s[i] / s[24] / self._env.max_episode_length_s) for i, k in enumerate(L.EPISODE_SUM_NAMES)
+              if k in self._env.reward_scales}
         level_sum = int(self._env._episode_stats_last[25:26].view(torch.int32).item())
         ep["terrain_level"] = torch.tensor(level_sum / self._env.num_envs)
         return ep

@@ -1,7 +1,10 @@
 """Lite3 DTC task configuration as nested classes with the reference's attribute names
 (legged_gym/envs/lite3/lite3_dtc_config.py:3-195, inheriting legged_robot_config.py).  Only the fields the hot
-path reads are present; values are shared with `dtc_b200.lite3`."""
+path reads are present; values are shared with `dtc_b200.lite3`.  `LeggedRobotDTC` resolves whatever object it is given
+through `envs/base/cfg_resolve.py` - an instance of the reference's own `Lite3DTCCfg` works as well - and edits to reward
+scales, command ranges, gains, noise or randomisation settings reach the kernels."""
 from .... import lite3 as L
+from ..base.cfg_resolve import class_to_dict  # noqa: F401  (legged_gym/utils/helpers.py:11-26)
 
 
 class Lite3DTCCfg:
@@ -30,6 +33,39 @@ class Lite3DTCCfg:
         terrain_length = terrain_width = L.TERRAIN_LENGTH
         max_init_terrain_level = 5
 
+    class commands:
+        curriculum = False
+        num_commands = 4
+        resampling_time = 10.0
+        heading_command = True
+
+        class ranges:
+            lin_vel_x = list(L.CMD_RANGES["lin_vel_x"])
+            lin_vel_y = list(L.CMD_RANGES["lin_vel_y"])
+            ang_vel_yaw = list(L.CMD_RANGES["ang_vel_yaw"])
+            heading = list(L.CMD_RANGES["heading"])
+
+    class init_state:
+        pos = list(L.BASE_INIT_STATE[0:3])
+        rot = list(L.BASE_INIT_STATE[3:7])
+        lin_vel = [0.0, 0.0, 0.0]
+        ang_vel = [0.0, 0.0, 0.0]
+        default_joint_angles = dict(zip(L.DOF_NAMES, L.DEFAULT_DOF_POS))
+
+    class domain_rand:
+        push_robots = True
+        push_interval_s = 15
+        max_push_vel_xy = L.MAX_PUSH_VEL_XY
+        max_push_force_xy = 0.0
+        randomize_motor_strength = True
+        motor_strength = list(L.MOTOR_STRENGTH_RANGE)
+        randomize_Kp_factor = False
+        randomize_Kd_factor = False
+
+    class asset:
+        penalize_contacts_on = ["TORSO", "THIGH", "SHANK"]
+        terminate_after_contacts_on = []
+
     class control:
         control_type = "P"
         stiffness = {"joint": L.P_GAIN}
@@ -45,7 +81,10 @@ class Lite3DTCCfg:
         tracking_sigma = L.TRACKING_SIGMA
         max_acc = L.MAX_ACC
         only_positive_rewards = False
-        scales = dict(L.REWARD_SCALES)
+        soft_dof_pos_limit = L.SOFT_DOF_POS_LIMIT
+
+        class scales:
+            pass
 
     class normalization:
         obs_scales = dict(L.OBS_SCALES)
@@ -89,19 +128,5 @@ class Lite3DTCCfgPPO:
         run_name = ""
 
 
-def class_to_dict(obj):
-    """legged_gym/utils/helpers.py:11-26 (alphabetical dir() order)."""
-    if not hasattr(obj, "__dict__") and not isinstance(obj, type):
-        return obj
-    out = {}
-    for key in dir(obj):
-        if key.startswith("_"):
-            continue
-        val = getattr(obj, key)
-        if isinstance(val, type):
-            out[key] = class_to_dict(val)
-        elif isinstance(val, list):
-            out[key] = [class_to_dict(v) for v in val]
-        else:
-            out[key] = val
-    return out
+for _k, _v in L.REWARD_SCALES.items():  # reward scales as class attributes, like the reference's `class scales`
+    setattr(Lite3DTCCfg.rewards.scales, _k, _v)

@@ -139,6 +139,7 @@ class PPO:
         self._update_calls = 0
         self._grad_tap = None  # tests: callable(which) invoked between backward and the optimizer step (0 = vae, 1 = policy)
         self.group = None  # torch.distributed process group for data parallel training (None = default group)
+        self._comm = None  # communication stream of the bucketed gradient all-reduce (created on first use)
 
     # ------------------------------------------------------------------ learning rate lives on the device
     @property
@@ -227,6 +228,29 @@ class PPO:
     def _world(self):
         return dp.world_size(self.group)
 
+    def _allreduce_buckets(self, h, which):
+        """SUM all-reduce of the step's flat gradient range in the two buckets the step publishes (include/dtc_b200.h:
+        dtc_learner_grad_bucket), on a communication stream: bucket 0 starts as soon as its event fires, underneath the shared
+        encoders' backward that is still running on the compute streams; the compute stream rejoins before the optimizer."""
+        if self._world() <= 1:
+            return
+        lib, ac = B.lib(), self.actor_critic
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(self.device)
+            self._buckets = {}
+            for w in (0, 1):
+                for k in (0, 1):
+                    b0, b1 = C.c_int64(), C.c_int64()
+                    B.check(lib.dtc_learner_grad_bucket(w, k, C.byref(b0), C.byref(b1)), "dtc_learner_grad_bucket")
+                    self._buckets[(w, k)] = (b0.value, b1.value)
+        comm = self._comm
+        for k in (0, 1):
+            b0, b1 = self._buckets[(which, k)]
+            B.check(lib.dtc_learner_wait_bucket(h, which, k, C.c_void_p(comm.cuda_stream)), "dtc_learner_wait_bucket")
+            with torch.cuda.stream(comm):
+                dp.allreduce_sum_(ac._grads[b0:b1], self.group)
+        torch.cuda.current_stream(self.device).wait_stream(comm)
+
     def update(self):
         ac, st, lib = self.actor_critic, self.storage, B.lib()
         T, N = st.num_transitions_per_env, st.num_envs
@@ -265,16 +289,14 @@ class PPO:
                 if sync:
                     if tap is not None:
                         tap(0)
-                    b0, b1 = tab.ranges["vae"]
-                    dp.allreduce_sum_(ac._grads[b0:b1], self.group)
+                    self._allreduce_buckets(h, 0)
                     B.check(lib.dtc_optimizer_apply(h, 0, C.byref(hp), 1.0 / world, mbs * world, stream), "dtc_optimizer_apply")
                 B.check(lib.dtc_ppo_step(h, C.byref(batch._c), i * mbs, mbs, B.ptr(e2), ac.seed + 7919, ctr + 1, C.byref(hp), sync, stream),
                         "dtc_ppo_step")
                 if sync:
                     if tap is not None:
                         tap(1)
-                    b0, b1 = tab.ranges["policy_sync"]
-                    dp.allreduce_sum_(ac._grads[b0:b1], self.group)
+                    self._allreduce_buckets(h, 1)
                     B.check(lib.dtc_optimizer_apply(h, 1, C.byref(hp), 1.0 / world, mbs * world, stream), "dtc_optimizer_apply")
         s = ac.stats().tolist()  # the one device->host read of update()
         n = self.num_learning_epochs * self.num_mini_batches

@@ -34,7 +34,9 @@ int dtc_profile_kind(int kind, double* work, double* ms, int64_t* launches);
 
 /* ------------------------------------------------------------------ environment half */
 
-/* Constant task description: Lite3DTCCfg (legged_gym/envs/lite3/lite3_dtc_config.py:3-181). */
+/* Constant task description, resolved from the caller's configuration object the way LeggedRobot._parse_cfg /
+ * _prepare_reward_function / _get_noise_scale_vec do (legged_robot.py:1230-1240, 929-952, 729-752); defaults: Lite3DTCCfg
+ * (legged_gym/envs/lite3/lite3_dtc_config.py:3-181). */
 typedef struct {
   int32_t num_envs;
   int32_t map_rows, map_cols;      /* height_samples [rows, cols] int16 (legged_gym/utils/terrain.py:26-30) */
@@ -54,7 +56,10 @@ typedef struct {
   int32_t max_terrain_level;       /* num_rows */
   int32_t num_terrain_cols;
   float episode_length_s;
-  float p_gain, d_gain, action_scale, torque_limit;
+  float p_gains[12], d_gains[12];  /* control.stiffness / damping resolved per DOF name (legged_robot.py:1098-1109) */
+  float action_scale, torque_limit;
+  int32_t terrain_curriculum;      /* cfg.terrain.curriculum: move environments between terrain levels on reset (legged_robot.py:216-217) */
+  int32_t push_robots;             /* cfg.domain_rand.push_robots (legged_robot.py:546) */
   float default_dof_pos[12];
   float dof_pos_lower[12], dof_pos_upper[12];
   float base_init_state[13];
@@ -271,6 +276,14 @@ int dtc_ppo_step(dtc_learner* l, const dtc_storage* batch, int64_t row0, int32_t
                  uint64_t counter, const dtc_ppo_hparams* hp, int sync_grads, void* stream);
 int dtc_optimizer_apply(dtc_learner* l, int which /*0 vae, 1 policy*/, const dtc_ppo_hparams* hp, float grad_scale,
                         int32_t rows_global /* minibatch rows over all ranks (KL mean) */, void* stream);
+
+/* Data parallel: with sync_grads != 0 a step publishes its flat gradient range in TWO contiguous buckets, each with
+ * an event, in the order backward completes them - bucket 0 (VAE step: the decoders; policy step: actor, critic, std and the
+ * piggy-back scalars) while the shared encoders' backward is still running, bucket 1 (the shared encoders) at the end of the call.
+ * dtc_learner_grad_bucket gives a bucket's [begin, end) floats; dtc_learner_wait_bucket makes `stream` (the caller's
+ * communication stream) wait for it, so the all-reduce of bucket 0 runs underneath the rest of the backward pass. */
+int dtc_learner_grad_bucket(int which /*0 vae, 1 policy*/, int bucket, int64_t* begin, int64_t* end);
+int dtc_learner_wait_bucket(dtc_learner* l, int which, int bucket, void* stream);
 
 /* learner statistics (device doubles): [0] value_loss sum, [1] surrogate sum, [2] recons, [3] vel, [4] kld,
  * [5] height, [6] entropy sum, [7] last kl_mean, [8] learning_rate, [9] last grad norm (vae), [10] last grad norm

@@ -32,8 +32,9 @@ class TapRng(Live):
         return out
 
 
-def make_pair(N, kind="stones", seed=3, device="cuda"):
-    """Oracle env (CPU) and CUDA env fed by twin FakeGyms holding identical synthetic states."""
+def make_pair(N, kind="stones", seed=3, device="cuda", K=K, cfg=None):
+    """Oracle env (CPU) and CUDA env fed by twin FakeGyms holding identical synthetic states.
+    K / cfg: the task constants on the oracle side and the configuration object on the CUDA side (defaults: Lite3 DTC)."""
     from dtc_b200.legged_gym.envs import LeggedRobotDTC, Lite3DTCCfg
     hs, tor = sim_stub.make_heightmap(kind, 0)
     layout = sim_stub.initial_env_layout(N, tor, seed)
@@ -41,7 +42,7 @@ def make_pair(N, kind="stones", seed=3, device="cuda"):
     fg_cpu = sim_stub.FakeGym(N)
     oenv = EO.OracleEnv(K, N, hs, layout, fg_cpu, rng)
     fg_gpu = sim_stub.FakeGym(N, device=device)
-    cfg = Lite3DTCCfg()
+    cfg = cfg if cfg is not None else Lite3DTCCfg()
     cfg.env.num_envs = N
     cenv = LeggedRobotDTC(cfg, sim_device=device, gym=fg_gpu, height_samples=hs, terrain_origins=tor, layout=layout, seed=seed)
     return oenv, cenv, fg_cpu, fg_gpu

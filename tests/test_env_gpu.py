@@ -328,4 +328,110 @@ def test_decimation_substeps_drive_a_moving_simulator():
         _close(fg_gpu.torque_log[3], oenv.torques, f"step{t} torque handed to the simulator", atol=1e-5)
         _close(cenv.dof_state, oenv.dof_state, f"step{t} dof_state")
         _close(cenv.rew_buf, oenv.rew_buf, f"step{t} rew", atol=5e-6)
-    assert fg_gpu.root_sets == fg_gpu.dof_sets == 4  # reset()'s step + 3 steps
+    assert fg_gpu.root_sets == fg_gpu.dof_sets == 5  # reset_idx(all) + the step inside reset() + 3 steps
+
+
+def test_cfg_edits_reach_the_kernels():
+    """Drop-in boundary (legged_robot.py:929-952,1230-1240): reward scales, command ranges, PD gains and noise scales are read
+    from the configuration object - edited on the CUDA side through the cfg classes, on the oracle side through its constants -
+    and parity holds; a setting the fused kernels cannot honour raises instead of being ignored."""
+    import copy
+    import types
+    from dtc_b200.legged_gym.envs import LeggedRobotDTC, Lite3DTCCfg
+    from dtc_b200.legged_gym.envs.base.cfg_resolve import CfgError
+
+    class Cfg(Lite3DTCCfg):  # edits on subclasses, the way the reference derives task configs
+        class rewards(Lite3DTCCfg.rewards):
+            base_height_target = 0.30
+
+            class scales(Lite3DTCCfg.rewards.scales):
+                torques = -1e-5
+                feet_air_time = 0.5
+                collision = 0.0  # dropped term (legged_robot.py:936-938)
+
+        class commands(Lite3DTCCfg.commands):
+            class ranges(Lite3DTCCfg.commands.ranges):
+                lin_vel_x = [-1.0, 1.0]
+                heading = [-1.5, 1.5]
+
+        class control(Lite3DTCCfg.control):
+            stiffness = {"joint": 30.0}
+            damping = {"HipX": 0.4, "HipY": 0.6, "Knee": 0.7}
+
+        class noise(Lite3DTCCfg.noise):
+            noise_scales = dict(Lite3DTCCfg.noise.noise_scales, dof_vel=1.0)
+
+    K2 = types.SimpleNamespace(**{k: copy.deepcopy(getattr(K, k)) for k in dir(K) if k.isupper()})
+    K2.soft_dof_pos_limits = K.soft_dof_pos_limits
+    K2.REWARD_SCALES.update(torques=-1e-5, feet_air_time=0.5, collision=0.0)
+    K2.REWARD_NAMES = sorted(k for k, v in K2.REWARD_SCALES.items() if k != "termination" and v != 0.0)
+    K2.CMD_RANGES.update(lin_vel_x=(-1.0, 1.0), heading=(-1.5, 1.5))
+    K2.BASE_HEIGHT_TARGET, K2.P_GAIN = 0.30, 30.0
+    K2.NOISE_SCALES["dof_vel"] = 1.0
+    N = 256
+    oenv, cenv, fg_cpu, fg_gpu = H.make_pair(N, "stones", seed=6, K=K2, cfg=Cfg())
+    oenv.d_gains = torch.tensor([0.4, 0.6, 0.7] * 4)
+    assert cenv.reward_scales["torques"] == pytest.approx(-1e-5 * 0.02) and "collision" not in cenv.reward_scales
+    assert cenv.command_ranges["lin_vel_x"] == [-1.0, 1.0] and "collision" not in cenv.reward_names
+    g = torch.Generator().manual_seed(7)
+    states = [sim_stub.synth_state(N, oenv.env_origins, g) for _ in range(5)]
+    H.reset_both(oenv, cenv, fg_cpu, fg_gpu, states[0])
+    for e in (oenv, cenv):
+        e.episode_length_buf[0:64] = 498  # command resampling from the edited ranges
+    ag = torch.Generator().manual_seed(9)
+    for t in range(4):
+        H.lockstep(oenv, cenv, fg_cpu, fg_gpu, states[t + 1], torch.randn(N, 12, generator=ag))
+        _compare_step(oenv, cenv, f"cfg step{t} ", {"score": None})
+    assert float(cenv.commands[:64, 0].abs().max()) > 0.75, "the widened lin_vel_x range must be used"
+    assert float(cenv._reward_terms[K.EPISODE_SUM_NAMES.index("collision")].abs().max()) == 0.0
+    # what the kernels cannot honour is refused, not ignored
+    for edit in (lambda c: setattr(c.rewards.scales, "tracking_lin_vel", 1.0), lambda c: setattr(c.rewards, "only_positive_rewards", True),
+                 lambda c: setattr(c.control, "decimation", 2), lambda c: setattr(c.terrain, "measured_points_x", [0.0, 0.1])):
+        class Bad(Lite3DTCCfg):
+            class rewards(Lite3DTCCfg.rewards):
+                class scales(Lite3DTCCfg.rewards.scales):
+                    pass
+            class control(Lite3DTCCfg.control):
+                pass
+            class terrain(Lite3DTCCfg.terrain):
+                pass
+        bad = Bad()
+        edit(bad)
+        bad.env.num_envs = N
+        with pytest.raises(CfgError):
+            LeggedRobotDTC(bad, sim_device="cuda", gym=fg_gpu, height_samples=sim_stub.make_heightmap("flat", 0)[0],
+                           terrain_origins=oenv.terrain_origins, layout=(oenv.terrain_levels, oenv.terrain_types, oenv.env_origins, oenv.terrain_origins))
+
+
+def test_partial_reset_idx_and_hooks():
+    """reset_idx(env_ids) for an arbitrary id list (user scripts; legged_robot.py:200-272) touches exactly those rows, and the
+    three post-physics hooks hand back the fused kernels' products."""
+    N = 128
+    oenv, cenv, fg_cpu, fg_gpu = H.make_pair(N, "stones", seed=8)
+    g = torch.Generator().manual_seed(3)
+    states = [sim_stub.synth_state(N, oenv.env_origins, g) for _ in range(3)]
+    H.reset_both(oenv, cenv, fg_cpu, fg_gpu, states[0])
+    H.lockstep(oenv, cenv, fg_cpu, fg_gpu, states[1], torch.randn(N, 12, generator=g))
+    assert cenv.check_termination() is cenv.reset_buf and cenv.compute_reward() is cenv.rew_buf
+    assert cenv.compute_observations()[0] is cenv.obs_buf
+    before = {k: getattr(cenv, k).clone() for k in ("root_states", "dof_state", "commands", "last_actions", "episode_length_buf", "feet_air_time")}
+    sums_before = cenv._episode_sums.clone()
+    ids = torch.tensor([3, 17, 90], device="cuda")
+    cenv._host_draws = None
+    cenv.reset_idx(ids)
+    keep = torch.ones(N, dtype=torch.bool, device="cuda")
+    keep[ids] = False
+    for k, v in before.items():
+        cur = getattr(cenv, k)
+        rows = cur.view(N, -1) if cur.shape[0] != N else cur
+        assert torch.equal(rows[keep], (v.view(N, -1) if v.shape[0] != N else v)[keep]), k + " of untouched environments changed"
+    assert torch.equal(cenv._episode_sums[:, keep], sums_before[:, keep])
+    assert float(cenv._episode_sums[:, ids].abs().max()) == 0.0 and int(cenv.episode_length_buf[ids].abs().max()) == 0
+    assert float(cenv.last_actions[ids].abs().max()) == 0.0 and float(cenv.dof_vel[ids].abs().max()) == 0.0
+    xy = cenv.root_states[ids, :2] - cenv.env_origins[ids, :2]
+    assert float(xy.abs().max()) <= 0.5 + 1e-6 and bool((cenv.reset_buf[ids] == 1).all())
+    ratio = cenv.dof_pos[ids] / cenv.default_dof_pos
+    assert float(ratio.min()) >= 0.5 - 1e-6 and float(ratio.max()) <= 1.5 + 1e-6
+    ep = cenv.extras["episode"]
+    assert float(ep["rew_torques"]) == pytest.approx(float(sums_before[K.EPISODE_SUM_NAMES.index("torques"), ids].mean()) / 20.0, rel=1e-5)
+    cenv.reset_idx(torch.zeros(0, dtype=torch.long))  # empty list: no-op, like the reference's early return
