@@ -37,6 +37,7 @@ static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b)
 // optional per-launch CUDA-event timing (bench.py's roofline leg): kind 0 = GEMM family (work = flops), 1 = foothold kernel
 extern int g_dtc_prof;
 void dtc_prof_begin(cudaStream_t st, int kind, double work);
+void dtc_prof_tag(int m, int n, int k, int layout);  // shape of the launch opened by the last dtc_prof_begin (per-shape dump)
 void dtc_prof_end(cudaStream_t st);
 
 #define RETURN_IF_ERR(x) do { int _rc = (x); if (_rc) return _rc; } while (0)

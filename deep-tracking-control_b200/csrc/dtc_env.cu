@@ -1,5 +1,6 @@
 // Environment half of the hot path as sm_100a kernels.
 // One launch sequence per policy step:  pre_physics -> [simulator stub] -> state_prep -> foothold -> reward_reset -> observe
+#include <stdlib.h>
 #include "dtc_common.cuh"
 #include "dtc_env_internal.cuh"
 
@@ -648,13 +649,14 @@ extern "C" int dtc_env_observe(dtc_env* e, int64_t step, uint64_t seed, const dt
 // ------------------------------------------------------------------ per-launch event timing
 #include <vector>
 int g_dtc_prof = 0;
-struct ProfRec { cudaEvent_t a, b; int kind; double work; };
+struct ProfRec { cudaEvent_t a, b; int kind; double work; int m, n, k, layout; };
 static std::vector<ProfRec> g_prof_recs;
 void dtc_prof_begin(cudaStream_t st, int kind, double work) {
   if (!g_dtc_prof) return;
   ProfRec r;
   cudaEventCreate(&r.a); cudaEventCreate(&r.b);
   r.kind = kind; r.work = work;
+  r.m = r.n = r.k = r.layout = 0;
   cudaEventRecord(r.a, st);
   g_prof_recs.push_back(r);
 }
@@ -662,21 +664,31 @@ void dtc_prof_end(cudaStream_t st) {
   if (!g_dtc_prof || g_prof_recs.empty()) return;
   cudaEventRecord(g_prof_recs.back().b, st);
 }
+void dtc_prof_tag(int m, int n, int k, int layout) {
+  if (!g_dtc_prof || g_prof_recs.empty()) return;
+  ProfRec& r = g_prof_recs.back();
+  r.m = m; r.n = n; r.k = k; r.layout = layout;
+}
 extern "C" void dtc_profile_enable(int on) { g_dtc_prof = on; }
 static double g_prof_last_work[4], g_prof_last_ms[4];
 static int64_t g_prof_last_n[4];
 // kinds: 0 = GEMM family except the CTA-pair kernel, 1 = foothold kernel, 2 = CTA-pair tensor-core GEMM (the dominant kernel)
 extern "C" int dtc_profile_read(double* gemm_flops, double* gemm_ms, int64_t* gemm_launches, double* foothold_ms, int64_t* foothold_launches) {
   for (int k = 0; k < 4; ++k) { g_prof_last_work[k] = g_prof_last_ms[k] = 0.0; g_prof_last_n[k] = 0; }
+  // env DTC_PROF_DUMP=<file>: one line per launch (kind m n k layout ms), for per-shape tables (tools/gemm_shapes.py)
+  FILE* dump = nullptr;
+  if (const char* path = getenv("DTC_PROF_DUMP")) dump = fopen(path, "a");
   for (auto& r : g_prof_recs) {
     float ms = 0.f;
     cudaEventSynchronize(r.b);
     cudaEventElapsedTime(&ms, r.a, r.b);
+    if (dump) fprintf(dump, "%d %d %d %d %d %.6f\n", r.kind, r.m, r.n, r.k, r.layout, ms);
     const int k = r.kind >= 0 && r.kind < 4 ? r.kind : 3;
     g_prof_last_work[k] += r.work; g_prof_last_ms[k] += ms; ++g_prof_last_n[k];
     cudaEventDestroy(r.a); cudaEventDestroy(r.b);
   }
   g_prof_recs.clear();
+  if (dump) fclose(dump);
   if (gemm_flops) *gemm_flops = g_prof_last_work[0] + g_prof_last_work[2];
   if (gemm_ms) *gemm_ms = g_prof_last_ms[0] + g_prof_last_ms[2];
   if (gemm_launches) *gemm_launches = g_prof_last_n[0] + g_prof_last_n[2];

@@ -351,6 +351,7 @@ int dtc_gemm_launch(GemmArgs a, cudaStream_t st) {
   a.k_per_split = ((ceil_div(a.K, a.splits) + GBK - 1) / GBK) * GBK;
   if (a.k_per_split == 0) a.k_per_split = GBK;
   dtc_prof_begin(st, 0, 2.0 * a.M * a.N * a.K);
+  dtc_prof_tag(a.M, a.N, a.K, 100 + (a.a_kc ? 0 : 2) + (a.b_kc ? 0 : 1));
   if (a.a_kc && a.b_kc) {
     if (a.N > 64) LAUNCH(128, 128, true, true);
     else if (a.N > 32) LAUNCH(128, 64, true, true);

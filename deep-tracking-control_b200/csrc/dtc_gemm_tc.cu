@@ -42,10 +42,16 @@ struct TcParams {
   float* colsum_part;  // [ceil(M/32)][round4(N)] column sums per 32-row block of the final output, or NULL
   int splits, has_alo, has_blo;
   int neff;   // 1: the MMA of a ragged / narrow n-tile covers only the live columns rounded up to the instruction granularity
+  int direct; // epilogue variant: 1 = registers -> global without the shared-memory transpose (env DTC_TC_EPI=direct|staged)
   int debug;  // timing experiments only (env DTC_TC_DEBUG): 1 = epilogue skips its stores, 2 = producer stops loading after the first ring fill
 };
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become
+// resident while its stream predecessor is still draining; griddepcontrol.wait blocks until that predecessor has completed and
+// its memory is visible, launch_dependents lets this kernel's own successor do the same.  Both are no-ops for a normal launch.
+__device__ __forceinline__ void tc_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void tc_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void tc_mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count));
 }
@@ -191,6 +197,77 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
       }
     }
     if (p.debug & 1) continue;
+    if (p.direct && n0 + c0 + 31 < p.N) {
+      // ---- direct variant: lane = row, its 32 consecutive columns straight from registers to global memory.  No shared-memory
+      // round trip (8 STS.128 + 8 LDS.128 per lane and chunk on a pipe the MMA operand reads already saturate); every lane writes
+      // whole 128-byte row segments, two 16-byte pieces of a sector in back-to-back instructions.
+      const int gm = m0 + q * 32 + lane, gn = n0 + c0;
+      const bool row_ok = gm < p.M;
+      if (has_bias) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn) + j4);  // same address on every lane: one broadcast
+          v[j4 * 4] += b4.x; v[j4 * 4 + 1] += b4.y; v[j4 * 4 + 2] += b4.z; v[j4 * 4 + 3] += b4.w;
+        }
+        if (epi == EPI_BIAS_RELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : 0.f;
+        } else if (epi == EPI_BIAS_ELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
+        }
+      } else if (has_src) {
+        const float4* sp = reinterpret_cast<const float4*>(p.act_src + (size_t)(row_ok ? gm : 0) * p.ld_act + gn);
+        float4 s4[8];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) s4[j4] = __ldg(sp + j4);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float sv[4] = {s4[j4].x, s4[j4].y, s4[j4].z, s4[j4].w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float sx = sv[c], x = v[j4 * 4 + c];
+            v[j4 * 4 + c] = epi == EPI_DRELU ? (sx > 0.f ? x : 0.f) : (sx > 0.f ? x : x * (sx + 1.0f));
+          }
+        }
+      }
+      float* orow = out + (size_t)(row_ok ? gm : 0) * ldo + gn;
+      if (accum && row_ok) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 o4 = *(reinterpret_cast<const float4*>(orow) + j4);
+          v[j4 * 4] += o4.x; v[j4 * 4 + 1] += o4.y; v[j4 * 4 + 2] += o4.z; v[j4 * 4 + 3] += o4.w;
+        }
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) *(reinterpret_cast<float4*>(orow) + j4) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+        if (out_lo) {
+          float* lrow = out_lo + (size_t)gm * ldo + gn;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            *(reinterpret_cast<float4*>(lrow) + j4) = make_float4(tf32_lo(v[j4 * 4]), tf32_lo(v[j4 * 4 + 1]), tf32_lo(v[j4 * 4 + 2]), tf32_lo(v[j4 * 4 + 3]));
+        }
+      }
+      if (p.colsum_part && !partial) {
+        // column sums of the 32 rows: butterfly transpose-reduce (31 shuffles), lane l ends up with column l
+        if (!row_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+#pragma unroll
+        for (int sft = 16; sft >= 1; sft >>= 1) {
+          const bool up = (lane & sft) != 0;
+#pragma unroll
+          for (int i = 0; i < sft; ++i) {
+            const float send = up ? v[i] : v[i + sft], keep = up ? v[i + sft] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+          }
+        }
+        if (m0 + q * 32 < p.M) p.colsum_part[(size_t)((m0 + q * 32) >> 5) * n4 + gn + lane] = v[0];
+      }
+      continue;
+    }
     // row `lane`, 16-byte block j4 -> physical block j4 ^ (lane & 7): conflict-free for the row-wise writes and the
     // 4-rows-x-8-blocks reads below
 #pragma unroll
@@ -272,6 +349,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt_n = (p.N + TC_BN - 1) / TC_BN, nt_m = (p.M + TC_BM - 1) / TC_BM;
   const int ntiles = nt_n * nt_m * p.splits;
+  tc_launch_dependents();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(&bar_full[s], 1); tc_mbar_init(&bar_empty[s], 1); }
@@ -286,6 +364,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
+  // programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the previous kernel's tail; its
+  // results are visible from here on
+  tc_grid_dependency_wait();
 
   if (warp == 0) {
    if (tc_elect_one()) {
@@ -428,6 +509,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
   const int nt_n = (p.N + TC_BN - 1) / TC_BN, nt_m = (p.M + 2 * TC_BM - 1) / (2 * TC_BM);
   const int ntiles = nt_n * nt_m * p.splits;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  tc_launch_dependents();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC2_STAGES; ++s) { tc_mbar_init(&bar_full[s], 1); tc_mbar_init(&bar_empty[s], 1); }
@@ -443,6 +525,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
   tc_cluster_sync();  // both CTAs' barriers are initialised before any remote arrival / multicast commit
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
+  tc_grid_dependency_wait();  // programmatic dependent launch (see k_gemm_tc)
 
   if (warp == 0) {
    if (tc_elect_one()) {
@@ -602,6 +685,29 @@ static int tc_pair_mode() {
 extern "C" void dtc_set_gemm_pair(int on) { g_tc_pair = on ? 1 : 0; }
 extern "C" int dtc_get_gemm_pair(void) { return tc_pair_mode(); }
 
+// Programmatic dependent launch of the tensor-core GEMMs: OFF by default (env DTC_PDL=1 enables).  Measured on the training step
+// (gpurun_out/r2n): 89.3 / 90.2 ms with it, 88.6 / 88.7 ms without - these persistent CTAs fill an SM, so a dependent grid can only
+// start on the SMs the running one leaves to the side streams, where it then spins in griddepcontrol.wait instead of letting the
+// side streams' small kernels run.
+static int g_tc_pdl = -1;
+static int tc_pdl_on() {
+  if (g_tc_pdl < 0) { const char* e = getenv("DTC_PDL"); g_tc_pdl = (e && e[0] == '1') ? 1 : 0; }
+  return g_tc_pdl;
+}
+template <typename K>
+static int tc_launch_pdl(K kernel, dim3 grid, int smem, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB,
+                         const CUtensorMap& mBlo, const TcParams& p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tc_pdl_on() ? 1 : 0;
+  DTC_CUDA(cudaLaunchKernelEx(&cfg, kernel, mA, mAlo, mB, mBlo, p));
+  return DTC_OK;
+}
+
 template <int AMAJ, int BMAJ>
 static int tc2_launch_t(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB, const CUtensorMap& mBlo, const TcParams& p,
                         dim3 grid, cudaStream_t st) {
@@ -610,8 +716,7 @@ static int tc2_launch_t(const CUtensorMap& mA, const CUtensorMap& mAlo, const CU
     DTC_CUDA(cudaFuncSetAttribute(k_gemm_tc2<AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
     attr_set = true;
   }
-  k_gemm_tc2<AMAJ, BMAJ><<<grid, TC_THREADS, TC2_SMEM_BYTES, st>>>(mA, mAlo, mB, mBlo, p);
-  return DTC_OK;
+  return tc_launch_pdl(k_gemm_tc2<AMAJ, BMAJ>, grid, TC2_SMEM_BYTES, st, mA, mAlo, mB, mBlo, p);
 }
 
 template <int AMAJ, int BMAJ>
@@ -622,8 +727,7 @@ static int tc_launch_t(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUt
     DTC_CUDA(cudaFuncSetAttribute(k_gemm_tc<AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set = true;
   }
-  k_gemm_tc<AMAJ, BMAJ><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mA, mAlo, mB, mBlo, p);
-  return DTC_OK;
+  return tc_launch_pdl(k_gemm_tc<AMAJ, BMAJ>, grid, TC_SMEM_BYTES, st, mA, mAlo, mB, mBlo, p);
 }
 
 void k_splitk_reduce_launch(const float* ws, float* C, float* C_lo, int M, int N, int ldc, int splits, int accumulate, cudaStream_t st);
@@ -645,6 +749,10 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   p.colsum_part = (splits == 1) ? a.colsum_part : nullptr;
   p.has_alo = a.A_lo ? 1 : 0; p.has_blo = a.B_lo ? 1 : 0;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DTC_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
+  // epilogue variant: "staged" (default) or "direct".  Measured (gpurun_out/r2o): direct wins on dgrad / narrow shapes alone (256x512
+  // dgrad 124 -> 148 TFLOP/s, 128x256 60 -> 77) but loses on the forward shapes (512x693 184 -> 169) and costs 6 ms per training
+  // iteration (88.5 -> 94.5 ms): its half-sector writes load the L2 write path that the step already saturates.
+  { static int direct = -1; if (direct < 0) { const char* e = getenv("DTC_TC_EPI"); direct = (e && e[0] == 'd') ? 1 : 0; } p.direct = direct; }
   { static int neff = -1; if (neff < 0) { const char* e = getenv("DTC_TC_NEFF"); neff = e ? atoi(e) : 1; } p.neff = neff; }  // DTC_TC_NEFF=0: always 128-column MMAs
   const int amaj = a.a_kc ? 0 : 1, bmaj = a.b_kc ? 0 : 1;
   static int num_sms = 0;
@@ -668,6 +776,7 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   const int used = ceil_div(ntiles, rounds);
   dim3 grid(use_pair ? 2 * used : used);
   dtc_prof_begin(st, use_pair ? 2 : 0, 2.0 * a.M * a.N * a.K);
+  dtc_prof_tag(a.M, a.N, a.K, (use_pair ? 10 : 0) + amaj * 2 + bmaj + 1000 * splits);
   int rc;
   if (use_pair) {
     if (amaj == 0 && bmaj == 0) rc = tc2_launch_t<0, 0>(mA, mAlo, mB, mBlo, p, grid, st);

@@ -126,7 +126,8 @@ class LeggedRobotDTC:
         self._reward_terms = f(24, N)
         self._episode_stats, self._episode_stats_last = f(26), f(26)
         self._time_outs_sent = u8(N)
-        self.episode_sums = {k: self._episode_sums[i] for i, k in enumerate(L.EPISODE_SUM_NAMES)}
+        # keys = the non-zero reward scales, like the reference's episode_sums (legged_robot.py:950-952)
+        self.episode_sums = {k: self._episode_sums[i] for i, k in enumerate(L.EPISODE_SUM_NAMES) if k in self.reward_scales}
         self.default_dof_pos = torch.tensor(R.default_dof_pos, device=dev).unsqueeze(0)
         self.dof_pos_limits = torch.tensor(R.dof_pos_limits, device=dev)
         self.torque_limits = torch.full((12,), R.torque_limit, device=dev)

@@ -126,6 +126,9 @@ class Lite3DTCCfgPPO:
         save_interval = 50
         experiment_name = "lite3_dtc_highres"
         run_name = ""
+        resume = False
+        load_run = -1    # -1 = last run
+        checkpoint = -1  # -1 = last saved model
 
 
 for _k, _v in L.REWARD_SCALES.items():  # reward scales as class attributes, like the reference's `class scales`

@@ -1,0 +1,1 @@
+from .helpers import class_to_dict, get_load_path, make_alg_runner  # noqa: F401

@@ -365,6 +365,7 @@ def test_cfg_edits_reach_the_kernels():
     K2.soft_dof_pos_limits = K.soft_dof_pos_limits
     K2.REWARD_SCALES.update(torques=-1e-5, feet_air_time=0.5, collision=0.0)
     K2.REWARD_NAMES = sorted(k for k, v in K2.REWARD_SCALES.items() if k != "termination" and v != 0.0)
+    K2.EPISODE_SUM_NAMES = sorted(k for k, v in K2.REWARD_SCALES.items() if v != 0.0)
     K2.CMD_RANGES.update(lin_vel_x=(-1.0, 1.0), heading=(-1.5, 1.5))
     K2.BASE_HEIGHT_TARGET, K2.P_GAIN = 0.30, 30.0
     K2.NOISE_SCALES["dof_vel"] = 1.0

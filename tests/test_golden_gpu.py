@@ -264,3 +264,63 @@ def test_cuda_runner_matches_reference_golden(golden_dir):
         d, r = _digest(v), out["param_digest"][k]
         assert abs(float(d[1] - r[1])) <= 1e-3 * max(1e-3, float(r[1])), (tag, k, d, r)
     assert list(ac.state_dict().keys()) == G["checkpoint_keys"] == list(STATE_KEYS)
+
+
+def test_save_load_resume_roundtrip(tmp_path, golden_dir):
+    """N1: OnPolicyRunner.save -> get_load_path -> make_alg_runner(resume) -> learn (on_policy_runner.py:249-264, helpers.py:73-95,
+    task_registry.py:123-128).  The file has the structure of the reference runner's own model_<it>.pt (recorded in the goldens),
+    a fresh runner resumed from it holds identical parameters / Adam moments / step counts / learning rate / iteration, and
+    continues training."""
+    import time
+    from dtc_b200.legged_gym.envs import LeggedRobotDTC, Lite3DTCCfg, Lite3DTCCfgPPO
+    from dtc_b200.legged_gym.utils import class_to_dict, get_load_path, make_alg_runner
+    G = torch.load(os.path.join(golden_dir, "learner_n8.pt"), weights_only=False)
+    N = 64
+
+    def build(seed):
+        hs, tor = sim_stub.make_heightmap("stones", 0)
+        layout = sim_stub.initial_env_layout(N, tor, seed)
+        fg = sim_stub.FakeGym(N, device=DEV)
+        g = torch.Generator(device=DEV).manual_seed(seed)
+        fg.source = lambda: sim_stub.synth_state(N, layout[2].to(DEV), g, device=DEV)
+        cfg = Lite3DTCCfg()
+        cfg.env.num_envs = N
+        return LeggedRobotDTC(cfg, sim_device=DEV, gym=fg, height_samples=hs, terrain_origins=tor, layout=layout, seed=seed)
+
+    root = str(tmp_path / "logs")
+    with pytest.raises(ValueError):
+        get_load_path(root)
+    torch.manual_seed(3)
+    ra, _ = make_alg_runner(build(1), Lite3DTCCfgPPO(), log_root=root, device=DEV)
+    ra.learn(2)
+    path = get_load_path(root)
+    assert os.path.basename(path) == "model_2.pt" and get_load_path(root, checkpoint=0).endswith("model_0.pt")
+    ck = torch.load(path, map_location="cpu", weights_only=True)
+    ref = G["checkpoint_struct"]
+    assert list(ck.keys()) == ref["top_keys"] and ck["iter"] == 2
+    assert {k: tuple(v.shape) for k, v in ck["model_state_dict"].items()} == ref["model"]
+    og, rg = ck["optimizer_state_dict"]["param_groups"], ref["opt_groups"]
+    assert len(og) == len(rg) == 1 and len(og[0]["params"]) == rg[0]["params"] and set(rg[0]) <= set(og[0])
+    ost = ck["optimizer_state_dict"]["state"]
+    assert set(ost.keys()) == set(ref["opt_state"].keys())
+    for i, st in ref["opt_state"].items():
+        assert {k: tuple(ost[i][k].shape) for k in st} == {k: v[0] for k, v in st.items()}, i
+    time.sleep(1.1)  # run directories are named to the second
+    class Resume(Lite3DTCCfgPPO):
+        class runner(Lite3DTCCfgPPO.runner):
+            resume = True
+    torch.manual_seed(99)  # a different initialisation, overwritten by the checkpoint
+    rb, _ = make_alg_runner(build(2), Resume(), log_root=root, device=DEV)
+    assert rb.current_learning_iteration == 2
+    sa, sb = ra.alg.actor_critic.state_dict(), rb.alg.actor_critic.state_dict()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    oa, ob = ra.alg.optimizer.state_dict(), rb.alg.optimizer.state_dict()
+    assert oa["param_groups"][0]["lr"] == ob["param_groups"][0]["lr"] and set(oa["state"]) == set(ob["state"])
+    for i in oa["state"]:
+        for key in ("step", "exp_avg", "exp_avg_sq"):
+            assert torch.equal(oa["state"][i][key].cpu(), ob["state"][i][key].cpu()), (i, key)
+    rb.learn(1)
+    assert rb.current_learning_iteration == 3 and os.path.exists(os.path.join(rb.log_dir, "model_3.pt"))
+    assert all(v == v for v in rb.alg.last_stats.values())
+    assert float(rb.alg.optimizer.state_dict()["state"][0]["step"]) == float(oa["state"][0]["step"]) + 20
