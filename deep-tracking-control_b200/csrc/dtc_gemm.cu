@@ -307,20 +307,23 @@ __global__ void k_colsum2(const float* __restrict__ ws, int N, float* __restrict
   out[n] = t;
 }
 
+int dtc_gemm_tc3_mode();  // dtc_gemm_tc.cu
 int dtc_gemm_pick_splits(int M, int N, int K) {
   const int tc_min = ceil_div(ceil_div(K, 32), 32);  // the tensor-core path keeps <= 32 k-blocks per TMEM accumulation
   if (K < 2048) return tc_min;
   if (M > 128 && N >= 100) {
     // CTA-pair kernel (256 x 128 tiles on 74 SM pairs): the split count that minimises rounds x k-blocks per split, e.g.
     // 512 x 693 over 24 576 rows: 24 splits = 288 tiles = 4 rounds of 32 k-blocks instead of 25 splits = 5 rounds of 31
-    const int pt = ceil_div(M, 256) * ceil_div(N, 128), nkb = ceil_div(K, 32), pairs = 74;
+    // 256-column tiles (k_gemm_tc3) for outputs at least 176 wide: half as many tiles, each twice as long per k-block
+    const bool wide = dtc_gemm_tc3_mode() && N >= 176;
+    const int pt = ceil_div(M, 256) * ceil_div(N, wide ? 256 : 128), nkb = ceil_div(K, 32), pairs = 74, w = wide ? 2 : 1;
     const int lo = tc_min < 1 ? 1 : tc_min;
     int best = lo;
     long best_cost = -1;
-    for (int c = lo; c <= lo + 24 && c <= nkb; ++c) {
-      if ((long)pt * c < pairs && c < lo + 24) continue;  // too few tiles for the pair kernel
+    for (int c = lo; c <= lo + 40 && c <= nkb; ++c) {
+      if ((long)pt * c < pairs && c < lo + 40) continue;  // too few tiles for the pair kernel
       // + the partial-tile round trip through the workspace: one split of a 512 x 693 output costs about 2.4 k-blocks of MMA time
-      const long cost = 5 * (long)ceil_div((long)pt * c, pairs) * ceil_div(nkb, c) + (long)pt * c;
+      const long cost = 5 * w * (long)ceil_div((long)pt * c, pairs) * ceil_div(nkb, c) + (long)w * pt * c;
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }
     }
     return best;
