@@ -579,6 +579,7 @@ extern "C" int dtc_env_create(const dtc_env_config* cfg, dtc_env** out) {
   e->bound = false;
   e->min3 = nullptr;
   e->min3_bytes = 0;
+  e->min3_map_ok = false;
   cudaError_t ce = cudaMalloc(&e->d_cfg, sizeof(dtc_env_config));
   if (ce == cudaSuccess) ce = cudaMemcpy(e->d_cfg, cfg, sizeof(dtc_env_config), cudaMemcpyHostToDevice);
   if (ce != cudaSuccess) { delete e; DTC_FAIL(DTC_ERR_CUDA, "dtc_env_create: %s", cudaGetErrorString(ce)); }

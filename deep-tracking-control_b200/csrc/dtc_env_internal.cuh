@@ -7,7 +7,9 @@ struct dtc_env {
   dtc_env_buffers buf;
   bool bound;
   dtc_env_config* d_cfg;  // device copy (tables are too large for kernel parameters)
-  int16_t* min3;          // variant 5: min(H[x][y], H[x+1][y], H[x][y+1]) of the bound heightmap (library-owned)
+  int16_t* min3;          // variants 5 / 6: min(H[x][y], H[x+1][y], H[x][y+1]) of the bound heightmap (library-owned)
   size_t min3_bytes;
+  CUtensorMap min3_map;   // variant 6: 2-D tensor map of min3 (box = one 42 x 48-cell patch) for the TMA patch loads
+  bool min3_map_ok;
 };
 int dtc_env_build_min3(dtc_env* e);  // dtc_foothold.cu

@@ -914,8 +914,9 @@ k_foothold_v5(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const i
 //     boundary are skipped there and finished by a compact while-loop over the set bits of the per-lane mask;
 //   * exception flags are a byte array in shared memory (no mask shuffles), the rotation tables are gone (the window search
 //     rotates its <= 96 candidates directly), divisions by constants are multiplications;
-//   * one patch buffer per warp, refilled with cp.async right after the sampling loop so the copy overlaps the window search;
-//     6.8 KB of shared memory per warp and 96 registers put 20 warps on an SM (variant 5: 16);
+//   * one patch buffer per warp, refilled by ONE 2-D TMA box load (cp.async.bulk.tensor.2d on the min3 table's tensor map, completion
+//     on the warp's mbarrier) right after the sampling loop, so the copy overlaps the window search;
+//     6.9 KB of shared memory per warp and 80 registers put 24 warps on an SM (variant 5: 16);
 //   * the sampling loop runs on the packed fp32x2 pipe (FFMA2 / FADD2 / FMUL2: two samples per issue slot).
 // packed fp32x2 arithmetic of sm_100 (FFMA2 / FADD2 / FMUL2: two IEEE round-to-nearest results per issue slot)
 __device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
@@ -959,9 +960,10 @@ struct V6Rec {  // per-environment constants written by the prepare threads
   float pf[4][3];          // Raibert nominal footholds (legged_robot_dtc.py:100-115)
   int ci[4], cj[4];        // lattice cell nearest to each nominal foothold
 };
-struct __align__(16) V6Warp {
-  int16_t patch[V6_PH * V6_PC];  // 4032 B
+struct __align__(128) V6Warp {
+  int16_t patch[V6_PH * V6_PC];  // 4032 B, 128-byte aligned: destination of one cp.async.bulk.tensor.2d box
   float gc[NP + 3];              // clamped relative heights
+  uint64_t mbar;                 // completion barrier of the patch load
 };
 struct __align__(16) V6Cta {
   V6Warp w[V6_WARPS];
@@ -1021,27 +1023,30 @@ __device__ __forceinline__ void v6_prepare(const dtc_env_config* __restrict__ cf
   R.cj[l] = (int)floorf((lyf + 0.5f) * 20.0f + 0.5f);
 }
 
-// 42 x 48-cell window of the min3 map around the rotated sampling grid: every lane moves eight 16-byte chunks (252 in all)
-__device__ __forceinline__ void v6_stage_patch(const int16_t* __restrict__ min3, int cols, const V6Rec& R, int16_t* patch, int lane) {
-  if (R.fast) {
-    const char* src0 = reinterpret_cast<const char*>(min3 + (size_t)R.x0 * cols + R.y0);
-    const uint32_t dst0 = smem_u32(patch);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int ch = lane + 32 * i;
-      const int r = (ch * 171) >> 10, q = ch - 6 * r;  // row = ch / 6, 16-byte column chunk = ch % 6
-      if (ch < V6_PH * (V6_PC / 8))
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(r * (V6_PC * 2) + q * 16)),
-                     "l"(src0 + (size_t)r * (size_t)(cols * 2) + q * 16)
-                     : "memory");
-    }
+// 42 x 48-cell window of the min3 map around the rotated sampling grid, staged by ONE 2-D TMA box load issued by lane 0
+// (cp.async.bulk.tensor.2d, completion on the warp's mbarrier).  The box must start on a 16-byte boundary of its row - an
+// unaligned inner coordinate is what raised "illegal instruction" in round 1 (tools/tma2d_probe.cu) - which the patch origin
+// already guarantees: y0 is rounded down to 8 cells.
+__device__ __forceinline__ void v6_stage_patch(const CUtensorMap* tmap, const V6Rec& R, V6Warp& W, int lane) {
+  if (R.fast && lane == 0) {
+    const uint32_t mb = smem_u32(&W.mbar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(V6_PH * V6_PC * 2) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(W.patch)),
+                 "l"((uint64_t)tmap), "r"(mb), "r"(R.y0), "r"(R.x0)
+                 : "memory");
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void v6_wait_patch(V6Warp& W, uint32_t parity) {
+  const uint32_t mb = smem_u32(&W.mbar);
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb), "r"(parity) : "memory");
 }
 
 template <bool SEP, int CPS>
 __global__ void __launch_bounds__(V6_WARPS * 32, CPS)
-k_foothold_v6(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const int16_t* __restrict__ min3, const V5Params P, int per_cta) {
+k_foothold_v6(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const int16_t* __restrict__ min3, const V5Params P, int per_cta,
+              const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) uint8_t v6_smem_raw[];
   V6Cta& S = *reinterpret_cast<V6Cta*>(v6_smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1053,6 +1058,11 @@ k_foothold_v6(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const i
   const float border = cfg->border_size, hscale = cfg->horizontal_scale, vscale = cfg->vertical_scale;
   if (threadIdx.x < GXN) S.gx[threadIdx.x] = cfg->grid_x[threadIdx.x];
   if (threadIdx.x >= 64 && threadIdx.x < 64 + GYN) S.gy[threadIdx.x - 64] = cfg->grid_y[threadIdx.x - 64];
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&W.mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t patch_phase = 0;  // parity of the next patch load to complete on this warp's barrier
   for (int i = threadIdx.x; i < (V6_NK / 2) * 32; i += V6_WARPS * 32) {
     const int pa_ = min(64 * (i >> 5) + (i & 31), NP - 1), pb_ = min(pa_ + 32, NP - 1);
     S.gtab[i >> 5][i & 31] = make_float4(cfg->grid_x[pa_ / GYN], cfg->grid_x[pb_ / GYN], cfg->grid_y[pa_ % GYN], cfg->grid_y[pb_ % GYN]);
@@ -1075,13 +1085,13 @@ k_foothold_v6(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const i
     __syncthreads();  // the previous round's records are no longer read (first round: the constant tables are written)
     if ((int)(threadIdx.x >> 2) < nb) v6_prepare(cfg, b, base + (threadIdx.x >> 2), threadIdx.x & 3, S.rec[threadIdx.x >> 2], P);
     __syncthreads();
-    if (warp < nb) v6_stage_patch(min3, cols, S.rec[warp], W.patch, lane);
+    if (warp < nb) v6_stage_patch(&tmap, S.rec[warp], W, lane);
     for (int e = warp; e < nb; e += V6_WARPS) {
       const V6Rec& R = S.rec[e];
       const int n = base + e;
       const float root_x = R.root_x, root_y = R.root_y, root_z = R.root_z, yz = R.yz, yw = R.yw;
       float* mh_out = b.measured_heights + (size_t)n * NP;
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (R.fast) { v6_wait_patch(W, patch_phase); patch_phase ^= 1u; }
       __syncwarp();
 
       // ---------------------------------------------------------------- phase 1: samples, stores, moments, plane fit
@@ -1198,8 +1208,7 @@ k_foothold_v6(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const i
         }
       }
       __syncwarp();  // every lane is done with the patch: refill it for this warp's next environment while the search runs
-      if (e + V6_WARPS < nb) v6_stage_patch(min3, cols, S.rec[e + V6_WARPS], W.patch, lane);
-      else asm volatile("cp.async.commit_group;" ::: "memory");
+      if (e + V6_WARPS < nb) v6_stage_patch(&tmap, S.rec[e + V6_WARPS], W, lane);
       const double S1 = warp_sum((double)s1.x + (double)s1.y), S2 = warp_sum((double)s2.x + (double)s2.y);
       const float CS = warp_sum(cs);
       const double PA = (double)warp_sum(pa.x + pa.y) * (SEP ? (double)P.ax : 1.0) + (double)mh0 * P.r0;
@@ -1338,12 +1347,13 @@ static int launch_v6(dtc_env* e, const V5Params& P, cudaStream_t st) {
   // contiguous chunks, a whole number of environments per warp, one wave of CTAs
   int per = ceil_div(N, sms * CPS);
   per = ceil_div(per, V6_WARPS) * V6_WARPS;
-  k_foothold_v6<SEP, CPS><<<ceil_div(N, per), V6_WARPS * 32, smem, st>>>(e->d_cfg, e->buf, e->min3, P, per);
+  if (!e->min3_map_ok) DTC_FAIL(DTC_ERR_STATE, "dtc_foothold_step: tensor map of the min3 table missing (dtc_env_bind builds it)");
+  k_foothold_v6<SEP, CPS><<<ceil_div(N, per), V6_WARPS * 32, smem, st>>>(e->d_cfg, e->buf, e->min3, P, per, e->min3_map);
   return DTC_OK;
 }
 static int v6_cps() {  // resident CTAs per SM the kernel is compiled for (env DTC_FH_CPS = 4 | 5 | 6, tuning knob)
   static int cps = 0;
-  if (!cps) { const char* s = getenv("DTC_FH_CPS"); cps = s ? atoi(s) : 5; if (cps < 4 || cps > 6) cps = 5; }
+  if (!cps) { const char* s = getenv("DTC_FH_CPS"); cps = s ? atoi(s) : 6; if (cps < 4 || cps > 6) cps = 6; }
   return cps;
 }
 template <bool SEP>
@@ -1374,6 +1384,23 @@ int dtc_env_build_min3(dtc_env* e) {
   k_min3_map<<<148 * 4, 256>>>(e->buf.height_samples, e->min3, e->cfg.map_rows, e->cfg.map_cols);
   DTC_CHECK_LAUNCH("k_min3_map");
   DTC_CUDA(cudaDeviceSynchronize());
+  // 2-D tensor map for variant 6's patch loads: int16 [rows, cols], box = 48 columns x 42 rows, no swizzle (rows of the box land
+  // 96 bytes apart in shared memory, the layout the sampling loop indexes)
+  e->min3_map_ok = false;
+  if ((e->cfg.map_cols * 2) % 16 == 0 && e->cfg.map_cols >= V6_PC && e->cfg.map_rows >= V6_PH) {
+    typedef CUresult (*PFN_enc)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    DTC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) DTC_FAIL(DTC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    cuuint64_t dims[2] = {(cuuint64_t)e->cfg.map_cols, (cuuint64_t)e->cfg.map_rows}, strides[1] = {(cuuint64_t)e->cfg.map_cols * 2};
+    cuuint32_t box[2] = {V6_PC, V6_PH}, es[2] = {1, 1};
+    const CUresult r = ((PFN_enc)fn)(&e->min3_map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, e->min3, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) DTC_FAIL(DTC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the min3 table", (int)r);
+    e->min3_map_ok = true;
+  }
   return DTC_OK;
 }
 
