@@ -22,7 +22,8 @@ __device__ __forceinline__ Philox env_rng(uint64_t seed, int64_t step, int env, 
 // back to back in one launch (count = 4) - the same arithmetic either way.
 __global__ void __launch_bounds__(256) k_pre_physics(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b,
                                                      const float* __restrict__ actions_in, int4 choice, int first, int count,
-                                                     int64_t step, uint64_t seed) {
+                                                     int64_t step, uint64_t seed, const int64_t* __restrict__ step_base) {
+  if (step_base) step += *step_base;  // CUDA-graph replays: the launch carries the step relative to a device-side counter
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int N = cfg->num_envs;
   if (i >= N * 12) return;
@@ -92,7 +93,8 @@ __device__ __forceinline__ void resample_commands_dev(const dtc_env_config* cfg,
 }
 
 __global__ void __launch_bounds__(128) k_state_prep(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b,
-                                                    int64_t step, uint64_t seed, dtc_env_noise nz) {
+                                                    int64_t step, uint64_t seed, dtc_env_noise nz, const int64_t* __restrict__ step_base) {
+  if (step_base) step += *step_base;
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   int N = cfg->num_envs;
   if (n >= N) return;
@@ -156,7 +158,9 @@ __global__ void __launch_bounds__(128) k_state_prep(const dtc_env_config* __rest
 __device__ __forceinline__ float norm3(float x, float y, float z) { return sqrtf(x * x + y * y + z * z); }
 
 __global__ void __launch_bounds__(128) k_reward_reset(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b,
-                                                      int64_t step, uint64_t seed, float reset_normal, dtc_env_noise nz) {
+                                                      int64_t step, uint64_t seed, float reset_normal, dtc_env_noise nz,
+                                                      const int64_t* __restrict__ step_base) {
+  if (step_base) step += *step_base;
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int N = cfg->num_envs;
   if (n >= N) return;
@@ -490,7 +494,8 @@ __global__ void __launch_bounds__(128) k_reward_reset(const dtc_env_config* __re
 // ================================================================== E14 + E15 + clip + last_* roll
 // One warp per environment: 53 obs + 1389 privileged + 265 history floats are written as coalesced rows.
 __global__ void __launch_bounds__(128) k_observe(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, int64_t step,
-                                                 uint64_t seed, dtc_env_noise nz) {
+                                                 uint64_t seed, dtc_env_noise nz, const int64_t* __restrict__ step_base) {
+  if (step_base) step += *step_base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = cfg->num_envs;
   const int n = blockIdx.x * 4 + warp;
@@ -580,6 +585,7 @@ extern "C" int dtc_env_create(const dtc_env_config* cfg, dtc_env** out) {
   e->min3 = nullptr;
   e->min3_bytes = 0;
   e->min3_map_ok = false;
+  e->step_base = nullptr;
   cudaError_t ce = cudaMalloc(&e->d_cfg, sizeof(dtc_env_config));
   if (ce == cudaSuccess) ce = cudaMemcpy(e->d_cfg, cfg, sizeof(dtc_env_config), cudaMemcpyHostToDevice);
   if (ce != cudaSuccess) { delete e; DTC_FAIL(DTC_ERR_CUDA, "dtc_env_create: %s", cudaGetErrorString(ce)); }
@@ -603,6 +609,19 @@ extern "C" int dtc_env_bind(dtc_env* e, const dtc_env_buffers* buf) {
   e->bound = true;
   return dtc_env_build_min3(e);
 }
+extern "C" int dtc_env_set_step_base(dtc_env* e, const int64_t* device_counter) {
+  if (!e) DTC_FAIL(DTC_ERR_ARG, "dtc_env_set_step_base: null env");
+  e->step_base = device_counter;
+  return DTC_OK;
+}
+__global__ void k_counter_add(int64_t* p, int64_t inc) { *p += inc; }
+extern "C" int dtc_counter_add(int64_t* device_counter, int64_t inc, void* stream) {
+  if (!device_counter) DTC_FAIL(DTC_ERR_ARG, "dtc_counter_add: null pointer");
+  k_counter_add<<<1, 1, 0, (cudaStream_t)stream>>>(device_counter, inc);
+  DTC_CHECK_LAUNCH("k_counter_add");
+  return DTC_OK;
+}
+extern "C" void dtc_count_launches(int64_t n) { g_dtc_launches += n; }
 extern "C" int dtc_env_heightmap_updated(dtc_env* e) {
   if (!e || !e->bound) DTC_FAIL(DTC_ERR_STATE, "dtc_env_heightmap_updated: env not bound");
   return dtc_env_build_min3(e);
@@ -618,7 +637,7 @@ extern "C" int dtc_env_pre_physics(dtc_env* e, const float* actions_in, const in
   int total = e->cfg.num_envs * 12;
   k_pre_physics<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
       e->d_cfg, e->buf, actions_in, make_int4(lag_choice[0], lag_choice[1], lag_choice[2], lag_choice[3]), first_substep, num_substeps,
-      step, seed);
+      step, seed, e->step_base);
   DTC_CHECK_LAUNCH("k_pre_physics");
   return DTC_OK;
 }
@@ -629,20 +648,20 @@ static dtc_env_noise noise_or_null(const dtc_env_noise* nz) {
 }
 extern "C" int dtc_env_state_prep(dtc_env* e, int64_t step, uint64_t seed, const dtc_env_noise* noise, void* stream) {
   if (!e || !e->bound) DTC_FAIL(DTC_ERR_STATE, "dtc_env_state_prep: env not bound");
-  k_state_prep<<<ceil_div(e->cfg.num_envs, 128), 128, 0, (cudaStream_t)stream>>>(e->d_cfg, e->buf, step, seed, noise_or_null(noise));
+  k_state_prep<<<ceil_div(e->cfg.num_envs, 128), 128, 0, (cudaStream_t)stream>>>(e->d_cfg, e->buf, step, seed, noise_or_null(noise), e->step_base);
   DTC_CHECK_LAUNCH("k_state_prep");
   return DTC_OK;
 }
 extern "C" int dtc_env_reward_reset(dtc_env* e, int64_t step, uint64_t seed, float reset_normal, const dtc_env_noise* noise, void* stream) {
   if (!e || !e->bound) DTC_FAIL(DTC_ERR_STATE, "dtc_env_reward_reset: env not bound");
   k_reward_reset<<<ceil_div(e->cfg.num_envs, 128), 128, 0, (cudaStream_t)stream>>>(e->d_cfg, e->buf, step, seed, reset_normal,
-                                                                                 noise_or_null(noise));
+                                                                                 noise_or_null(noise), e->step_base);
   DTC_CHECK_LAUNCH("k_reward_reset");
   return DTC_OK;
 }
 extern "C" int dtc_env_observe(dtc_env* e, int64_t step, uint64_t seed, const dtc_env_noise* noise, void* stream) {
   if (!e || !e->bound) DTC_FAIL(DTC_ERR_STATE, "dtc_env_observe: env not bound");
-  k_observe<<<ceil_div(e->cfg.num_envs, 4), 128, 0, (cudaStream_t)stream>>>(e->d_cfg, e->buf, step, seed, noise_or_null(noise));
+  k_observe<<<ceil_div(e->cfg.num_envs, 4), 128, 0, (cudaStream_t)stream>>>(e->d_cfg, e->buf, step, seed, noise_or_null(noise), e->step_base);
   DTC_CHECK_LAUNCH("k_observe");
   return DTC_OK;
 }

@@ -11,5 +11,6 @@ struct dtc_env {
   size_t min3_bytes;
   CUtensorMap min3_map;   // variant 6: 2-D tensor map of min3 (box = one 42 x 48-cell patch) for the TMA patch loads
   bool min3_map_ok;
+  const int64_t* step_base;  // optional device-side counter added to every launch's step argument (dtc_env_set_step_base)
 };
 int dtc_env_build_min3(dtc_env* e);  // dtc_foothold.cu

@@ -196,6 +196,7 @@ struct dtc_learner {
   // data parallel: gradient buckets of the last step, [which][bucket] (see dtc_learner_wait_bucket)
   bool bucket_ready;
   cudaEvent_t bucket_ev[2][2];
+  const uint64_t* act_counter_base;  // optional device-side counter added to dtc_policy_act's Philox counter (CUDA-graph replays)
 };
 
 static const float* lo_of(const dtc_learner* l, const float* p) {
@@ -271,6 +272,7 @@ extern "C" int dtc_learner_create(int32_t max_rows, float* params, float* grads,
   l->last_M = 0;
   l->side_ready = false;
   l->bucket_ready = false;
+  l->act_counter_base = nullptr;
   l->ev_next = 0;
   // ordered with the caller's own work (the parameter upload ahead of this call, the first step after it): no host sync
   DTC_CUDA(cudaMemsetAsync(l->stats, 0, ST_COUNT * sizeof(double), (cudaStream_t)stream));

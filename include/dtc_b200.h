@@ -330,6 +330,17 @@ int dtc_terrain_rasterize(int32_t rows, int32_t cols, int32_t border_px, int32_t
                           const dtc_subterrain* subs, const int32_t* tables, double terrain_length, double vertical_scale,
                           int16_t* height_samples, float* terrain_origins, void* stream);
 
+/* The reference's own generator, legged_gym/utils/terrain.py:9-243 (Terrain.curiculum / randomized_terrain / make_terrain /
+ * add_terrain_to_map and the isaacgym.terrain_utils + gap / pit / stones_everywhere generators behind it): each sub-terrain is a
+ * background height plus an ORDERED list of `height_field_raw[x0:x1, y0:y1] = h` assignments, which the host records while replaying
+ * the generator's loops and numpy draws (deep-tracking-control_b200/legged_gym/utils/terrain.py); the device paints them - the last
+ * rectangle covering a cell wins.  subs[s] = {type 5, a = number of rectangles, b = index of the first in `rects`, c = background};
+ * rects: int32 [n][5] = {x0, x1, y0, y1, height} in sub-terrain cells, half-open.  terrain_origins [n_rows, n_cols, 3] = sub-terrain
+ * centre with the maximum height over origin_window = {x1, x2, y1, y2} (terrain.py:152-160). */
+int dtc_terrain_paint(int32_t rows, int32_t cols, int32_t border_px, int32_t len_px, int32_t wid_px, int32_t n_rows, int32_t n_cols,
+                      const dtc_subterrain* subs, const int32_t* rects, const int32_t origin_window[4], double terrain_length,
+                      double terrain_width, double vertical_scale, int16_t* height_samples, float* terrain_origins, void* stream);
+
 /* ------------------------------------------------------------------ P14 / SURVEY 8f N2: the optional GRU `Memory`
  * Memory.forward / Memory.reset (rsl_rl/rsl_rl/modules/actor_critic_decoder.py:584-614): nn.GRU(input_size, hidden_size,
  * num_layers) over T time steps for N rows.  `weights`: per layer weight_ih_l [3H,in_l] | weight_hh_l [3H,H] | bias_ih_l [3H] |

@@ -170,7 +170,36 @@ def learner_golden(N=8, iters=2, seed=5):
     print("learner golden: lr", [o["lr"] for o in out["iters_out"]], "params", out["num_params"])
 
 
+TERRAIN_CASES = {
+    # name: (seed, overrides of Lite3DTCCfg.terrain)
+    "lite3": (7, {}),                                                       # the task's own 6 x 2 curriculum: stairs down | discrete obstacles
+    "mix10": (3, dict(num_rows=3, num_cols=10)),                            # + stairs up and Isaac Gym stepping stones
+    "custom3": (5, dict(num_rows=4, num_cols=3, terrain_proportions=[0, 0, 0, 0, 0, 0, 1 / 3, 1 / 3, 1 / 3])),  # gap | pit | stones_everywhere
+    "random": (9, dict(num_rows=2, num_cols=4, curriculum=False, terrain_proportions=[0, 0, 0.2, 0.2, 0.2, 0.2, 0.1, 0.05, 0.05])),
+}
+
+
+def terrain_cfg(overrides):
+    RH.import_reference()
+    from legged_gym.envs.lite3.lite3_dtc_config import Lite3DTCCfg
+    return type("terrain", (Lite3DTCCfg.terrain,), dict(overrides))
+
+
+def terrain_golden():
+    """N3: the UNMODIFIED reference `Terrain` (legged_gym/utils/terrain.py) over the isaacgym.terrain_utils stand-in."""
+    RH.import_reference()
+    from legged_gym.utils.terrain import Terrain
+    for name, (seed, ov) in TERRAIN_CASES.items():
+        np.random.seed(seed)
+        t = Terrain(terrain_cfg(ov), 16)
+        np.savez_compressed(os.path.join(OUT, f"terrain_{name}.npz"), height_field_raw=t.height_field_raw, env_origins=t.env_origins, seed=seed)
+        print("terrain golden", name, t.height_field_raw.shape, int(t.height_field_raw.min()), int(t.height_field_raw.max()))
+
+
 if __name__ == "__main__":
+    terrain_golden()
+    if "--terrain-only" in sys.argv:
+        sys.exit(0)
     env_golden()
     learner_golden()
     for f in sorted(os.listdir(OUT)):

@@ -436,3 +436,35 @@ def test_partial_reset_idx_and_hooks():
     ep = cenv.extras["episode"]
     assert float(ep["rew_torques"]) == pytest.approx(float(sums_before[K.EPISODE_SUM_NAMES.index("torques"), ids].mean()) / 20.0, rel=1e-5)
     cenv.reset_idx(torch.zeros(0, dtype=torch.long))  # empty list: no-op, like the reference's early return
+
+
+@pytest.mark.parametrize("name", ["lite3", "mix10", "custom3", "random"])
+def test_terrain_class_matches_reference_golden(name, golden_dir):
+    """N3: `dtc_b200.legged_gym.utils.Terrain` (generators replayed on the host as rectangle lists, rasterised by dtc_terrain_paint)
+    against the heightmap / env origins the UNMODIFIED reference class produced from the same numpy seed: bit-exact."""
+    import os
+    import numpy as np
+    from dtc_b200.legged_gym.utils import Terrain
+    from tests.test_oracle_golden import TERRAIN_CASES, terrain_cfg
+    seed, ov = TERRAIN_CASES[name]
+    G = np.load(os.path.join(golden_dir, f"terrain_{name}.npz"))
+    np.random.seed(seed)
+    t = Terrain(terrain_cfg(ov), 16, device="cuda")
+    hf = t.height_field_raw.cpu().numpy()
+    assert hf.dtype == np.int16 and hf.shape == G["height_field_raw"].shape == (t.tot_rows, t.tot_cols)
+    assert np.array_equal(hf, G["height_field_raw"]), int((hf != G["height_field_raw"]).sum())
+    # origins: float32 on the device vs the reference's float64 numpy
+    assert np.allclose(t.env_origins, G["env_origins"], rtol=0, atol=1e-6)
+    if name == "lite3":
+        # the device-built map drives an environment without visiting the host
+        from dtc_b200.legged_gym.envs import LeggedRobotDTC, Lite3DTCCfg
+        N = 128
+        layout = sim_stub.initial_env_layout(N, t.terrain_origins, 1)
+        fg = sim_stub.FakeGym(N, device="cuda")
+        cfg = Lite3DTCCfg()
+        cfg.env.num_envs = N
+        env = LeggedRobotDTC(cfg, sim_device="cuda", gym=fg, height_samples=t.height_field_raw, terrain_origins=t.terrain_origins, layout=layout, seed=1)
+        g = torch.Generator(device="cuda").manual_seed(2)
+        fg.load(sim_stub.synth_state(N, env.env_origins, g, device="cuda"))
+        env.reset()
+        assert float(env.measured_heights.abs().max()) > 0.0

@@ -206,3 +206,34 @@ def test_learner_matches_reference(learner_gold):
         for k, v in ac.state_dict().items():
             d, r = _digest(v), out["param_digest"][k]
             assert abs(float(d[1] - r[1])) <= (1e-3 if it == 0 else 1e-2) * max(1e-3, float(r[1])), (tag, k, d, r)
+
+
+TERRAIN_CASES = {  # same table as tests/golden/make_golden.py
+    "lite3": (7, {}),
+    "mix10": (3, dict(num_rows=3, num_cols=10)),
+    "custom3": (5, dict(num_rows=4, num_cols=3, terrain_proportions=[0, 0, 0, 0, 0, 0, 1 / 3, 1 / 3, 1 / 3])),
+    "random": (9, dict(num_rows=2, num_cols=4, curriculum=False, terrain_proportions=[0, 0, 0.2, 0.2, 0.2, 0.2, 0.1, 0.05, 0.05])),
+}
+
+
+def terrain_cfg(overrides):
+    """cfg.terrain of the Lite3 DTC task (lite3_dtc_config.py:20-51) with a test case's overrides."""
+    import types
+    base = dict(horizontal_scale=0.05, vertical_scale=0.005, border_size=20, curriculum=True, terrain_length=8.0, terrain_width=8.0,
+                num_rows=6, num_cols=2, terrain_proportions=[0.0, 0.0, 0.2, 0.2, 0.2, 0.4], mesh_type="trimesh", selected=False,
+                max_init_terrain_level=5, slope_treshold=0.75)
+    base.update(overrides)
+    return types.SimpleNamespace(**base)
+
+
+@pytest.mark.parametrize("name", sorted(TERRAIN_CASES))
+def test_terrain_matches_reference(name, golden_dir):
+    """N3: the terrain oracle against heightmaps / env origins recorded from the unmodified reference `Terrain` class."""
+    from oracle import terrain_oracle as TO
+    seed, ov = TERRAIN_CASES[name]
+    G = np.load(os.path.join(golden_dir, f"terrain_{name}.npz"))
+    np.random.seed(seed)
+    hf, origins = TO.terrain_map(terrain_cfg(ov))
+    assert hf.dtype == np.int16 and hf.shape == G["height_field_raw"].shape
+    assert np.array_equal(hf, G["height_field_raw"]), int((hf != G["height_field_raw"]).sum())
+    assert np.array_equal(origins, G["env_origins"])
