@@ -134,7 +134,9 @@ def build_world(n_envs, rank, device, kind="stones"):
 
     fg.source = source
     torch.manual_seed(1)  # identical initial policy on every rank (data parallel replicas)
-    runner = OnPolicyRunner(env, class_to_dict(Lite3DTCCfgPPO()), log_dir=None, device=device)
+    tc = class_to_dict(Lite3DTCCfgPPO())
+    tc["runner"]["cuda_graph"] = os.environ.get("DTC_CUDA_GRAPH", "1") != "0"  # rollout replayed as one CUDA graph (A/B switch)
+    runner = OnPolicyRunner(env, tc, log_dir=None, device=device)
     return env, fg, runner, state, pool_host, pool_dev
 
 
@@ -315,12 +317,14 @@ def run_cuda(args):
     else:
         state["pool"] = pool_host
         fg.enable_prefetch(True)  # host->device copies of step t+1 on a copy stream while step t's kernels run
-        runner.learn(1)
+        runner.reset_graph()      # the captured rollout baked the device pool in: one eager iteration, one capturing, then timed replays
+        runner.learn(2)
         ms_e2e = timed(runner, args.steps, world, device)
         e2e_value = env_steps / (ms_e2e * 1e-3)
         fg.enable_prefetch(False)
         torch.cuda.synchronize(device)
         state["pool"] = pool_dev
+        runner.reset_graph()
 
     # roofline of the dominant kernel (the GEMM family: > 90 % of the step), measured with CUDA events around every
     # launch of one extra iteration
@@ -328,7 +332,7 @@ def run_cuda(args):
     if rank == 0 and not args.profile_lite:
         lib.dtc_profile_enable(1)
     if not args.profile_lite:
-        runner.learn(1)  # every rank takes part (the optimizer steps all-reduce); only rank 0 records events
+        runner.learn(1)  # every rank takes part (the optimizer steps all-reduce); only rank 0 records events (eager launches: the graph was reset)
     torch.cuda.synchronize(device)
     if rank == 0 and not args.profile_lite:
         import ctypes as C

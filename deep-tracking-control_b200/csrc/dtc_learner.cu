@@ -365,6 +365,11 @@ extern "C" int dtc_learner_reset_stats(dtc_learner* l, void* stream) {
   DTC_CUDA(cudaMemsetAsync(l->stats + ST_NVAE, 0, 2 * sizeof(double), (cudaStream_t)stream));
   return DTC_OK;
 }
+extern "C" int dtc_learner_set_act_counter_base(dtc_learner* l, const uint64_t* device_counter) {
+  if (!l) DTC_FAIL(DTC_ERR_ARG, "dtc_learner_set_act_counter_base: null learner");
+  l->act_counter_base = device_counter;
+  return DTC_OK;
+}
 extern "C" int dtc_learner_set_adam_steps(dtc_learner* l, int64_t vae_steps, int64_t main_steps) {
   if (!l) DTC_FAIL(DTC_ERR_ARG, "null learner");
   l->vae_steps = vae_steps; l->main_steps = main_steps;
@@ -610,7 +615,8 @@ __global__ void __launch_bounds__(256) k_pack_inputs(int M, const float* __restr
 __global__ void __launch_bounds__(128) k_latent_fwd(int M, int mode, float* __restrict__ ML, const LvStat* __restrict__ st,
                                                     const float* __restrict__ eps_in, uint64_t seed, uint64_t counter,
                                                     float* __restrict__ EPS, float* __restrict__ OUTM, const float* __restrict__ xc,
-                                                    float* __restrict__ X, float* __restrict__ X_lo) {
+                                                    float* __restrict__ X, float* __restrict__ X_lo, const uint64_t* __restrict__ cbase) {
+  if (cbase) counter += 2ull * *cbase;  // dtc_policy_act under a CUDA graph: the launch carries a counter relative to a device-side one
   const int r8 = threadIdx.x >> 4, j = threadIdx.x & 15;
   const int row = blockIdx.x * 8 + r8;
   const int ldx = mode == 0 ? LD_XA : LD_XD, zoff = mode == 0 ? XA_Z : XD_Z, muoff = mode == 0 ? XA_MU : XD_MU;
@@ -698,7 +704,8 @@ __global__ void __launch_bounds__(128) k_act_head(int M, const float* __restrict
                                                   uint64_t counter, float* __restrict__ o_act, float* __restrict__ o_val,
                                                   float* __restrict__ o_logp, float* __restrict__ o_mu, float* __restrict__ o_sig,
                                                   float* __restrict__ x_act, float* __restrict__ x_val, float* __restrict__ x_logp,
-                                                  float* __restrict__ x_mu, float* __restrict__ x_sig) {
+                                                  float* __restrict__ x_mu, float* __restrict__ x_sig, const uint64_t* __restrict__ cbase) {
+  if (cbase) counter += 2ull * *cbase;
   const int row = blockIdx.x * 128 + threadIdx.x;
   if (row >= M) return;
   float logp = 0.f;
@@ -1082,7 +1089,7 @@ extern "C" int dtc_learner_wait_bucket(dtc_learner* l, int which, int bucket, vo
 }
 
 static int encode(dtc_learner* l, int M, const float* hist, const float* priv_a, const float* xc, int mode, const float* eps,
-                  uint64_t seed, uint64_t counter, const StepStreams& S) {
+                  uint64_t seed, uint64_t counter, const StepStreams& S, const uint64_t* cbase = nullptr) {
   float* X = mode == 0 ? l->XA : l->XD;
   const int ldx = mode == 0 ? LD_XA : LD_XD;
   cudaStream_t st = S.main, sc = S.c;
@@ -1100,7 +1107,7 @@ static int encode(dtc_learner* l, int M, const float* hist, const float* priv_a,
   RET_IF(fwd(l, TE2, l->T1, 512, l->T2, 512, 1, M, st));
   RET_IF(fwd(l, TE4, l->T2, 512, X, ldx, 0, M, st));
   RET_IF(chain(l, sc, st));
-  k_latent_fwd<<<ceil_div(M, 8), 128, 0, st>>>(M, mode, l->ML, l->lvstat, eps, seed, counter, l->EPS, l->OUTM, xc, X, lo_of(l, X));
+  k_latent_fwd<<<ceil_div(M, 8), 128, 0, st>>>(M, mode, l->ML, l->lvstat, eps, seed, counter, l->EPS, l->OUTM, xc, X, lo_of(l, X), cbase);
   DTC_CHECK_LAUNCH("k_latent_fwd");
   return DTC_OK;
 }
@@ -1188,11 +1195,11 @@ extern "C" int dtc_policy_act(dtc_learner* l, int32_t M, const float* obs, int32
   StepStreams S;
   RET_IF(streams_begin(l, st, &S));
   RET_IF(critic_fwd(l, M, xc, S.w));
-  RET_IF(encode(l, M, xh, xp, xc, 0, eps_z, seed, counter * 2, S));
+  RET_IF(encode(l, M, xh, xp, xc, 0, eps_z, seed, counter * 2, S, l->act_counter_base));
   RET_IF(actor_fwd(l, M, st));
   RET_IF(streams_end(l, S));
   k_act_head<<<ceil_div(M, 128), 128, 0, st>>>(M, l->MEAN, l->V, l->params + g_off_std, eps_a, seed, counter * 2 + 1, o_act, o_val,
-                                              o_logp, o_mu, o_sig, actions, values, logp, mean, sigma);
+                                              o_logp, o_mu, o_sig, actions, values, logp, mean, sigma, l->act_counter_base);
   DTC_CHECK_LAUNCH("k_act_head");
   return DTC_OK;
 }

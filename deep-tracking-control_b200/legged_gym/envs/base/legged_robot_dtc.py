@@ -141,6 +141,11 @@ class LeggedRobotDTC:
         self._host_draws = None  # injected host draws: dict(lag=[4 ints], reset_normal=float)
         self._make_ctx()
         self.extras = _Extras(self)
+        # CUDA-graph support (include/dtc_b200.h: dtc_env_set_step_base): kernels receive common_step_counter - _step_offset and add
+        # the device-side copy of _step_offset, so a captured rollout can be replayed with an advancing step counter
+        self._step_offset = 0
+        self._step_base = torch.zeros(1, device=dev, dtype=torch.int64)
+        B.check(self.lib.dtc_env_set_step_base(self._h, B.ptr(self._step_base)), "dtc_env_set_step_base")
 
     # ------------------------------------------------------------------ construction helpers
     def _plane_op(self):
@@ -314,7 +319,7 @@ class LeggedRobotDTC:
         hd = self._host_draws or {}
         lag = hd.get("lag") or ([int(self.np_rng.integers(1, 5)) for _ in range(L.DECIMATION)] if self.host_rng else [0] * L.DECIMATION)
         arr = (C.c_int32 * 4)(*lag)
-        nstep, seed = self.common_step_counter + 1, self.seed
+        nstep, seed = self.common_step_counter + 1 - self._step_offset, self.seed
         gym, sim, uw = self.gym, self.sim, self._unwrap
         if getattr(gym, "static_dof_state", False):
             # stubbed simulator: the dof state does not move inside the decimation loop -> the four PD sub-steps in one launch
@@ -342,7 +347,7 @@ class LeggedRobotDTC:
         self.common_step_counter += 1
         nz = self._noise_struct()
         hd = self._host_draws or {}
-        step, seed = self.common_step_counter, self.seed
+        step, seed = self.common_step_counter - self._step_offset, self.seed
         B.check(lib.dtc_env_state_prep(self._h, step, seed, C.byref(nz), st), "dtc_env_state_prep")
         dbg = B.ptr(self._debug_score) if self._debug_score is not None else C.c_void_p(0)
         B.check(lib.dtc_foothold_step(self._h, self.foothold_variant, dbg, st), "dtc_foothold_step")
@@ -412,6 +417,37 @@ class LeggedRobotDTC:
         # hand the new state to the simulator (legged_robot.py:643-667)
         self.gym.set_actor_root_state_tensor(self.sim, self._unwrap(self.root_states))
         self.gym.set_dof_state_tensor(self.sim, self._unwrap(self.dof_state))
+
+    # ------------------------------------------------------------------ CUDA-graph capture of step() sequences
+    def graph_supported(self):
+        """step() can be captured when nothing in it depends on the host: device-side draws, no injected tables."""
+        return not self.host_rng and self._noise is None and self._host_draws is None and self._debug_score is None
+
+    def graph_capture_begin(self):
+        """Call before capturing a sequence of step() calls: from here on the launches carry steps relative to the device counter."""
+        self._step_offset = self.common_step_counter
+        self._step_base.fill_(self._step_offset)
+
+    def graph_capture_end(self, steps):
+        """Call as the LAST captured operation: the graph itself advances the device counter by the steps it contains."""
+        B.check(self.lib.dtc_counter_add(B.ptr(self._step_base), int(steps), B.stream_ptr(self.device)), "dtc_counter_add")
+        self._step_offset += int(steps)
+
+    def graph_replayed(self, steps):
+        """Host mirror of one replay of a captured `steps`-step sequence."""
+        self.common_step_counter += int(steps)
+        self._step_offset += int(steps)
+
+    def graph_before_replay(self):
+        """Simulator hook: whatever the captured refresh_*() calls read has to be in place before the replay is queued."""
+        f = getattr(self.gym, "graph_before_replay", None)
+        if f is not None:
+            f()
+
+    def graph_after_replay(self):
+        f = getattr(self.gym, "graph_after_replay", None)
+        if f is not None:
+            f()
 
     # The reference calls these three inside post_physics_step (legged_robot_dtc.py:205-213).  Here they are fused into
     # dtc_env_reward_reset / dtc_env_observe, so a call returns what the fused launch of the CURRENT step produced; a subclass

@@ -149,6 +149,8 @@ class ActorCriticDecoder:
         self.device = None
         self.seed = int(seed)
         self._calls = 0
+        self._calls_offset = 0      # CUDA-graph support: dtc_policy_act gets _calls - _calls_offset, the device adds _calls_base
+        self._calls_base = None
         self._inject = None  # tests: dict(eps_z=[M,16], eps_a=[M,12]) consumed by the next act()
         self.vae = _VaeView(self)
         self._out = None
@@ -255,6 +257,10 @@ class ActorCriticDecoder:
                     "dtc_learner_create")
         self._h, self._max_rows = h, rows
         self._stats_ptr = lib.dtc_learner_stats(h)
+        if self._calls_base is None:
+            self._calls_base = torch.zeros(1, device=self.device, dtype=torch.int64)
+        self._calls_base.fill_(self._calls_offset)
+        B.check(lib.dtc_learner_set_act_counter_base(h, B.ptr(self._calls_base)), "dtc_learner_set_act_counter_base")
         if steps is not None:
             lib.dtc_learner_set_adam_steps(h, steps[0], steps[1])
             self._stats_tensor().copy_(stats)
@@ -294,7 +300,7 @@ class ActorCriticDecoder:
         o = self._buffers(M) if need_copies or storage is None else None
         self._calls += 1
         args = [h, M, B.ptr(obs), obs.stride(0), B.ptr(hist), hist.stride(0), B.ptr(priv), priv.stride(0), B.ptr(base_vel),
-                base_vel.stride(0), B.ptr(ez), B.ptr(ea), self.seed, self._calls,
+                base_vel.stride(0), B.ptr(ez), B.ptr(ea), self.seed, self._calls - self._calls_offset,
                 C.byref(storage) if storage is not None else None, step]
         if o is not None:
             args += [B.ptr(o["actions"]), B.ptr(o["values"]), B.ptr(o["logp"]), B.ptr(o["mean"]), B.ptr(o["sigma"])]
@@ -302,6 +308,19 @@ class ActorCriticDecoder:
             args += [None] * 5
         B.check(B.lib().dtc_policy_act(*args, B.stream_ptr(self.device)), "dtc_policy_act")
         return o
+
+    # ------------------------------------------------------------------ CUDA-graph capture of act() sequences (see LeggedRobotDTC)
+    def graph_capture_begin(self):
+        self._calls_offset = self._calls
+        self._calls_base.fill_(self._calls_offset)
+
+    def graph_capture_end(self, calls):
+        B.check(B.lib().dtc_counter_add(B.ptr(self._calls_base), int(calls), B.stream_ptr(self.device)), "dtc_counter_add")
+        self._calls_offset += int(calls)
+
+    def graph_replayed(self, calls):
+        self._calls += int(calls)
+        self._calls_offset += int(calls)
 
     def act(self, observations, observation_history, privileged_observations, rew_buf=None, base_vel=None, **kwargs):
         if base_vel is None:

@@ -40,6 +40,10 @@ class OnPolicyRunner:
         self.tot_time = 0
         self.current_learning_iteration = 0
         self.last_perf = {}
+        # the rollout (T x {PPO.act, env.step, process_env_step}: ~28 launches per step) as ONE CUDA graph, captured after a first
+        # eager iteration and replayed from then on; used when nothing in the loop needs the host (no logging, device-side draws)
+        self.cuda_graph = bool(self.cfg.get("cuda_graph", True))
+        self._graph, self._graph_obs, self._graph_launches, self._eager_iters = None, None, 0, 0
         self.env.reset()
 
     def learn(self, num_learning_iterations, init_at_random_ep_len=False):
@@ -68,20 +72,25 @@ class OnPolicyRunner:
             start = time.time()
             rew_buf = self.env.get_reward_buf()
             with torch.inference_mode():
-                for i in range(T):
-                    actions = self.alg.act(obs, privileged_obs, obs_history, obs_dict["base_vel"], rew_buf)
-                    obs_dict, rewards, dones, infos = self.env.step(actions)
+                if self._use_graph():
+                    obs_dict = self._graph_rollout(obs_dict, rew_buf, T)
                     obs, privileged_obs, obs_history = obs_dict["obs"], obs_dict["privileged_obs"], obs_dict["obs_history"]
-                    self.alg.process_env_step(rewards, dones, next_obs=obs_dict["obs"], infos=infos)
-                    if self.log_dir is not None:
-                        if "episode" in infos:
-                            ep_infos.append(infos["episode"])
-                        cur_reward_sum += rewards
-                        cur_episode_length += 1
-                        d = dones > 0
-                        rec_rew[i], rec_len[i], rec_done[i] = cur_reward_sum, cur_episode_length, d
-                        cur_reward_sum.masked_fill_(d, 0)
-                        cur_episode_length.masked_fill_(d, 0)
+                else:
+                    self._eager_iters += 1
+                    for i in range(T):
+                        actions = self.alg.act(obs, privileged_obs, obs_history, obs_dict["base_vel"], rew_buf)
+                        obs_dict, rewards, dones, infos = self.env.step(actions)
+                        obs, privileged_obs, obs_history = obs_dict["obs"], obs_dict["privileged_obs"], obs_dict["obs_history"]
+                        self.alg.process_env_step(rewards, dones, next_obs=obs_dict["obs"], infos=infos)
+                        if self.log_dir is not None:
+                            if "episode" in infos:
+                                ep_infos.append(infos["episode"])
+                            cur_reward_sum += rewards
+                            cur_episode_length += 1
+                            d = dones > 0
+                            rec_rew[i], rec_len[i], rec_done[i] = cur_reward_sum, cur_episode_length, d
+                            cur_reward_sum.masked_fill_(d, 0)
+                            cur_episode_length.masked_fill_(d, 0)
                 stop = time.time()
                 collection_time = stop - start
                 start = stop
@@ -101,6 +110,58 @@ class OnPolicyRunner:
         self.current_learning_iteration += num_learning_iterations
         if self.log_dir is not None:
             self.save(os.path.join(self.log_dir, "model_{}.pt".format(self.current_learning_iteration)))
+
+    # ------------------------------------------------------------------ CUDA graph of the rollout
+    def _use_graph(self):
+        env, ac = self.env.env, self.alg.actor_critic
+        ok = (self.cuda_graph and self.log_dir is None and self._eager_iters >= 1 and getattr(env, "graph_supported", lambda: False)()
+              and ac._inject is None and self.alg._inject is None)
+        if not ok and self._graph is not None:
+            self._graph = None  # conditions changed (e.g. a test injected draws): fall back to eager launches for good
+            self.cuda_graph = False
+        return ok
+
+    def reset_graph(self):
+        """Drop the captured rollout (call after changing anything the capture baked in, e.g. where the simulator tensors come
+        from): the next iteration runs eagerly, the one after it captures again."""
+        self._graph, self._graph_obs, self._eager_iters = None, None, 0
+
+    def _graph_rollout(self, obs_dict, rew_buf, T):
+        from ... import _lib as B
+        env, ac, st = self.env.env, self.alg.actor_critic, self.alg.storage
+        gym = getattr(env, "gym", None)
+        if self._graph is None:
+            torch.cuda.synchronize(self.device)
+            env.graph_capture_begin()
+            ac.graph_capture_begin()
+            l0 = B.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                od = obs_dict
+                for i in range(T):
+                    if gym is not None and hasattr(gym, "graph_step"):
+                        gym.graph_step = (i, T)
+                    actions = self.alg.act(od["obs"], od["privileged_obs"], od["obs_history"], od["base_vel"], rew_buf)
+                    od, rewards, dones, infos = self.env.step(actions)
+                    self.alg.process_env_step(rewards, dones, next_obs=od["obs"], infos=infos)
+                env.graph_capture_end(T)
+                ac.graph_capture_end(T)
+            if gym is not None and hasattr(gym, "graph_step"):
+                gym.graph_step = None
+            self._graph, self._graph_obs, self._graph_launches = g, od, B.launch_count() - l0
+            # the capture pass advanced the host-side counters (storage step, common_step_counter, act calls) exactly as a real
+            # rollout does but launched nothing: the first replay does this iteration's work
+            env.graph_before_replay()
+            g.replay()
+        else:
+            env.graph_before_replay()
+            self._graph.replay()
+            B.lib().dtc_count_launches(self._graph_launches)
+            env.graph_replayed(T)
+            ac.graph_replayed(T)
+            st.step = T
+        env.graph_after_replay()
+        return self._graph_obs
 
     def log(self, locs, width=80, pad=35):
         self.tot_timesteps += self.num_steps_per_env * self.env.num_envs

@@ -263,6 +263,7 @@ class FakeGym:
         self.queue = []  # list of state dicts consumed FIFO
         self.source = None  # optional callable() -> state dict, used when the queue is empty
         self._pf = None     # host->device double buffering (enable_prefetch)
+        self.graph_step = None  # (t, T) while a T-step rollout is being captured into a CUDA graph (OnPolicyRunner)
 
     def load(self, st):
         self.root_states.copy_(st["root_states"], non_blocking=True)
@@ -297,14 +298,57 @@ class FakeGym:
 
     def _take_prefetched(self):
         pf = self._pf
+        cur = torch.cuda.current_stream(self.root_states.device)
+        if self.graph_step is not None:
+            # inside a CUDA-graph capture of a T-step rollout: step t moves ring[t] into the simulator tensors device-to-device;
+            # the ring itself is filled from pinned host memory OUTSIDE the graph, on the copy stream, while the previous
+            # iteration's update runs (graph_after_replay / graph_before_replay)
+            t, T = self.graph_step
+            if t == 0:
+                pf["ring"] = [{k: torch.empty_like(v) for k, v in self._tensors().items()} for _ in range(T)]
+                pf["ring_pending"] = False
+            for k, v in self._tensors().items():
+                v.copy_(pf["ring"][t][k], non_blocking=True)
+            return
         if not pf["staged"]:
             self._prefetch_next()
-        cur = torch.cuda.current_stream(self.root_states.device)
         cur.wait_event(pf["ready"])
         for k, v in self._tensors().items():
             v.copy_(pf["buf"][k], non_blocking=True)
         pf["free"].record(cur)
+        pf["staged"] = False
         self._prefetch_next()  # the next step's state starts flowing while this step's kernels run
+
+    def _upload_ring(self):
+        pf = self._pf
+        with torch.cuda.stream(pf["stream"]):
+            pf["stream"].wait_event(pf["free"])  # the replay that read the ring last has finished with it
+            for slot in pf["ring"]:
+                # a state an eager step prefetched before the capture is consumed first (queued earlier on this same stream)
+                st, pf["staged"] = (pf["buf"], False) if pf["staged"] else (self.source(), False)
+                for k, v in slot.items():
+                    v.copy_(st[k], non_blocking=True)
+            pf["ready"].record(pf["stream"])
+        pf["ring_pending"] = True
+
+    def graph_before_replay(self):
+        """Runner hook: the captured rollout is about to be replayed -> its T states must be in the ring."""
+        pf = self._pf
+        if pf is None or pf.get("ring") is None:
+            return
+        if not pf["ring_pending"]:
+            self._upload_ring()
+        torch.cuda.current_stream(self.root_states.device).wait_event(pf["ready"])
+        pf["ring_pending"] = False
+
+    def graph_after_replay(self):
+        """Runner hook: a replay has been queued -> start uploading the next rollout's states behind it (they travel over PCIe
+        while the update runs)."""
+        pf = self._pf
+        if pf is None or pf.get("ring") is None:
+            return
+        pf["free"].record(torch.cuda.current_stream(self.root_states.device))
+        self._upload_ring()
 
     # --- tensor API
     def acquire_actor_root_state_tensor(self, sim): return self.root_states

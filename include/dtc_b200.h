@@ -152,6 +152,14 @@ void dtc_env_destroy(dtc_env* e);
 int dtc_env_bind(dtc_env* e, const dtc_env_buffers* buf);
 /* call after writing height_samples in place (the reference never does after start-up) */
 int dtc_env_heightmap_updated(dtc_env* e);
+/* CUDA-graph support: launches captured into a graph carry baked arguments, but every environment launch needs the running
+ * common_step_counter (command resampling, pushes, Philox streams).  With a device-side counter set here, each environment kernel
+ * adds its value to the `common_step_counter` / `step` argument of the call, so a captured rollout passes the step RELATIVE to the
+ * counter and advances the counter with dtc_counter_add at the end of the graph.  NULL (default) = arguments are absolute.
+ * dtc_count_launches adds kernels launched by graph replays to dtc_launch_count(). */
+int dtc_env_set_step_base(dtc_env* e, const int64_t* device_counter);
+int dtc_counter_add(int64_t* device_counter, int64_t inc, void* stream);
+void dtc_count_launches(int64_t n);
 
 /* E1+E2: clip actions (first_substep == 0), PD torque of decimation sub-steps [first_substep, first_substep + num_substeps) with the
  * lag buffer (legged_robot.py:92-111,595-630).  The reference recomputes the torque from the refreshed dof state in every
@@ -241,6 +249,8 @@ int dtc_policy_act(dtc_learner* l, int32_t M, const float* obs, int32_t obs_ld, 
                    const float* eps_z, const float* eps_a, uint64_t seed, uint64_t counter,
                    const dtc_storage* s, int32_t step,
                    float* actions, float* values, float* logp, float* mean, float* sigma, void* stream);
+/* CUDA-graph support, as dtc_env_set_step_base: a device-side counter added to dtc_policy_act's `counter` argument (NULL = absolute). */
+int dtc_learner_set_act_counter_base(dtc_learner* l, const uint64_t* device_counter);
 /* P4 alone (ppo.py:170-171) */
 int dtc_policy_evaluate(dtc_learner* l, int32_t M, const float* obs, int32_t obs_ld, const float* priv, int32_t priv_ld,
                         const float* base_vel, int32_t bv_ld, float* values, void* stream);

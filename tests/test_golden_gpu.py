@@ -324,3 +324,64 @@ def test_save_load_resume_roundtrip(tmp_path, golden_dir):
     assert rb.current_learning_iteration == 3 and os.path.exists(os.path.join(rb.log_dir, "model_3.pt"))
     assert all(v == v for v in rb.alg.last_stats.values())
     assert float(rb.alg.optimizer.state_dict()["state"][0]["step"]) == float(oa["state"][0]["step"]) + 20
+
+
+def test_graph_rollout_equals_eager_rollout():
+    """The rollout captured into one CUDA graph (OnPolicyRunner: T x {PPO.act, env.step, process_env_step} with device-side step /
+    Philox counters) leaves bit-identical storage and environment state to the same iterations launched eagerly -- with the
+    simulator tensors coming from device memory, and from pinned host memory through the staging ring (bench.py's e2e leg)."""
+    from dtc_b200.legged_gym.envs import LeggedRobotDTC, Lite3DTCCfg, Lite3DTCCfgPPO
+    from dtc_b200.legged_gym.envs.lite3.lite3_dtc_config import class_to_dict
+    from dtc_b200.rsl_rl.runners import OnPolicyRunner
+    N = 256
+    hs, tor = sim_stub.make_heightmap("stones", 0)
+    layout = sim_stub.initial_env_layout(N, tor, 5)
+    g = torch.Generator().manual_seed(5)
+    host = [{k: v.pin_memory() for k, v in sim_stub.synth_state(N, layout[2], g).items()} for _ in range(8)]
+    # a flipped robot: resets and resampling happen inside the captured steps as well
+    host[3]["root_states"][1, 3:7] = torch.tensor([0.9, 0.0, 0.0, 0.435])
+    dev = [{k: v.to(DEV) for k, v in s.items()} for s in host]
+
+    def build(use_graph, pool, prefetch):
+        fg = sim_stub.FakeGym(N, device=DEV)
+        st = {"i": 0}
+
+        def source():
+            st["i"] = (st["i"] + 1) % 8  # 24 steps per iteration: every iteration sees the same sequence in every mode
+            return pool[st["i"]]
+
+        fg.source = source
+        cfg = Lite3DTCCfg()
+        cfg.env.num_envs = N
+        env = LeggedRobotDTC(cfg, sim_device=DEV, gym=fg, height_samples=hs, terrain_origins=tor, layout=layout, seed=5)
+        torch.manual_seed(7)
+        tc = class_to_dict(Lite3DTCCfgPPO())
+        tc["runner"]["cuda_graph"] = use_graph
+        r = OnPolicyRunner(env, tc, log_dir=None, device=DEV)
+        if prefetch:
+            fg.enable_prefetch(True)
+        r.env.env.episode_length_buf[5:9] = 980  # episodes about to time out
+        return r
+
+    runners = [build(False, dev, False), build(True, dev, False), build(True, host, True)]
+    ra = runners[0]
+    for it in range(4):  # iteration 0 eager everywhere, then the graph runners capture (1) and replay (2, 3)
+        for r in runners:
+            torch.manual_seed(100 + it)  # the minibatch permutation comes from torch's generator
+            r.learn(1)
+        for r in runners[1:]:
+            what = f"iteration {it}, {'host ring' if r is runners[2] else 'device pool'}"
+            assert (r._graph is not None) == (it >= 1)
+            ea, eb = ra.env.env, r.env.env
+            assert ea.common_step_counter == eb.common_step_counter and ra.alg.actor_critic._calls == r.alg.actor_critic._calls
+            for name in ("actions", "values", "rewards", "returns", "advantages", "hist", "priv_a", "xc", "dones"):
+                assert torch.equal(getattr(ra.alg.storage, name), getattr(r.alg.storage, name)), (what, name)
+            for name in ("obs_buf", "rew_buf", "episode_length_buf", "commands", "terrain_levels", "_episode_sums", "measured_heights"):
+                assert torch.equal(getattr(ea, name), getattr(eb, name)), (what, name)
+            # The UPDATE is not run-to-run deterministic (float atomics in the weight-gradient reductions; Adam then normalises that
+            # noise to +-lr on parameters whose gradient is zero, and the KL-adaptive learning rate can branch on it), with or
+            # without the graph -- so the parameters are re-synchronised and the claim checked here is the rollout's.
+            r.alg.actor_critic._flat.copy_(ra.alg.actor_critic._flat)
+            r.alg.actor_critic._params_written()
+    assert runners[1]._graph_launches > 24 * 20
+    assert int(ra.env.env.episode_length_buf.min()) < 24 * 4, "resets must have happened inside the captured rollouts"
