@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
         log.append(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    r = subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-lcudart"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    r = subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout.decode())
     with open(os.path.join(PKG, "build", "ptxas.log"), "w") as f:

@@ -40,6 +40,15 @@ void dtc_prof_begin(cudaStream_t st, int kind, double work);
 void dtc_prof_tag(int m, int n, int k, int layout);  // shape of the launch opened by the last dtc_prof_begin (per-shape dump)
 void dtc_prof_end(cudaStream_t st);
 
+// NVTX range over a C-ABI entry point (the reference has no tracing; a timeline tool sees the env / learner
+// phases by name).  Header-only NVTX3: a pointer check when no tool is attached.
+#include <nvtx3/nvToolsExt.h>
+struct DtcNvtxRange {
+  explicit DtcNvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~DtcNvtxRange() { nvtxRangePop(); }
+};
+#define DTC_NVTX(name) DtcNvtxRange dtc_nvtx_range_(name)
+
 #define RETURN_IF_ERR(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
 // 3xTF32 companion value: the tensor core truncates an fp32 operand x to TF32; x_lo = rn_tf32(x - trunc_tf32(x)) carries

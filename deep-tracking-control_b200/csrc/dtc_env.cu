@@ -628,6 +628,7 @@ extern "C" int dtc_env_heightmap_updated(dtc_env* e) {
 }
 extern "C" int dtc_env_pre_physics(dtc_env* e, const float* actions_in, const int32_t lag_choice[4], int32_t first_substep,
                                    int32_t num_substeps, int64_t step, uint64_t seed, void* stream) {
+  DTC_NVTX("dtc_env_pre_physics");
   if (!e || !e->bound) DTC_FAIL(DTC_ERR_STATE, "dtc_env_pre_physics: env not bound");
   if (first_substep < 0 || num_substeps < 1 || first_substep + num_substeps > 4)
     DTC_FAIL(DTC_ERR_ARG, "dtc_env_pre_physics: sub-steps [%d, %d) outside the decimation loop [0, 4)", first_substep, first_substep + num_substeps);
@@ -647,12 +648,14 @@ static dtc_env_noise noise_or_null(const dtc_env_noise* nz) {
   return nz ? *nz : z;
 }
 extern "C" int dtc_env_state_prep(dtc_env* e, int64_t step, uint64_t seed, const dtc_env_noise* noise, void* stream) {
+  DTC_NVTX("dtc_env_state_prep");
   if (!e || !e->bound) DTC_FAIL(DTC_ERR_STATE, "dtc_env_state_prep: env not bound");
   k_state_prep<<<ceil_div(e->cfg.num_envs, 128), 128, 0, (cudaStream_t)stream>>>(e->d_cfg, e->buf, step, seed, noise_or_null(noise), e->step_base);
   DTC_CHECK_LAUNCH("k_state_prep");
   return DTC_OK;
 }
 extern "C" int dtc_env_reward_reset(dtc_env* e, int64_t step, uint64_t seed, float reset_normal, const dtc_env_noise* noise, void* stream) {
+  DTC_NVTX("dtc_env_reward_reset");
   if (!e || !e->bound) DTC_FAIL(DTC_ERR_STATE, "dtc_env_reward_reset: env not bound");
   k_reward_reset<<<ceil_div(e->cfg.num_envs, 128), 128, 0, (cudaStream_t)stream>>>(e->d_cfg, e->buf, step, seed, reset_normal,
                                                                                  noise_or_null(noise), e->step_base);
@@ -660,6 +663,7 @@ extern "C" int dtc_env_reward_reset(dtc_env* e, int64_t step, uint64_t seed, flo
   return DTC_OK;
 }
 extern "C" int dtc_env_observe(dtc_env* e, int64_t step, uint64_t seed, const dtc_env_noise* noise, void* stream) {
+  DTC_NVTX("dtc_env_observe");
   if (!e || !e->bound) DTC_FAIL(DTC_ERR_STATE, "dtc_env_observe: env not bound");
   k_observe<<<ceil_div(e->cfg.num_envs, 4), 128, 0, (cudaStream_t)stream>>>(e->d_cfg, e->buf, step, seed, noise_or_null(noise), e->step_base);
   DTC_CHECK_LAUNCH("k_observe");

@@ -1447,6 +1447,7 @@ static int launch_v5(dtc_env* e, const V5Params& P, cudaStream_t st) {
 
 // ------------------------------------------------------------------ host side
 extern "C" int dtc_foothold_step(dtc_env* e, int variant, float* debug_score, void* stream) {
+  DTC_NVTX("dtc_foothold_step");
   if (!e || !e->bound) DTC_FAIL(DTC_ERR_STATE, "dtc_foothold_step: env not bound");
   cudaStream_t st = (cudaStream_t)stream;
   int N = e->cfg.num_envs;

@@ -414,6 +414,7 @@ int dtc_colsum_launch(const float* X, int ld, int M, int N, float* out, float* w
 
 extern "C" int dtc_linear_forward(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* W, int32_t ldw,
                                   const float* bias, int32_t act, float* C, int32_t ldc, void* stream) {
+  DTC_NVTX("dtc_linear_forward");
   GemmArgs g{};
   g.A = A; g.lda = lda; g.a_kc = true;
   g.B = W; g.ldb = ldw; g.b_kc = true;

@@ -80,6 +80,7 @@ extern "C" int64_t dtc_gru_param_floats(int32_t input_size, int32_t hidden_size,
 
 extern "C" int dtc_gru_forward(int32_t T, int32_t N, int32_t input_size, int32_t hidden_size, int32_t num_layers, const float* weights,
                                const float* x, float* h, float* out, void* stream) {
+  DTC_NVTX("dtc_gru_forward");
   if (!weights || !x || !h) DTC_FAIL(DTC_ERR_ARG, "dtc_gru_forward: null argument");
   if (T <= 0 || N <= 0 || num_layers <= 0) DTC_FAIL(DTC_ERR_ARG, "dtc_gru_forward: T, N, num_layers must be positive");
   if (input_size <= 0 || input_size > GRU_MAX_IN || hidden_size <= 0 || hidden_size > GRU_MAX_H)

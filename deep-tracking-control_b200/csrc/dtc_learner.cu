@@ -1165,6 +1165,7 @@ extern "C" int dtc_policy_act(dtc_learner* l, int32_t M, const float* obs, int32
                               const float* priv, int32_t priv_ld, const float* base_vel, int32_t bv_ld, const float* eps_z,
                               const float* eps_a, uint64_t seed, uint64_t counter, const dtc_storage* s, int32_t step,
                               float* actions, float* values, float* logp, float* mean, float* sigma, void* stream) {
+  DTC_NVTX("dtc_policy_act");
   if (!l || !obs || !hist || !priv || !base_vel) DTC_FAIL(DTC_ERR_ARG, "dtc_policy_act: null argument");
   if (M <= 0 || M > l->R) DTC_FAIL(DTC_ERR_ARG, "dtc_policy_act: M=%d outside (0,%d]", M, l->R);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1206,6 +1207,7 @@ extern "C" int dtc_policy_act(dtc_learner* l, int32_t M, const float* obs, int32
 
 extern "C" int dtc_policy_evaluate(dtc_learner* l, int32_t M, const float* obs, int32_t obs_ld, const float* priv, int32_t priv_ld,
                                    const float* base_vel, int32_t bv_ld, float* values, void* stream) {
+  DTC_NVTX("dtc_policy_evaluate");
   if (!l || !obs || !priv || !base_vel || !values) DTC_FAIL(DTC_ERR_ARG, "dtc_policy_evaluate: null argument");
   if (M <= 0 || M > l->R) DTC_FAIL(DTC_ERR_ARG, "dtc_policy_evaluate: M=%d outside (0,%d]", M, l->R);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1245,6 +1247,7 @@ __global__ void __launch_bounds__(256) k_teacher_gate(int M, const float* __rest
 }
 extern "C" int dtc_policy_act_teacher(dtc_learner* l, int32_t M, const float* obs, int32_t obs_ld, const float* hist,
                                       int32_t hist_ld, const float* priv, int32_t priv_ld, float* actions, void* stream) {
+  DTC_NVTX("dtc_policy_act_teacher");
   if (!l || !obs || !hist || !priv || !actions) DTC_FAIL(DTC_ERR_ARG, "dtc_policy_act_teacher: null argument");
   if (M <= 0 || M > l->R) DTC_FAIL(DTC_ERR_ARG, "dtc_policy_act_teacher: M=%d outside (0,%d]", M, l->R);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1276,6 +1279,7 @@ extern "C" int dtc_policy_act_teacher(dtc_learner* l, int32_t M, const float* ob
 
 extern "C" int dtc_store_transition(const dtc_storage* s, int32_t step, const float* rewards, const uint8_t* dones,
                                     const uint8_t* time_outs, const float* next_obs, int32_t next_obs_ld, float gamma, void* stream) {
+  DTC_NVTX("dtc_store_transition");
   RET_IF(check_storage(s, "dtc_store_transition"));
   if (step < 0 || step >= s->T) DTC_FAIL(DTC_ERR_STATE, "Rollout buffer overflow");
   if (!rewards || !dones || !next_obs) DTC_FAIL(DTC_ERR_ARG, "dtc_store_transition: null argument");
@@ -1287,6 +1291,7 @@ extern "C" int dtc_store_transition(const dtc_storage* s, int32_t step, const fl
 
 extern "C" int dtc_gae(const dtc_storage* s, const float* last_values, float gamma, float lam, double* scratch, int defer_normalize,
                        void* stream) {
+  DTC_NVTX("dtc_gae");
   RET_IF(check_storage(s, "dtc_gae"));
   if (!last_values || !scratch) DTC_FAIL(DTC_ERR_ARG, "dtc_gae: null argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1297,6 +1302,7 @@ extern "C" int dtc_gae(const dtc_storage* s, const float* last_values, float gam
   return DTC_OK;
 }
 extern "C" int dtc_gae_normalize(const dtc_storage* s, const double* stats3, void* stream) {
+  DTC_NVTX("dtc_gae_normalize");
   RET_IF(check_storage(s, "dtc_gae_normalize"));
   k_gae_normalize<<<grid1d((long long)s->T * s->N, 256), 256, 0, (cudaStream_t)stream>>>(*s, stats3);
   DTC_CHECK_LAUNCH("k_gae_normalize");
@@ -1304,6 +1310,7 @@ extern "C" int dtc_gae_normalize(const dtc_storage* s, const double* stats3, voi
 }
 
 extern "C" int dtc_gather_minibatch(const dtc_storage* src, const dtc_storage* dst, const int64_t* perm, int64_t rows, void* stream) {
+  DTC_NVTX("dtc_gather_minibatch");
   RET_IF(check_storage(src, "dtc_gather_minibatch(src)"));
   RET_IF(check_storage(dst, "dtc_gather_minibatch(dst)"));
   if (!perm || rows < 0 || rows > (int64_t)dst->T * dst->N) DTC_FAIL(DTC_ERR_ARG, "dtc_gather_minibatch: bad rows");
@@ -1337,6 +1344,7 @@ static int optimizer_apply(dtc_learner* l, int which, const dtc_ppo_hparams* hp,
 }
 extern "C" int dtc_optimizer_apply(dtc_learner* l, int which, const dtc_ppo_hparams* hp, float grad_scale, int32_t rows_global,
                                    void* stream) {
+  DTC_NVTX("dtc_optimizer_apply");
   if (!l || !hp || (which != 0 && which != 1)) DTC_FAIL(DTC_ERR_ARG, "dtc_optimizer_apply: bad arguments");
   if (!l->m_main || !l->v_main || !l->m_vae || !l->v_vae || !l->grads) DTC_FAIL(DTC_ERR_STATE, "learner was created without optimizer state");
   return optimizer_apply(l, which, hp, grad_scale, rows_global, (cudaStream_t)stream);
@@ -1353,6 +1361,7 @@ static int check_batch(dtc_learner* l, const dtc_storage* b, int64_t row0, int32
 
 extern "C" int dtc_vae_step(dtc_learner* l, const dtc_storage* batch, int64_t row0, int32_t M, const float* eps, uint64_t seed,
                             uint64_t counter, const dtc_ppo_hparams* hp, int sync_grads, void* stream) {
+  DTC_NVTX("dtc_vae_step");
   RET_IF(check_batch(l, batch, row0, M, "dtc_vae_step"));
   if (!hp) DTC_FAIL(DTC_ERR_ARG, "dtc_vae_step: null hparams");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1417,6 +1426,7 @@ extern "C" int dtc_vae_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
 
 extern "C" int dtc_ppo_step(dtc_learner* l, const dtc_storage* batch, int64_t row0, int32_t M, const float* eps, uint64_t seed,
                             uint64_t counter, const dtc_ppo_hparams* hp, int sync_grads, void* stream) {
+  DTC_NVTX("dtc_ppo_step");
   RET_IF(check_batch(l, batch, row0, M, "dtc_ppo_step"));
   if (!hp) DTC_FAIL(DTC_ERR_ARG, "dtc_ppo_step: null hparams");
   cudaStream_t st = (cudaStream_t)stream;

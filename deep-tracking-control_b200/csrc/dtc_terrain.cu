@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(32) k_terrain_origins(int cols, int border_px,
 extern "C" int dtc_terrain_rasterize(int32_t rows, int32_t cols, int32_t border_px, int32_t sub_px, int32_t n_rows, int32_t n_cols,
                                      const dtc_subterrain* subs, const int32_t* tables, double terrain_length, double vertical_scale,
                                      int16_t* height_samples, float* terrain_origins, void* stream) {
+  DTC_NVTX("dtc_terrain_rasterize");
   if (!subs || !tables || !height_samples) DTC_FAIL(DTC_ERR_ARG, "dtc_terrain_rasterize: null argument");
   if (rows <= 0 || cols <= 0 || sub_px < 20 || n_rows <= 0 || n_cols <= 0 || border_px < 0 || n_rows * sub_px + 2 * border_px > rows ||
       n_cols * sub_px + 2 * border_px > cols)
@@ -141,12 +142,17 @@ __global__ void __launch_bounds__(128) k_terrain_origins_win(int cols, int borde
 extern "C" int dtc_terrain_paint(int32_t rows, int32_t cols, int32_t border_px, int32_t len_px, int32_t wid_px, int32_t n_rows, int32_t n_cols,
                                  const dtc_subterrain* subs, const int32_t* rects, const int32_t origin_window[4], double terrain_length,
                                  double terrain_width, double vertical_scale, int16_t* height_samples, float* terrain_origins, void* stream) {
+  DTC_NVTX("dtc_terrain_paint");
   if (!subs || !height_samples) DTC_FAIL(DTC_ERR_ARG, "dtc_terrain_paint: null argument");
   if (rows <= 0 || cols <= 0 || len_px <= 0 || wid_px <= 0 || n_rows <= 0 || n_cols <= 0 || border_px < 0 || n_rows * len_px + 2 * border_px > rows ||
       n_cols * wid_px + 2 * border_px > cols)
     DTC_FAIL(DTC_ERR_ARG, "dtc_terrain_paint: %d x %d sub-terrains of %d x %d px + 2 x %d px border do not fit a %d x %d map", n_rows, n_cols,
              len_px, wid_px, border_px, rows, cols);
   cudaStream_t st = (cudaStream_t)stream;
+  // this library carries its own (static) CUDA runtime; when a launch is the first thing it is asked to do, the runtime initialises
+  // inside the launch path and compute-sanitizer reports the benign first-try cuKernelGetFunction error -> initialise it up front
+  static const cudaError_t runtime_ready = cudaFree(nullptr);
+  (void)runtime_ready;
   k_terrain_paint<<<148 * 8, 256, 0, st>>>(rows, cols, border_px, len_px, wid_px, n_rows, n_cols, subs, rects, height_samples);
   DTC_CHECK_LAUNCH("k_terrain_paint");
   if (terrain_origins) {

@@ -32,6 +32,15 @@ class Lite3DTCCfg:
         num_rows, num_cols = L.NUM_ROWS, L.NUM_COLS
         terrain_length = terrain_width = L.TERRAIN_LENGTH
         max_init_terrain_level = 5
+        static_friction = 1.0
+        dynamic_friction = 1.0
+        restitution = 0.0
+        num_height_points = L.GRID_X * L.GRID_Y
+        selected = False
+        terrain_kwargs = None
+        # terrain types: [smooth slope, rough slope, stairs up, stairs down, discrete, stepping stones, gap, pit] (terrain.py:79-141)
+        terrain_proportions = [0.0, 0.0, 0.2, 0.2, 0.2, 0.4]
+        slope_treshold = 0.75
 
     class commands:
         curriculum = False

@@ -19,6 +19,17 @@ from ..env.wrappers import HistoryWrapper
 from ..modules import ActorCriticDecoder
 
 
+def _nvtx_push(name):
+    """Timeline ranges around the three phases of an iteration (the C ABI adds one per entry point below them)."""
+    if torch.cuda.is_available():
+        torch.cuda.nvtx.range_push(name)
+
+
+def _nvtx_pop():
+    if torch.cuda.is_available():
+        torch.cuda.nvtx.range_pop()
+
+
 class OnPolicyRunner:
     def __init__(self, env, train_cfg, log_dir=None, device="cuda:0"):
         self.cfg = train_cfg["runner"]
@@ -72,6 +83,7 @@ class OnPolicyRunner:
             start = time.time()
             rew_buf = self.env.get_reward_buf()
             with torch.inference_mode():
+                _nvtx_push("rollout")
                 if self._use_graph():
                     obs_dict = self._graph_rollout(obs_dict, rew_buf, T)
                     obs, privileged_obs, obs_history = obs_dict["obs"], obs_dict["privileged_obs"], obs_dict["obs_history"]
@@ -91,12 +103,17 @@ class OnPolicyRunner:
                             rec_rew[i], rec_len[i], rec_done[i] = cur_reward_sum, cur_episode_length, d
                             cur_reward_sum.masked_fill_(d, 0)
                             cur_episode_length.masked_fill_(d, 0)
+                _nvtx_pop()
                 stop = time.time()
                 collection_time = stop - start
                 start = stop
+                _nvtx_push("compute_returns")
                 self.alg.compute_returns(obs, privileged_obs, obs_dict["base_vel"])
+                _nvtx_pop()
+            _nvtx_push("update")
             (mean_value_loss, mean_surrogate_loss, mean_adaptation_module_loss, mean_decoder_loss, mean_recons_loss, mean_vel_loss,
              mean_kld_loss) = self.alg.update()
+            _nvtx_pop()
             stop = time.time()
             learn_time = stop - start
             if self.log_dir is not None:

@@ -72,3 +72,24 @@ def test_reference_init_is_bit_identical_to_oracle():
     assert list(a) == list(b)
     for k in a:
         assert torch.equal(a[k], b[k]), k
+
+
+def test_nvtx_ranges_are_emitted(tmp_path):
+    """Every hot C-ABI entry point opens an NVTX range named after itself (dtc_common.cuh: DTC_NVTX).  No profiler in this image, so
+    a test-only injection library (tests/support/nvtx_inject.c, loaded by NVTX3 through NVTX_INJECTION64_PATH) records the names.
+    The calls below fail their argument checks (no GPU needed) -- the range is opened before them and closed on return."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    inj = tmp_path / "libnvtx_inject.so"
+    subprocess.run(["gcc", "-shared", "-fPIC", "-O1", "-I/usr/local/cuda/include", os.path.join(here, "support", "nvtx_inject.c"), "-o", str(inj)],
+                   check=True)
+    log = tmp_path / "nvtx.log"
+    code = ("import ctypes as C, dtc_b200\nfrom dtc_b200 import _lib as B\nlib = B.lib()\n"
+            "assert lib.dtc_env_state_prep(None, 0, 0, None, None) != 0\n"
+            "assert lib.dtc_foothold_step(None, 6, None, None) != 0\n"
+            "assert lib.dtc_env_observe(None, 0, 0, None, None) != 0\n")
+    env = dict(os.environ, NVTX_INJECTION64_PATH=str(inj), DTC_NVTX_LOG=str(log), PYTHONPATH=os.path.dirname(here))
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd=os.path.dirname(here))
+    lines = log.read_text().split("\n")
+    assert lines[:6] == ["push dtc_env_state_prep", "pop", "push dtc_foothold_step", "pop", "push dtc_env_observe", "pop"], lines
