@@ -17,7 +17,8 @@ struct GemmArgs {
   const float* B; int ldb; bool b_kc;  // b_kc: B(n,k) = B[n*ldb + k]   else B[k*ldb + n]
   float* C; int ldc;
   int M, N, K;        // logical extents.  Storage contract: every base pointer is 16-byte aligned and every leading
-                      // dimension is a multiple of 4 floats; tails inside a float4 are masked by the loaders.
+                      // dimension is a multiple of 4 floats; tails inside a float4 are masked by the loaders.  Columns
+                      // [N, round4(N)) of C are either left alone or (tensor-core path, ldc == round4(N)) set to zero.
   const float* bias;  // [N] for EPI_BIAS*
   const float* act_src; int ld_act;  // [M, ld_act] for EPI_D*
   int epi;

@@ -132,6 +132,217 @@ __device__ __forceinline__ float tc_epi(float v, int epi, float bias, float src)
 // correction accumulators summed in fp32) -> a 32x32 XOR-swizzled staging tile -> global, so that every global access is a
 // coalesced 128-byte row segment; the act'(x) operand of a chunk is fetched with eight independent loads before any of it is used.
 // The accumulator set is handed back to the MMA issuer (acc_empty: 8 arrivals per CTA) as soon as this warp's TMEM reads are done.
+// ---- TMA-store epilogue (default).  What paces these kernels on the learner's shapes is the LENGTH OF THE EPILOGUE'S INSTRUCTION
+// CHAIN, not bytes: ncu on the staged epilogue below shows ~800 dependent instructions per 32x32 chunk and warp (shared-memory
+// transpose, per-row address arithmetic, 16 predicated STG.128, a run-time switch per element) at ~16 cycles each with only two
+// epilogue warps per scheduler - 26 k cycles per 256x128 tile against 20.5 k cycles of MMAs at K = 512 (epilogue-bound: 178 of the
+// 232 TFLOP/s the same kernel reaches with its stores compiled out), and ~9 us of pure epilogue on the 64..256-wide layers whose
+// K loop is a few k-blocks.  Here every lane keeps its own row: bias / activation / derivative mask / fan-in accumulate are applied in
+// registers, the 32x32 chunk goes to shared memory once (128-byte rows, 16-byte pieces XOR-ed with row % 8 = the layout
+// CU_TENSOR_MAP_SWIZZLE_128B expects, conflict-free for the row-wise STS.128) and ONE cp.async.bulk.tensor store (UTMASTG) per chunk
+// and output moves it to global memory; the TMA unit clips ragged right / bottom edges.  ~3x fewer instructions per chunk.
+__device__ __forceinline__ void tc_tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)map), "r"(src), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tc_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tc_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// A warp owns NBUF staging chunks of 4 KB used round-robin, one TMA store per use: before a chunk is rewritten at most NBUF - 1 of the
+// lane-0 store groups may still be reading shared memory.
+template <int NBUF> __device__ __forceinline__ void tc_stg_acquire(int lane) {
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NBUF - 1) : "memory");
+  __syncwarp();
+}
+// the 32 values of this lane's row -> staging chunk (128-byte rows, 16-byte pieces XOR-ed with row % 8)
+__device__ __forceinline__ void tc_stage_rows(const float (&v)[32], float* stg, int lane) {
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4)
+    *reinterpret_cast<float4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2)) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+}
+__device__ __forceinline__ void tc_store_chunk(float* stg, int lane, bool issue, const CUtensorMap* map, bool is3d, int gn, int gm_box, int z) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA unit
+  __syncwarp();
+  if (lane == 0 && issue) {
+    if (is3d) tc_tma_store_3d(map, tc_smem_u32(stg), gn, gm_box, z);
+    else tc_tma_store_2d(map, tc_smem_u32(stg), gn, gm_box);
+  }
+  if (lane == 0) tc_bulk_commit();  // an (empty) group even when nothing was issued keeps the round-robin count in step
+}
+// A 32-row x 32-column block of a row-major global matrix, read COALESCED (lane -> 16-byte piece lane & 7 of rows (lane >> 3) + 4 i:
+// eight lanes cover one 128-byte row segment), for the epilogue's per-row arithmetic.  Rows >= M and pieces past round4(N) read as 0.
+struct TcAux { float4 r[8]; };
+__device__ __forceinline__ TcAux tc_aux_load(const float* base, int ld, int gm_box, int gn, int M, int n4, int lane) {
+  TcAux a;
+  const int cb = lane & 7, r0 = lane >> 3;
+  const bool col_ok = gn + 4 * cb < n4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = gm_box + r0 + 4 * i;
+    a.r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col_ok && gm < M) a.r[i] = __ldg(reinterpret_cast<const float4*>(base + (size_t)gm * ld + gn) + cb);
+  }
+  return a;
+}
+// coalesced registers -> staging chunk -> this lane's row (the chunk must have been acquired; it is free again on return)
+__device__ __forceinline__ void tc_aux_to_rows(const TcAux& a, float* stg, int lane, float (&out)[32]) {
+  const int cb = lane & 7, r0 = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + 4 * i;
+    *reinterpret_cast<float4*>(stg + r * 32 + ((cb ^ (r & 7)) << 2)) = a.r[i];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 t = *reinterpret_cast<const float4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2));
+    out[j4 * 4] = t.x; out[j4 * 4 + 1] = t.y; out[j4 * 4 + 2] = t.z; out[j4 * 4 + 3] = t.w;
+  }
+  __syncwarp();
+}
+// Waits for the tile's accumulator (acc_full) itself, so that the derivative-mask block of the first chunk is already in flight.
+template <int BN, int NBUF>
+__device__ __forceinline__ void tc_epilogue_tma(const TcParams& p, const CUtensorMap* mapC, const CUtensorMap* mapClo, uint32_t tmem, int buf,
+                                                int warp, int lane, int m0, int n0, int z, float* stg_base, int& stg_turn,
+                                                uint64_t* acc_full, uint32_t acc_full_parity, uint32_t acc_empty_addr, bool cluster_arrive) {
+  const int q = warp & 3, half = (warp - 4) >> 2;
+  const bool partial = p.splits > 1;
+  const int n4 = (p.N + 3) & ~3;
+  const int epi = partial ? EPI_STORE : p.epi;
+  const bool has_bias = epi >= EPI_BIAS && epi <= EPI_BIAS_ELU, has_src = epi == EPI_DRELU || epi == EPI_DELU;
+  const bool accum = !partial && p.accumulate;
+  const bool has_corr = p.has_alo || p.has_blo;
+  const bool want_lo = !partial && p.C_lo != nullptr;
+  const bool colsum = p.colsum_part && !partial;
+  int nchunks = (p.N - n0 + 31) / 32;  // live 32-column chunks of this tile
+  nchunks = nchunks > BN / 32 ? BN / 32 : nchunks;
+  const int ch_first = (BN / 64) * half;
+  const int ch_last = min(ch_first + BN / 64 - 1, nchunks - 1);  // last chunk this warp reads (< ch_first: none)
+  const int gm_box = m0 + q * 32, gm = gm_box + lane;
+  const bool row_ok = gm < p.M, box_ok = gm_box < p.M;
+  TcAux src;
+  if (has_src && ch_last >= ch_first) src = tc_aux_load(p.act_src, p.ld_act, gm_box, n0 + ch_first * 32, p.M, n4, lane);
+  tc_mbar_wait(acc_full, acc_full_parity);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (ch_last < ch_first) {  // nothing to read: release the accumulator set right away
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      if (cluster_arrive) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(acc_empty_addr) : "memory");
+      else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty_addr) : "memory");
+    }
+    return;
+  }
+#pragma unroll 1
+  for (int ch = ch_first; ch <= ch_last; ++ch) {
+    const int c0 = ch * 32, gn = n0 + c0;
+    float v[32];
+    {
+      uint32_t u[32], w[32];
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN + c0);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+          "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+            "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
+            "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
+            "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+          : "r"(taddr));
+      if (has_corr) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+            "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]), "=r"(w[9]),
+              "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]), "=r"(w[16]), "=r"(w[17]), "=r"(w[18]),
+              "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]), "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]),
+              "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
+            : "r"(taddr + BN));
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = has_corr ? __uint_as_float(u[i]) + __uint_as_float(w[i]) : __uint_as_float(u[i]);
+    }
+    if (ch == ch_last) {
+      // all TMEM reads of this warp are done: hand the accumulator set back to the MMA issuer
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        if (cluster_arrive) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(acc_empty_addr) : "memory");
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty_addr) : "memory");
+      }
+    }
+    if (p.debug & 1) continue;
+    float* stg = stg_base + (stg_turn % NBUF) * (32 * 32);
+    tc_stg_acquire<NBUF>(lane);  // `stg` is free from here until the store below is issued
+    // ---- epilogue function on this lane's row (columns gn .. gn + 31; pieces past round4(N) are clipped by the store)
+    if (has_bias) {
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const int col = gn + 4 * j4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col + 3 < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));  // same address on every lane: one broadcast
+        else {
+          if (col < p.N) b4.x = __ldg(p.bias + col);
+          if (col + 1 < p.N) b4.y = __ldg(p.bias + col + 1);
+          if (col + 2 < p.N) b4.z = __ldg(p.bias + col + 2);
+        }
+        v[j4 * 4] += b4.x; v[j4 * 4 + 1] += b4.y; v[j4 * 4 + 2] += b4.z; v[j4 * 4 + 3] += b4.w;
+      }
+      if (epi == EPI_BIAS_RELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : 0.f;
+      } else if (epi == EPI_BIAS_ELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
+      }
+    } else if (has_src) {
+      float sv[32];
+      tc_aux_to_rows(src, stg, lane, sv);
+      if (ch < ch_last) src = tc_aux_load(p.act_src, p.ld_act, gm_box, gn + 32, p.M, n4, lane);  // next chunk's block: in flight under this one
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float sx = sv[i], x = v[i];
+        v[i] = epi == EPI_DRELU ? (sx > 0.f ? x : 0.f) : (sx > 0.f ? x : x * (sx + 1.0f));
+      }
+    }
+    if (accum) {
+      float ov[32];
+      const TcAux old = tc_aux_load(p.C, p.ldc, gm_box, gn, p.M, n4, lane);
+      tc_aux_to_rows(old, stg, lane, ov);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += ov[i];
+    }
+    if (colsum && !row_ok) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    }
+    tc_stage_rows(v, stg, lane);
+    tc_store_chunk(stg, lane, box_ok, mapC, partial, gn, gm_box, z);
+    ++stg_turn;
+    if (colsum) {
+      // column sums of the 32 staged rows, lane = column: piece (lane >> 2) ^ (r & 7) of row r - 32 distinct banks per read.  The
+      // TMA unit may be reading the chunk at the same time; nothing writes it before the next acquire.
+      float cs = 0.f;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) cs += stg[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
+      if (box_ok && gn + lane < n4) p.colsum_part[(size_t)(gm_box >> 5) * n4 + gn + lane] = cs;
+    }
+    if (want_lo) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = tf32_lo(v[i]);
+      stg = stg_base + (stg_turn % NBUF) * (32 * 32);
+      tc_stg_acquire<NBUF>(lane);
+      tc_stage_rows(v, stg, lane);
+      tc_store_chunk(stg, lane, box_ok, mapClo, false, gn, gm_box, 0);
+      ++stg_turn;
+    }
+  }
+}
+
 template <int BN>
 __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tmem, int buf, int warp, int lane, int m0, int n0, int z,
                                                  float* stg, uint32_t acc_empty_addr, bool cluster_arrive) {
@@ -344,7 +555,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
 template <int AMAJ, int BMAJ>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapB,
-          const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
+          const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapC,
+           const __grid_constant__ CUtensorMap mapClo, const TcParams p) {
   extern __shared__ uint8_t tc_smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_base_s;
@@ -446,13 +658,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue: 8 warps, TMEM -> registers -> smem -> global
     float* const stg = reinterpret_cast<float*>(tc_smem_raw + (smem0 - tc_smem_u32(tc_smem_raw)) + TC_STAGES * TC_STAGE_BYTES) + (warp - 4) * (32 * 32);
-    int j = 0;
+    int j = 0, stg_turn = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
       const int n0 = (t % nt_n) * TC_BN, m0 = ((t / nt_n) % nt_m) * TC_BM, z = t / (nt_n * nt_m);
       const int buf = j & 1;
-      tc_mbar_wait(&bar_acc_full[buf], (j >> 1) & 1);
-      tc_epilogue_tile<TC_BN>(p, tmem, buf, warp, lane, m0, n0, z, stg, tc_smem_u32(&bar_acc_empty[buf]), false);
+      if (p.direct == 2) {
+        tc_epilogue_tma<TC_BN, 1>(p, &mapC, &mapClo, tmem, buf, warp, lane, m0, n0, z, stg, stg_turn, &bar_acc_full[buf], (j >> 1) & 1,
+                                  tc_smem_u32(&bar_acc_empty[buf]), false);
+      } else {
+        tc_mbar_wait(&bar_acc_full[buf], (j >> 1) & 1);
+        tc_epilogue_tile<TC_BN>(p, tmem, buf, warp, lane, m0, n0, z, stg, tc_smem_u32(&bar_acc_empty[buf]), false);
+      }
     }
+    if (p.direct == 2 && lane == 0) tc_bulk_wait_read();  // the staging chunks must outlive the last stores' reads
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -472,10 +690,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 //   * acc_empty[b] lives in the leader: 8 arrivals (4 epilogue warps x 2 CTAs, the peer's through mapa);
 //   * each CTA drains its own 128 TMEM lanes with the same epilogue as above.
 #define TC2_STAGES 4
+#define TC2_STG_BUFS 1                     // staging chunks per epilogue warp (TMA-store epilogue: C and C_lo stores in flight together)
 #define TC2_A_BYTES TC_TILE_BYTES          // 128 rows x 32 k fp32
 #define TC2_B_BYTES (TC_TILE_BYTES / 2)    // 64 rows x 32 k fp32
 #define TC2_STAGE_BYTES (2 * TC2_A_BYTES + 2 * TC2_B_BYTES)
-#define TC2_SMEM_BYTES (TC2_STAGES * TC2_STAGE_BYTES + TC_STG_BYTES + 1024)
+#define TC2_SMEM_BYTES (TC2_STAGES * TC2_STAGE_BYTES + TC2_STG_BUFS * TC_STG_BYTES + 1024)
 
 __device__ __forceinline__ uint32_t tc_cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t tc_mapa(uint32_t saddr, uint32_t rank) {
@@ -502,7 +721,8 @@ __device__ __forceinline__ void tc2_commit(uint64_t* bar) {
 template <int AMAJ, int BMAJ>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapB,
-           const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
+           const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapC,
+           const __grid_constant__ CUtensorMap mapClo, const TcParams p) {
   extern __shared__ uint8_t tc_smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[TC2_STAGES], bar_empty[TC2_STAGES], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_base_s;
@@ -611,14 +831,20 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue: this CTA's 128 rows, 8 warps
-    float* const stg = reinterpret_cast<float*>(tc_smem_raw + (smem0 - tc_smem_u32(tc_smem_raw)) + TC2_STAGES * TC2_STAGE_BYTES) + (warp - 4) * (32 * 32);
-    int j = 0;
+    float* const stg = reinterpret_cast<float*>(tc_smem_raw + (smem0 - tc_smem_u32(tc_smem_raw)) + TC2_STAGES * TC2_STAGE_BYTES) + (warp - 4) * (TC2_STG_BUFS * 32 * 32);
+    int j = 0, stg_turn = 0;
     for (int t = pair; t < ntiles; t += npairs, ++j) {
       const int n0 = (t % nt_n) * TC_BN, m0 = ((t / nt_n) % nt_m) * (2 * TC_BM) + (int)rank * TC_BM, z = t / (nt_n * nt_m);
       const int buf = j & 1;
-      tc_mbar_wait(&bar_acc_full[buf], (j >> 1) & 1);
-      tc_epilogue_tile<TC_BN>(p, tmem, buf, warp, lane, m0, n0, z, stg, tc_mapa(tc_smem_u32(&bar_acc_empty[buf]), 0), true);
+      if (p.direct == 2) {
+        tc_epilogue_tma<TC_BN, TC2_STG_BUFS>(p, &mapC, &mapClo, tmem, buf, warp, lane, m0, n0, z, stg, stg_turn, &bar_acc_full[buf], (j >> 1) & 1,
+                                             tc_mapa(tc_smem_u32(&bar_acc_empty[buf]), 0), true);
+      } else {
+        tc_mbar_wait(&bar_acc_full[buf], (j >> 1) & 1);
+        tc_epilogue_tile<TC_BN>(p, tmem, buf, warp, lane, m0, n0, z, stg, tc_mapa(tc_smem_u32(&bar_acc_empty[buf]), 0), true);
+      }
     }
+    if (p.direct == 2 && lane == 0) tc_bulk_wait_read();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -650,7 +876,8 @@ __device__ __forceinline__ int tc3_n_eff(const TcParams& p, int n0) {
 template <int AMAJ, int BMAJ>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc3(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapB,
-           const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
+           const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapC,
+           const __grid_constant__ CUtensorMap mapClo, const TcParams p) {
   extern __shared__ uint8_t tc_smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[TC3_STAGES], bar_empty[TC3_STAGES], bar_acc_full, bar_acc_empty;
   __shared__ uint32_t tmem_base_s;
@@ -756,12 +983,18 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue: this CTA's 128 rows x 256 columns, 8 warps
     float* const stg = reinterpret_cast<float*>(tc_smem_raw + (smem0 - tc_smem_u32(tc_smem_raw)) + TC3_STAGES * TC3_STAGE_BYTES) + (warp - 4) * (32 * 32);
-    int j = 0;
+    int j = 0, stg_turn = 0;
     for (int t = pair; t < ntiles; t += npairs, ++j) {
       const int n0 = (t % nt_n) * TC3_BN, m0 = ((t / nt_n) % nt_m) * (2 * TC_BM) + (int)rank * TC_BM, z = t / (nt_n * nt_m);
-      tc_mbar_wait(&bar_acc_full, j & 1);
-      tc_epilogue_tile<TC3_BN>(p, tmem, 0, warp, lane, m0, n0, z, stg, tc_mapa(tc_smem_u32(&bar_acc_empty), 0), true);
+      if (p.direct == 2) {
+        tc_epilogue_tma<TC3_BN, 1>(p, &mapC, &mapClo, tmem, 0, warp, lane, m0, n0, z, stg, stg_turn, &bar_acc_full, j & 1,
+                                   tc_mapa(tc_smem_u32(&bar_acc_empty), 0), true);
+      } else {
+        tc_mbar_wait(&bar_acc_full, j & 1);
+        tc_epilogue_tile<TC3_BN>(p, tmem, 0, warp, lane, m0, n0, z, stg, tc_mapa(tc_smem_u32(&bar_acc_empty), 0), true);
+      }
     }
+    if (p.direct == 2 && lane == 0) tc_bulk_wait_read();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -815,6 +1048,32 @@ static int tc_get_map(const float* base, int rows, int k, int ld, int maj, CUten
   return DTC_OK;
 }
 
+// output of the TMA-store epilogue: box 32 columns x 32 rows, SWIZZLE_128B.  planes == 0: C[rows][ld] with `cols` live columns (the
+// unit clips the ragged edges); planes > 0: the split-K workspace [planes][rows][cols] as a 3-D tensor (a box never crosses a plane)
+static int tc_get_out_map(const float* base, int rows, int cols, int ld, int planes, CUtensorMap* out) {
+  MapKey key{base, rows, cols, planes > 0 ? planes : ld, planes > 0 ? 4 : 3};
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return DTC_OK; }
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    DTC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) DTC_FAIL(DTC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    g_encode = (PFN_tc_encode)fn;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(planes > 0 ? planes : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)(planes > 0 ? cols : ld) * sizeof(float), (cuuint64_t)rows * cols * sizeof(float)};
+  cuuint32_t box[3] = {32, 32, 1}, es[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, planes > 0 ? 3 : 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) DTC_FAIL(DTC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for output [%d x %d] ld %d planes %d", (int)r, rows, cols, ld, planes);
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps.emplace(key, m);
+  *out = m;
+  return DTC_OK;
+}
+
 bool dtc_gemm_tc_eligible(const GemmArgs& a) {
   // N down to 32 pays off even though the tile pads it to 128: the 35..64-wide CENet layers run 2-3x faster than on the SIMT path
   if (a.M < 64 || a.N < 32 || a.K < 8) return false;
@@ -842,7 +1101,7 @@ static int tc_pdl_on() {
 }
 template <typename K>
 static int tc_launch_pdl(K kernel, dim3 grid, int smem, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB,
-                         const CUtensorMap& mBlo, const TcParams& p) {
+                         const CUtensorMap& mBlo, const CUtensorMap& mC, const CUtensorMap& mClo, const TcParams& p) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -850,30 +1109,32 @@ static int tc_launch_pdl(K kernel, dim3 grid, int smem, cudaStream_t st, const C
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = tc_pdl_on() ? 1 : 0;
-  DTC_CUDA(cudaLaunchKernelEx(&cfg, kernel, mA, mAlo, mB, mBlo, p));
+  DTC_CUDA(cudaLaunchKernelEx(&cfg, kernel, mA, mAlo, mB, mBlo, mC, mClo, p));
   return DTC_OK;
 }
 
 template <int AMAJ, int BMAJ>
-static int tc2_launch_t(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB, const CUtensorMap& mBlo, const TcParams& p,
+static int tc2_launch_t(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB, const CUtensorMap& mBlo, const CUtensorMap& mC,
+                        const CUtensorMap& mClo, const TcParams& p,
                         dim3 grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     DTC_CUDA(cudaFuncSetAttribute(k_gemm_tc2<AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
     attr_set = true;
   }
-  return tc_launch_pdl(k_gemm_tc2<AMAJ, BMAJ>, grid, TC2_SMEM_BYTES, st, mA, mAlo, mB, mBlo, p);
+  return tc_launch_pdl(k_gemm_tc2<AMAJ, BMAJ>, grid, TC2_SMEM_BYTES, st, mA, mAlo, mB, mBlo, mC, mClo, p);
 }
 
 template <int AMAJ, int BMAJ>
-static int tc3_launch_t(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB, const CUtensorMap& mBlo, const TcParams& p,
+static int tc3_launch_t(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB, const CUtensorMap& mBlo, const CUtensorMap& mC,
+                        const CUtensorMap& mClo, const TcParams& p,
                         dim3 grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     DTC_CUDA(cudaFuncSetAttribute(k_gemm_tc3<AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
     attr_set = true;
   }
-  return tc_launch_pdl(k_gemm_tc3<AMAJ, BMAJ>, grid, TC3_SMEM_BYTES, st, mA, mAlo, mB, mBlo, p);
+  return tc_launch_pdl(k_gemm_tc3<AMAJ, BMAJ>, grid, TC3_SMEM_BYTES, st, mA, mAlo, mB, mBlo, mC, mClo, p);
 }
 // 256-column pair tiles: OFF by default (env DTC_GEMM_TC3=1 enables).  The kernel is correct (bit-identical to the other two:
 // tests/test_learner_gpu.py::test_gemm_cta_pair_matches_single runs it when enabled) but slower on every learner shape
@@ -890,14 +1151,15 @@ bool dtc_gemm_tc3_shape(int M, int N, int splits, int pairs) {
 }
 
 template <int AMAJ, int BMAJ>
-static int tc_launch_t(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB, const CUtensorMap& mBlo, const TcParams& p,
+static int tc_launch_t(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB, const CUtensorMap& mBlo, const CUtensorMap& mC,
+                        const CUtensorMap& mClo, const TcParams& p,
                        dim3 grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     DTC_CUDA(cudaFuncSetAttribute(k_gemm_tc<AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set = true;
   }
-  return tc_launch_pdl(k_gemm_tc<AMAJ, BMAJ>, grid, TC_SMEM_BYTES, st, mA, mAlo, mB, mBlo, p);
+  return tc_launch_pdl(k_gemm_tc<AMAJ, BMAJ>, grid, TC_SMEM_BYTES, st, mA, mAlo, mB, mBlo, mC, mClo, p);
 }
 
 void k_splitk_reduce_launch(const float* ws, float* C, float* C_lo, int M, int N, int ldc, int splits, int accumulate, cudaStream_t st);
@@ -922,7 +1184,8 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   // epilogue variant: "staged" (default) or "direct".  Measured (gpurun_out/r2o): direct wins on dgrad / narrow shapes alone (256x512
   // dgrad 124 -> 148 TFLOP/s, 128x256 60 -> 77) but loses on the forward shapes (512x693 184 -> 169) and costs 6 ms per training
   // iteration (88.5 -> 94.5 ms): its half-sector writes load the L2 write path that the step already saturates.
-  { static int direct = -1; if (direct < 0) { const char* e = getenv("DTC_TC_EPI"); direct = (e && e[0] == 'd') ? 1 : 0; } p.direct = direct; }
+  // DTC_TC_EPI = tma (default: registers -> one shared-memory chunk -> cp.async.bulk.tensor store, see tc_epilogue_tma) | staged | direct
+  { static int direct = -1; if (direct < 0) { const char* e = getenv("DTC_TC_EPI"); direct = !e ? 2 : e[0] == 'd' ? 1 : e[0] == 's' ? 0 : 2; } p.direct = direct; }
   { static int neff = -1; if (neff < 0) { const char* e = getenv("DTC_TC_NEFF"); neff = e ? atoi(e) : 1; } p.neff = neff; }  // DTC_TC_NEFF=0: always 128-column MMAs
   const int amaj = a.a_kc ? 0 : 1, bmaj = a.b_kc ? 0 : 1;
   static int num_sms = 0;
@@ -939,6 +1202,18 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   RETURN_IF_ERR(tc_get_map(a.B, a.N, a.K, a.ldb, bmap, &mB));
   if (a.A_lo) RETURN_IF_ERR(tc_get_map(a.A_lo, a.M, a.K, a.lda, amaj, &mAlo)); else mAlo = mA;
   if (a.B_lo) RETURN_IF_ERR(tc_get_map(a.B_lo, a.N, a.K, a.ldb, bmap, &mBlo)); else mBlo = mB;
+  CUtensorMap mC = mA, mClo = mA;
+  // the TMA unit clips a store at 16-byte granularity: with N % 4 != 0 it writes zeros into the columns up to round4(N).  Harmless when
+  // those are this matrix's own padding (ldc == round4(N)); a narrower view into a wider buffer keeps the element-exact staged epilogue
+  if (p.direct == 2 && (a.N & 3) && splits == 1 && a.ldc != ((a.N + 3) & ~3)) p.direct = 0;
+  if (p.direct == 2) {
+    const int n4 = (a.N + 3) & ~3;
+    if (splits > 1) RETURN_IF_ERR(tc_get_out_map(a.ws, a.M, n4, n4, splits, &mC));
+    else {
+      RETURN_IF_ERR(tc_get_out_map(a.C, a.M, a.N, a.ldc, 0, &mC));
+      if (a.C_lo) RETURN_IF_ERR(tc_get_out_map(a.C_lo, a.M, a.N, a.ldc, 0, &mClo));
+    }
+  }
   const int ntiles = use_tc3 ? ceil_div(a.N, TC3_BN) * ceil_div(a.M, 2 * TC_BM) * splits
                              : use_pair ? pair_tiles : ceil_div(a.N, TC_BN) * ceil_div(a.M, TC_BM) * splits;
   // persistent grid: the tile list takes R = ceil(tiles / units) rounds whatever happens, so launch only ceil(tiles / R) units -
@@ -951,18 +1226,18 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   dtc_prof_tag(a.M, a.N, a.K, (use_tc3 ? 20 : use_pair ? 10 : 0) + amaj * 2 + bmaj + 1000 * splits);
   int rc;
   if (use_tc3) {
-    if (amaj == 0 && bmaj == 0) rc = tc3_launch_t<0, 0>(mA, mAlo, mB, mBlo, p, grid, st);
-    else if (amaj == 0 && bmaj == 1) rc = tc3_launch_t<0, 1>(mA, mAlo, mB, mBlo, p, grid, st);
-    else if (amaj == 1 && bmaj == 1) rc = tc3_launch_t<1, 1>(mA, mAlo, mB, mBlo, p, grid, st);
+    if (amaj == 0 && bmaj == 0) rc = tc3_launch_t<0, 0>(mA, mAlo, mB, mBlo, mC, mClo, p, grid, st);
+    else if (amaj == 0 && bmaj == 1) rc = tc3_launch_t<0, 1>(mA, mAlo, mB, mBlo, mC, mClo, p, grid, st);
+    else if (amaj == 1 && bmaj == 1) rc = tc3_launch_t<1, 1>(mA, mAlo, mB, mBlo, mC, mClo, p, grid, st);
     else DTC_FAIL(DTC_ERR_ARG, "gemm_tc: unsupported operand layout");
   } else if (use_pair) {
-    if (amaj == 0 && bmaj == 0) rc = tc2_launch_t<0, 0>(mA, mAlo, mB, mBlo, p, grid, st);
-    else if (amaj == 0 && bmaj == 1) rc = tc2_launch_t<0, 1>(mA, mAlo, mB, mBlo, p, grid, st);
-    else if (amaj == 1 && bmaj == 1) rc = tc2_launch_t<1, 1>(mA, mAlo, mB, mBlo, p, grid, st);
+    if (amaj == 0 && bmaj == 0) rc = tc2_launch_t<0, 0>(mA, mAlo, mB, mBlo, mC, mClo, p, grid, st);
+    else if (amaj == 0 && bmaj == 1) rc = tc2_launch_t<0, 1>(mA, mAlo, mB, mBlo, mC, mClo, p, grid, st);
+    else if (amaj == 1 && bmaj == 1) rc = tc2_launch_t<1, 1>(mA, mAlo, mB, mBlo, mC, mClo, p, grid, st);
     else DTC_FAIL(DTC_ERR_ARG, "gemm_tc: unsupported operand layout");
-  } else if (amaj == 0 && bmaj == 0) rc = tc_launch_t<0, 0>(mA, mAlo, mB, mBlo, p, grid, st);
-  else if (amaj == 0 && bmaj == 1) rc = tc_launch_t<0, 1>(mA, mAlo, mB, mBlo, p, grid, st);
-  else if (amaj == 1 && bmaj == 1) rc = tc_launch_t<1, 1>(mA, mAlo, mB, mBlo, p, grid, st);
+  } else if (amaj == 0 && bmaj == 0) rc = tc_launch_t<0, 0>(mA, mAlo, mB, mBlo, mC, mClo, p, grid, st);
+  else if (amaj == 0 && bmaj == 1) rc = tc_launch_t<0, 1>(mA, mAlo, mB, mBlo, mC, mClo, p, grid, st);
+  else if (amaj == 1 && bmaj == 1) rc = tc_launch_t<1, 1>(mA, mAlo, mB, mBlo, mC, mClo, p, grid, st);
   else DTC_FAIL(DTC_ERR_ARG, "gemm_tc: unsupported operand layout");
   if (rc) return rc;
   DTC_CHECK_LAUNCH("k_gemm_tc");
