@@ -29,6 +29,8 @@ struct GemmArgs {
   // 3xTF32 companions (dtc_gemm_tc.cu): x_lo = rn_tf32(x - trunc_tf32(x)).  A_lo / B_lo feed the tensor-core path (NULL = that
   // correction term is skipped); C_lo, when set, receives the companion of the result from either path's epilogue.
   const float* A_lo; const float* B_lo; float* C_lo;
+  // a_split / b_split: that operand has no companion array; the tensor-core kernels compute its companion tile in shared memory
+  bool a_split, b_split;
   // tensor-core path only, splits == 1: when set, the epilogue also writes the column sums of every 32-row block of the final C
   // to colsum_part[ceil(M/32)][round4(N)] (the bias gradient of the layer below a dgrad, without re-reading C from HBM)
   float* colsum_part;

@@ -30,7 +30,7 @@
 #define TC_TILE_BYTES (128 * 32 * 4)
 #define TC_STAGE_BYTES (4 * TC_TILE_BYTES)
 #define TC_STG_BYTES (8 * 32 * 32 * 4)  // epilogue staging: 8 warps x 32 rows x 32 floats (XOR-swizzled)
-#define TC_THREADS 384              // warp 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..11 epilogue
+#define TC_THREADS 512              // warp 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..11 epilogue, 12..15 operand splitters
 #define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + TC_STG_BYTES + 1024)
 
 struct TcParams {
@@ -41,6 +41,7 @@ struct TcParams {
   float* ws;
   float* colsum_part;  // [ceil(M/32)][round4(N)] column sums per 32-row block of the final output, or NULL
   int splits, has_alo, has_blo;
+  int split_a, split_b;  // 1: that operand's TF32 companion tile is computed in shared memory by the splitter warps (no *_lo array in HBM)
   int neff;   // 1: the MMA of a ragged / narrow n-tile covers only the live columns rounded up to the instruction granularity
   int direct; // epilogue variant: 1 = registers -> global without the shared-memory transpose (env DTC_TC_EPI=direct|staged)
   int debug;  // timing experiments only (env DTC_TC_DEBUG): 1 = epilogue skips its stores, 2 = producer stops loading after the first ring fill
@@ -90,6 +91,11 @@ __device__ __forceinline__ bool tc_elect_one() {
 }
 // descriptor halves: the low word carries the start address (and LBO), the high word is constant per operand layout, so the
 // per-k8 / per-stage descriptor update is one 32-bit add
+// Warp-specialised register budget: the kernels run 512 threads (128 registers each at launch); the control warpgroup (TMA producer, MMA
+// issuer, TMEM allocator) and the splitter warpgroup hand registers back, the two epilogue warpgroups - which hold a 32x32 fp32 chunk plus
+// its correction / mask block per warp - take them: 128 x 64 + 128 x 64 + 256 x 184 = 63 488 <= 65 536.
+#define TC_REG_DEC() asm volatile("setmaxnreg.dec.sync.aligned.u32 64;")
+#define TC_REG_INC() asm volatile("setmaxnreg.inc.sync.aligned.u32 184;")
 template <int MAJ> __device__ __forceinline__ uint32_t tc_desc_hi() {
   return MAJ == 0 ? (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29)) : (uint32_t)((512u >> 4) | (1u << 14) | (1u << 29));
 }
@@ -549,6 +555,20 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
   }
 }
 
+// ---- in-SM operand split.  The 3xTF32 companion x_lo = rn_tf32(x - trunc_tf32(x)) of an ACTIVATION operand used to live in HBM
+// next to x: every producer wrote 8 bytes per element and every consumer pulled 8 bytes per element through L2 and TMA - a third of a
+// forward GEMM's operand stream and half of its stores, on kernels whose stores queue behind a 190 KB-deep TMA load pipeline.  With
+// split_a / split_b the TMA loads only x; warps 12..15 turn each landed tile into its companion tile in shared memory (element-wise,
+// so the same byte offset whatever the swizzle / major-ness), fence the generic-proxy writes for the tensor core's async-proxy reads
+// and arrive on split[s], which the MMA issuer waits on instead of full[s].
+__device__ __forceinline__ void tc_split_tile(const uint8_t* src, uint8_t* dst, int n16, int tid) {
+#pragma unroll 4
+  for (int i = tid; i < n16; i += 128) {
+    const float4 x = *reinterpret_cast<const float4*>(src + (size_t)i * 16);
+    *reinterpret_cast<float4*>(dst + (size_t)i * 16) = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+  }
+}
+
 // Persistent kernel: one CTA per SM walks the (split, m-tile, n-tile) list with stride gridDim.x.  TMEM holds two
 // accumulator sets (main | correction, 2 x 128 columns each), so the epilogue of tile j overlaps the MMAs of tile j+1; the TMA
 // producer runs ahead across tile boundaries.
@@ -558,7 +578,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
           const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapC,
            const __grid_constant__ CUtensorMap mapClo, const TcParams p) {
   extern __shared__ uint8_t tc_smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_acc_full[2], bar_acc_empty[2];
+  __shared__ __align__(8) uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_split[TC_STAGES], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   const uint32_t smem0 = (tc_smem_u32(tc_smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -567,7 +587,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   tc_launch_dependents();
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(&bar_full[s], 1); tc_mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(&bar_full[s], 1); tc_mbar_init(&bar_empty[s], 1); tc_mbar_init(&bar_split[s], 4); }
     for (int s = 0; s < 2; ++s) { tc_mbar_init(&bar_acc_full[s], 1); tc_mbar_init(&bar_acc_empty[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -583,10 +603,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   // results are visible from here on
   tc_grid_dependency_wait();
 
+  if (warp < 4) {
+  TC_REG_DEC();
   if (warp == 0) {
    if (tc_elect_one()) {
     // ------------------------------------------------------------ TMA producer
-    const uint32_t bytes = TC_TILE_BYTES * (2 + p.has_alo + p.has_blo);
+    const uint32_t bytes = TC_TILE_BYTES * (2 + (p.has_alo && !p.split_a) + (p.has_blo && !p.split_b));
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const int n0 = (t % nt_n) * TC_BN, m0 = ((t / nt_n) % nt_m) * TC_BM, z = t / (nt_n * nt_m);
@@ -598,22 +620,22 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const uint32_t st = smem0 + s * TC_STAGE_BYTES;
         if (AMAJ == 0) {
           tc_tma_2d(st, &mapA, &bar_full[s], kb * TC_BK, m0);
-          if (p.has_alo) tc_tma_2d(st + TC_TILE_BYTES, &mapAlo, &bar_full[s], kb * TC_BK, m0);
+          if (p.has_alo && !p.split_a) tc_tma_2d(st + TC_TILE_BYTES, &mapAlo, &bar_full[s], kb * TC_BK, m0);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             tc_tma_2d(st + j * 4096, &mapA, &bar_full[s], m0 + 32 * j, kb * TC_BK);
-            if (p.has_alo) tc_tma_2d(st + TC_TILE_BYTES + j * 4096, &mapAlo, &bar_full[s], m0 + 32 * j, kb * TC_BK);
+            if (p.has_alo && !p.split_a) tc_tma_2d(st + TC_TILE_BYTES + j * 4096, &mapAlo, &bar_full[s], m0 + 32 * j, kb * TC_BK);
           }
         }
         if (BMAJ == 0) {
           tc_tma_2d(st + 2 * TC_TILE_BYTES, &mapB, &bar_full[s], kb * TC_BK, n0);
-          if (p.has_blo) tc_tma_2d(st + 3 * TC_TILE_BYTES, &mapBlo, &bar_full[s], kb * TC_BK, n0);
+          if (p.has_blo && !p.split_b) tc_tma_2d(st + 3 * TC_TILE_BYTES, &mapBlo, &bar_full[s], kb * TC_BK, n0);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             tc_tma_2d(st + 2 * TC_TILE_BYTES + j * 4096, &mapB, &bar_full[s], n0 + 32 * j, kb * TC_BK);
-            if (p.has_blo) tc_tma_2d(st + 3 * TC_TILE_BYTES + j * 4096, &mapBlo, &bar_full[s], n0 + 32 * j, kb * TC_BK);
+            if (p.has_blo && !p.split_b) tc_tma_2d(st + 3 * TC_TILE_BYTES + j * 4096, &mapBlo, &bar_full[s], n0 + 32 * j, kb * TC_BK);
           }
         }
       }
@@ -636,7 +658,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       const uint32_t d_main = tmem + (uint32_t)buf * (2 * TC_BN), d_corr = d_main + TC_BN;
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % TC_STAGES;
-        tc_mbar_wait(&bar_full[s], (it / TC_STAGES) & 1);
+        tc_mbar_wait((p.split_a | p.split_b) ? &bar_split[s] : &bar_full[s], (it / TC_STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = smem0 + s * TC_STAGE_BYTES;
         const uint32_t a0 = tc_desc_lo<AMAJ>(st), al0 = tc_desc_lo<AMAJ>(st + TC_TILE_BYTES);
@@ -655,7 +677,31 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       tc_commit(&bar_acc_full[buf]);  // accumulator set complete
     }
    }
-  } else if (warp >= 4) {
+  }
+  } else if (warp >= 12) {
+    TC_REG_DEC();
+    // ------------------------------------------------------------ operand splitters (4 warps), see tc_split_tile
+    if (p.split_a | p.split_b) {
+      uint8_t* const base = tc_smem_raw + (smem0 - tc_smem_u32(tc_smem_raw));
+      const int tid = threadIdx.x - 384;
+      int it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int z = t / (nt_n * nt_m);
+        const int kb0 = z * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % TC_STAGES;
+          tc_mbar_wait(&bar_full[s], (it / TC_STAGES) & 1);
+          uint8_t* const st = base + (size_t)s * TC_STAGE_BYTES;
+          if (p.split_a) tc_split_tile(st, st + TC_TILE_BYTES, TC_TILE_BYTES / 16, tid);
+          if (p.split_b) tc_split_tile(st + 2 * TC_TILE_BYTES, st + 3 * TC_TILE_BYTES, TC_TILE_BYTES / 16, tid);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&bar_split[s])) : "memory");
+        }
+      }
+    }
+  } else {
+    TC_REG_INC();
     // ------------------------------------------------------------ epilogue: 8 warps, TMEM -> registers -> smem -> global
     float* const stg = reinterpret_cast<float*>(tc_smem_raw + (smem0 - tc_smem_u32(tc_smem_raw)) + TC_STAGES * TC_STAGE_BYTES) + (warp - 4) * (32 * 32);
     int j = 0, stg_turn = 0;
@@ -724,7 +770,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
            const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapC,
            const __grid_constant__ CUtensorMap mapClo, const TcParams p) {
   extern __shared__ uint8_t tc_smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[TC2_STAGES], bar_empty[TC2_STAGES], bar_acc_full[2], bar_acc_empty[2];
+  __shared__ __align__(8) uint64_t bar_full[TC2_STAGES], bar_empty[TC2_STAGES], bar_split[TC2_STAGES], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   const uint32_t smem0 = (tc_smem_u32(tc_smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -735,7 +781,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
   tc_launch_dependents();
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC2_STAGES; ++s) { tc_mbar_init(&bar_full[s], 1); tc_mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < TC2_STAGES; ++s) { tc_mbar_init(&bar_full[s], 1); tc_mbar_init(&bar_empty[s], 1); tc_mbar_init(&bar_split[s], 8); }
     for (int s = 0; s < 2; ++s) { tc_mbar_init(&bar_acc_full[s], 1); tc_mbar_init(&bar_acc_empty[s], 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -750,10 +796,14 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
   const uint32_t tmem = tmem_base_s;
   tc_grid_dependency_wait();  // programmatic dependent launch (see k_gemm_tc)
 
+  if (warp < 4) {
+  TC_REG_DEC();
   if (warp == 0) {
    if (tc_elect_one()) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
-    const uint32_t bytes_cta = (uint32_t)(TC2_A_BYTES * (1 + p.has_alo) + TC2_B_BYTES * (1 + p.has_blo));
+    const bool split = (p.split_a | p.split_b) != 0;  // then each CTA's tiles complete on its OWN full[s] (its splitters wait there)
+    const bool load_alo = p.has_alo && !p.split_a, load_blo = p.has_blo && !p.split_b;
+    const uint32_t bytes_cta = (uint32_t)(TC2_A_BYTES * (1 + load_alo) + TC2_B_BYTES * (1 + load_blo));
     int it = 0;
     for (int t = pair; t < ntiles; t += npairs) {
       const int nt0 = (t % nt_n) * TC_BN;
@@ -763,32 +813,33 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % TC2_STAGES;
         tc_mbar_wait(&bar_empty[s], ((it / TC2_STAGES) & 1) ^ 1);
-        const uint32_t full = tc_mapa(tc_smem_u32(&bar_full[s]), 0);  // the leader's barrier
+        const uint32_t full = split ? tc_smem_u32(&bar_full[s]) : tc_mapa(tc_smem_u32(&bar_full[s]), 0);  // own / the leader's barrier
         if ((p.debug & 2) && it >= TC2_STAGES) {
           if (rank == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&bar_full[s])) : "memory");
           continue;
         }
-        if (rank == 0) tc_mbar_expect_tx(&bar_full[s], 2 * bytes_cta);
+        if (split) tc_mbar_expect_tx(&bar_full[s], bytes_cta);
+        else if (rank == 0) tc_mbar_expect_tx(&bar_full[s], 2 * bytes_cta);
         const uint32_t st = smem0 + s * TC2_STAGE_BYTES;
         const uint32_t sA = st, sAlo = st + TC2_A_BYTES, sB = st + 2 * TC2_A_BYTES, sBlo = sB + TC2_B_BYTES;
         if (AMAJ == 0) {
           tc2_tma_2d(sA, &mapA, full, kb * TC_BK, m0);
-          if (p.has_alo) tc2_tma_2d(sAlo, &mapAlo, full, kb * TC_BK, m0);
+          if (load_alo) tc2_tma_2d(sAlo, &mapAlo, full, kb * TC_BK, m0);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             tc2_tma_2d(sA + j * 4096, &mapA, full, m0 + 32 * j, kb * TC_BK);
-            if (p.has_alo) tc2_tma_2d(sAlo + j * 4096, &mapAlo, full, m0 + 32 * j, kb * TC_BK);
+            if (load_alo) tc2_tma_2d(sAlo + j * 4096, &mapAlo, full, m0 + 32 * j, kb * TC_BK);
           }
         }
         if (BMAJ == 0) {
           tc2_tma_2d(sB, &mapB, full, kb * TC_BK, n0);
-          if (p.has_blo) tc2_tma_2d(sBlo, &mapBlo, full, kb * TC_BK, n0);
+          if (load_blo) tc2_tma_2d(sBlo, &mapBlo, full, kb * TC_BK, n0);
         } else {
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             tc2_tma_2d(sB + j * 4096, &mapB, full, n0 + 32 * j, kb * TC_BK);
-            if (p.has_blo) tc2_tma_2d(sBlo + j * 4096, &mapBlo, full, n0 + 32 * j, kb * TC_BK);
+            if (load_blo) tc2_tma_2d(sBlo + j * 4096, &mapBlo, full, n0 + 32 * j, kb * TC_BK);
           }
         }
       }
@@ -810,7 +861,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       const uint32_t d_main = tmem + (uint32_t)buf * (2 * TC_BN), d_corr = d_main + TC_BN;
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % TC2_STAGES;
-        tc_mbar_wait(&bar_full[s], (it / TC2_STAGES) & 1);
+        tc_mbar_wait((p.split_a | p.split_b) ? &bar_split[s] : &bar_full[s], (it / TC2_STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = smem0 + s * TC2_STAGE_BYTES;
         const uint32_t sA = st, sAlo = st + TC2_A_BYTES, sB = st + 2 * TC2_A_BYTES, sBlo = sB + TC2_B_BYTES;
@@ -829,7 +880,33 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       tc2_commit(&bar_acc_full[buf]);  // accumulator set complete, both CTAs
     }
    }
-  } else if (warp >= 4) {
+  }
+  } else if (warp >= 12) {
+    TC_REG_DEC();
+    // ------------------------------------------------------------ operand splitters: this CTA's tiles, 4 warps; 8 arrivals (both CTAs)
+    // on the leader's split[s]
+    if (p.split_a | p.split_b) {
+      uint8_t* const base = tc_smem_raw + (smem0 - tc_smem_u32(tc_smem_raw));
+      const int tid = threadIdx.x - 384;
+      int it = 0;
+      for (int t = pair; t < ntiles; t += npairs) {
+        const int z = t / (nt_n * nt_m);
+        const int kb0 = z * p.kb_per_split, kb1 = min(p.nkb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % TC2_STAGES;
+          tc_mbar_wait(&bar_full[s], (it / TC2_STAGES) & 1);
+          uint8_t* const st = base + (size_t)s * TC2_STAGE_BYTES;
+          if (p.split_a && !(p.debug & 4)) tc_split_tile(st, st + TC2_A_BYTES, TC2_A_BYTES / 16, tid);
+          if (p.split_b && !(p.debug & 4)) tc_split_tile(st + 2 * TC2_A_BYTES, st + 2 * TC2_A_BYTES + TC2_B_BYTES, TC2_B_BYTES / 16, tid);
+          if (!(p.debug & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0)
+            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tc_mapa(tc_smem_u32(&bar_split[s]), 0)) : "memory");
+        }
+      }
+    }
+  } else {
+    TC_REG_INC();
     // ------------------------------------------------------------ epilogue: this CTA's 128 rows, 8 warps
     float* const stg = reinterpret_cast<float*>(tc_smem_raw + (smem0 - tc_smem_u32(tc_smem_raw)) + TC2_STAGES * TC2_STAGE_BYTES) + (warp - 4) * (TC2_STG_BUFS * 32 * 32);
     int j = 0, stg_turn = 0;
@@ -906,6 +983,8 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
   const uint32_t tmem = tmem_base_s;
   tc_grid_dependency_wait();
 
+  if (warp < 4) {
+  TC_REG_DEC();
   if (warp == 0) {
    if (tc_elect_one()) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -980,7 +1059,11 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       tc2_commit(&bar_acc_full);
     }
    }
-  } else if (warp >= 4) {
+  }
+  } else if (warp >= 12) {
+    TC_REG_DEC();
+  } else {
+    TC_REG_INC();
     // ------------------------------------------------------------ epilogue: this CTA's 128 rows x 256 columns, 8 warps
     float* const stg = reinterpret_cast<float*>(tc_smem_raw + (smem0 - tc_smem_u32(tc_smem_raw)) + TC3_STAGES * TC3_STAGE_BYTES) + (warp - 4) * (32 * 32);
     int j = 0, stg_turn = 0;
@@ -1077,7 +1160,7 @@ static int tc_get_out_map(const float* base, int rows, int cols, int ld, int pla
 bool dtc_gemm_tc_eligible(const GemmArgs& a) {
   // N down to 32 pays off even though the tile pads it to 128: the 35..64-wide CENet layers run 2-3x faster than on the SIMT path
   if (a.M < 64 || a.N < 32 || a.K < 8) return false;
-  if (!a.A_lo || !a.B_lo) return false;  // fp32-grade results need both companions; otherwise the FP32 SIMT path runs
+  if (!(a.A_lo || a.a_split) || !(a.B_lo || a.b_split)) return false;  // fp32-grade results need both companions; otherwise the FP32 SIMT path runs
   if (a.a_kc != true && a.b_kc == true) return false;  // (MN-major A, K-major B) is not used by the learner
   return true;
 }
@@ -1179,13 +1262,16 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   p.bias = a.bias; p.act_src = a.act_src; p.ld_act = a.ld_act; p.epi = a.epi; p.accumulate = a.accumulate ? 1 : 0;
   p.ws = a.ws;
   p.colsum_part = (splits == 1) ? a.colsum_part : nullptr;
-  p.has_alo = a.A_lo ? 1 : 0; p.has_blo = a.B_lo ? 1 : 0;
+  p.split_a = a.a_split ? 1 : 0; p.split_b = a.b_split ? 1 : 0;
+  p.has_alo = (a.A_lo || a.a_split) ? 1 : 0; p.has_blo = (a.B_lo || a.b_split) ? 1 : 0;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DTC_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
   // epilogue variant: "staged" (default) or "direct".  Measured (gpurun_out/r2o): direct wins on dgrad / narrow shapes alone (256x512
   // dgrad 124 -> 148 TFLOP/s, 128x256 60 -> 77) but loses on the forward shapes (512x693 184 -> 169) and costs 6 ms per training
   // iteration (88.5 -> 94.5 ms): its half-sector writes load the L2 write path that the step already saturates.
   // DTC_TC_EPI = tma (default: registers -> one shared-memory chunk -> cp.async.bulk.tensor store, see tc_epilogue_tma) | staged | direct
   { static int direct = -1; if (direct < 0) { const char* e = getenv("DTC_TC_EPI"); direct = !e ? 2 : e[0] == 'd' ? 1 : e[0] == 's' ? 0 : 2; } p.direct = direct; }
+  // Measured in the training step (gpurun_out/r2q, ms per iteration / in-step TFLOP/s of the pair kernel): tma 86.7 / 138.7, staged
+  // 95.8 / 117.1, tma for forward + staged for the mask / fan-in epilogues 88.4 / 127.7.
   { static int neff = -1; if (neff < 0) { const char* e = getenv("DTC_TC_NEFF"); neff = e ? atoi(e) : 1; } p.neff = neff; }  // DTC_TC_NEFF=0: always 128-column MMAs
   const int amaj = a.a_kc ? 0 : 1, bmaj = a.b_kc ? 0 : 1;
   static int num_sms = 0;
@@ -1195,13 +1281,13 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   static int pair_min = -1;  // fewest pair tiles worth a cluster launch (env DTC_GEMM_PAIR_MIN, default: one per SM pair)
   if (pair_min < 0) { const char* e = getenv("DTC_GEMM_PAIR_MIN"); pair_min = e ? atoi(e) : num_sms / 2; }
   const bool use_pair = tc_pair_mode() && a.M > TC_BM && pair_tiles >= pair_min;
-  const bool use_tc3 = use_pair && dtc_gemm_tc3_shape(a.M, a.N, splits, pair_min);
+  const bool use_tc3 = use_pair && !a.a_split && !a.b_split && dtc_gemm_tc3_shape(a.M, a.N, splits, pair_min);
   const int bmap = (use_pair && !use_tc3 && bmaj == 0) ? 2 : bmaj;  // tc2 stages 64 B rows per CTA, tc3 128
   CUtensorMap mA, mAlo, mB, mBlo;
   RETURN_IF_ERR(tc_get_map(a.A, a.M, a.K, a.lda, amaj, &mA));
   RETURN_IF_ERR(tc_get_map(a.B, a.N, a.K, a.ldb, bmap, &mB));
-  if (a.A_lo) RETURN_IF_ERR(tc_get_map(a.A_lo, a.M, a.K, a.lda, amaj, &mAlo)); else mAlo = mA;
-  if (a.B_lo) RETURN_IF_ERR(tc_get_map(a.B_lo, a.N, a.K, a.ldb, bmap, &mBlo)); else mBlo = mB;
+  if (a.A_lo && !a.a_split) RETURN_IF_ERR(tc_get_map(a.A_lo, a.M, a.K, a.lda, amaj, &mAlo)); else mAlo = mA;
+  if (a.B_lo && !a.b_split) RETURN_IF_ERR(tc_get_map(a.B_lo, a.N, a.K, a.ldb, bmap, &mBlo)); else mBlo = mB;
   CUtensorMap mC = mA, mClo = mA;
   // the TMA unit clips a store at 16-byte granularity: with N % 4 != 0 it writes zeros into the columns up to round4(N).  Harmless when
   // those are this matrix's own padding (ldc == round4(N)); a narrower view into a wider buffer keeps the element-exact staged epilogue

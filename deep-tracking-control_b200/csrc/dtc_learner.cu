@@ -199,8 +199,19 @@ struct dtc_learner {
   const uint64_t* act_counter_base;  // optional device-side counter added to dtc_policy_act's Philox counter (CUDA-graph replays)
 };
 
+// Where the TF32 companions of ACTIVATIONS come from: 1 (default) = computed tile by tile in shared memory by the GEMM kernels'
+// splitter warps (dtc_gemm_tc.cu: tc_split_tile) - no activation *_lo array is written or read; 0 (env DTC_TC_SPLIT=0) = round 1's
+// layout, every activation buffer has a companion array in HBM filled by its producer.  Parameters keep their companion array
+// (refreshed by the optimizer kernel) either way.
+static int g_split_sm = -1;
+static bool split_sm() {
+  if (g_split_sm < 0) { const char* e = getenv("DTC_TC_SPLIT"); g_split_sm = (e && e[0] == '1') ? 1 : 0; }
+  return g_split_sm != 0;
+}
 static const float* lo_of(const dtc_learner* l, const float* p) {
   if (!p) return nullptr;
+  if (p >= l->params && p < l->params + g_total) return l->params_lo + (p - l->params);
+  if (split_sm()) return nullptr;
   if (p >= l->ws_val_begin && p < l->ws_val_end) return p + l->lo_shift;
   if (p >= l->params && p < l->params + g_total) return l->params_lo + (p - l->params);
   for (int i = 0; i < 3; ++i)
@@ -400,6 +411,7 @@ static int fwd(dtc_learner* l, int id, const float* A, int lda, float* C, int ld
   g.B = l->params + L.w; g.ldb = L.ld; g.b_kc = true;
   g.C = C; g.ldc = ldc; g.M = M; g.N = L.out; g.K = L.in;
   g.A_lo = lo_of(l, A); g.B_lo = lo_of(l, g.B); g.C_lo = need_lo ? lo_of(l, C) : nullptr;
+  g.a_split = split_sm();
   g.bias = l->params + L.b;
   g.epi = act == 1 ? EPI_BIAS_RELU : act == 2 ? EPI_BIAS_ELU : EPI_BIAS;
   g.splits = 1;
@@ -412,6 +424,7 @@ static int wgrad(dtc_learner* l, int id, const float* dY, int ldy, const float* 
   g.A = dY; g.lda = ldy; g.a_kc = false;
   g.B = X; g.ldb = ldx; g.b_kc = false;
   g.A_lo = lo_of(l, dY); g.B_lo = lo_of(l, X);
+  g.a_split = g.b_split = split_sm();
   g.C = l->grads + L.w; g.ldc = L.ld; g.M = L.out; g.N = L.in; g.K = M;
   g.epi = EPI_STORE;
   g.splits = dtc_gemm_pick_splits(L.out, L.in, M);
@@ -430,6 +443,7 @@ static int dgrad(dtc_learner* l, int id, const float* dY, int ldy, float* dX, in
   g.A = dY; g.lda = ldy; g.a_kc = true;
   g.B = l->params + L.w; g.ldb = L.ld; g.b_kc = false;
   g.A_lo = lo_of(l, dY); g.B_lo = lo_of(l, g.B); g.C_lo = lo_of(l, dX);
+  g.a_split = split_sm();
   g.C = dX; g.ldc = lddx; g.M = M; g.N = ncols; g.K = L.out;
   g.act_src = act_src; g.ld_act = ld_act; g.epi = epi; g.accumulate = accumulate;
   g.splits = 1;
@@ -1318,6 +1332,7 @@ extern "C" int dtc_gather_minibatch(const dtc_storage* src, const dtc_storage* d
   k_gather<<<grid1d(rows * 32, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(*src, *dst, perm, rows);
   DTC_CHECK_LAUNCH("k_gather");
   cudaStream_t st = (cudaStream_t)stream;
+  if (split_sm()) return DTC_OK;
   RET_IF(split_lo(dst->hist, dst->hist_lo, rows * LD_HIST, st));
   RET_IF(split_lo(dst->priv_a, dst->priv_a_lo, rows * LD_PRIVA, st));
   return split_lo(dst->xc, dst->xc_lo, rows * LD_XC, st);
@@ -1496,6 +1511,10 @@ extern "C" int dtc_gemm_debug(int32_t M, int32_t N, int32_t K, const float* A, c
   g.C = C; g.C_lo = C_lo; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
   g.epi = EPI_STORE; g.splits = splits; g.ws = ws;
   const int saved = dtc_gemm_mode();
+  if (mode == 2) {  // tensor cores, operands' companions computed in shared memory (A_lo / B_lo ignored)
+    g.A_lo = g.B_lo = nullptr; g.a_split = g.b_split = true;
+    mode = 1;
+  }
   dtc_gemm_set_mode(mode);
   int rc = dtc_gemm_launch(g, (cudaStream_t)stream);
   dtc_gemm_set_mode(saved);

@@ -310,7 +310,8 @@ int dtc_learner_debug_buffer(dtc_learner* l, const char* name, float** ptr, int3
 int dtc_linear_forward(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* W, int32_t ldw,
                        const float* bias, int32_t act /*0 none,1 relu,2 elu*/, float* C, int32_t ldc, void* stream);
 /* general form used by the learner: C = A op B with either operand k-contiguous (1) or k-strided (0); tests and
- * microbenchmarks.  mode 0 = FP32 SIMT, 1 = tcgen05 3xTF32 (A_lo / B_lo = companions x - trunc_tf32(x), may be NULL). */
+ * microbenchmarks.  mode 0 = FP32 SIMT, 1 = tcgen05 3xTF32 (A_lo / B_lo = companions x - trunc_tf32(x), may be NULL),
+ * 2 = tcgen05 3xTF32 with both companions computed tile by tile in shared memory (A_lo / B_lo ignored): the learner's default. */
 int dtc_gemm_debug(int32_t M, int32_t N, int32_t K, const float* A, const float* A_lo, int32_t lda, int32_t a_kc, const float* B,
                    const float* B_lo, int32_t ldb, int32_t b_kc, float* C, float* C_lo, int32_t ldc, int32_t splits, float* ws,
                    int32_t mode, void* stream);

@@ -65,11 +65,12 @@ def _gemm(lib, mode, M, N, K, A, a_kc, Bm, b_kc, Cd, splits=1, ws=None, C_lo=Non
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("M,N,K", [(4096, 512, 693), (300, 35, 64), (1000, 12, 128), (777, 693, 512), (64, 1, 128), (130, 588, 512),
                                    (256, 128, 265), (5000, 256, 12), (24576, 512, 693), (10000, 693, 512), (19000, 256, 512)])
 def test_gemm_forward_and_dgrad(M, N, K, mode):
-    """mode 0: FP32 SIMT kernels; mode 1: tcgen05 3xTF32 (shapes too small for a tile fall back to SIMT inside the launcher)."""
+    """mode 0: FP32 SIMT kernels; mode 1: tcgen05 3xTF32 with companion arrays; mode 2: tcgen05 3xTF32, companions computed in shared
+    memory by the splitter warps (shapes too small for a tile fall back to SIMT inside the launcher)."""
     lib = B.lib()
     g = torch.Generator().manual_seed(M + N + K)
     r4 = lambda x: (x + 3) // 4 * 4
@@ -100,7 +101,7 @@ def test_gemm_forward_and_dgrad(M, N, K, mode):
     _close(Cd[:, :K], dY[:, :N].double() @ W[:, :K].double(), f"dgrad mode{mode}")
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("M,N,K", [(512, 693, 24576), (35, 64, 4096), (12, 128, 3000), (1, 128, 2500), (53, 128, 999), (693, 512, 6144),
                                    (128, 268, 1000), (256, 588, 777), (512, 693, 1026), (512, 512, 1026), (256, 512, 1026)])
 def test_gemm_wgrad_splitk(M, N, K, mode):

@@ -26,8 +26,9 @@ def main():
             Al, Wl = lo(A), lo(W)
             t = bench(lambda: lib.dtc_gemm_debug(M, N, K, B.ptr(A), B.ptr(Al), A.shape[1], 1, B.ptr(W), B.ptr(Wl), W.shape[1], 1, B.ptr(Cc), B.ptr(Cl), Cc.shape[1], 1, None, 1, st))
             t2 = bench(lambda: lib.dtc_gemm_debug(M, N, K, B.ptr(A), B.ptr(Al), A.shape[1], 1, B.ptr(W), B.ptr(Wl), W.shape[1], 1, B.ptr(Cc), None, Cc.shape[1], 1, None, 1, st))
+            t3 = bench(lambda: lib.dtc_gemm_debug(M, N, K, B.ptr(A), None, A.shape[1], 1, B.ptr(W), None, W.shape[1], 1, B.ptr(Cc), None, Cc.shape[1], 1, None, 2, st))
             byt = (M * r4(K) * 8 + M * r4(N) * 8 + N * r4(K) * 8)
-            print(f"M={M:6d} N={N:4d} K={K:4d}  {t:7.1f} us   hbm floor {byt / 6.5e6:6.1f} us   {2*M*N*K/t/1e6:6.1f} TF | no C_lo: {t2:7.1f} us {2*M*N*K/t2/1e6:6.1f} TF", flush=True)
+            print(f"M={M:6d} N={N:4d} K={K:4d}  {t:7.1f} us   hbm floor {byt / 6.5e6:6.1f} us   {2*M*N*K/t/1e6:6.1f} TF | no C_lo: {t2:7.1f} us {2*M*N*K/t2/1e6:6.1f} TF | in-SM split: {t3:7.1f} us {2*M*N*K/t3/1e6:6.1f} TF", flush=True)
 
 if __name__ == "__main__":
     main()
