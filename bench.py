@@ -45,10 +45,11 @@ sys.path.insert(0, ROOT)
 
 T_STEPS = 24
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_gemm_tc2 launch from the committed ncu --set full capture
-# (profiles/r1_gemm_tc2_ncu_raw.csv: dgrad 24576 x 693 x 512, 103.94 MB read + 37.52 MB written; algorithmic 100.7 MB of operands +
-# 68.4 MB of output, part of which is still L2-resident when the kernel ends)
-TRAFFIC_GEMM_TC2 = 141465344
-TRAFFIC_FOOTHOLD_16384 = 11958016  # profiles/r2_foothold_v6_ncu_raw.csv: 10.81 MB read + 1.15 MB written
+# (profiles/r2_gemm_tc2_ncu_raw.csv: forward 24576 x 512 x 512, the most frequent shape: 102.84 MB read + 59.29 MB written;
+# algorithmic 100.7 MB of operands (x and its TF32 companion) + 2 MB of weights + 100.7 MB of output, part of which is still
+# L2-resident when the kernel ends)
+TRAFFIC_GEMM_TC2 = 162128896
+TRAFFIC_FOOTHOLD_16384 = 11802112  # profiles/r2_foothold_v6_ncu_raw.csv: 10.82 MB read + 0.98 MB written
 PORT_OVER_REFERENCE = 1.245  # tools/port_vs_reference.py (build container, 1024 envs, 8 cores)
 BYTES_STATE_PER_ENV = (13 + 12 * 2 + 17 * 3 + 17 * 13) * 4  # root, dof, contact, rigid body
 
@@ -198,9 +199,9 @@ def foothold_microbench(device, peaks, N=16384, iters=20, warmup=3):
             "launches_timed": iters, "algorithmic_bytes_per_launch": nbytes, "traffic": TRAFFIC_FOOTHOLD_16384,
             "workload": "configs[4]: 16384 envs x 4 legs x 45-candidate windows (7x7 lattice minus corners = every point within 0.16 m) "
                         "over the 1.5 m heightmap patch, stepping-stone map; L2 flushed (256 MB memset) before every launch",
-            "traffic_note": "ncu --set full at 16384 envs: DRAM 10.81 MB read + 1.15 MB written per launch; the 46 MB of outputs stay "
+            "traffic_note": "ncu --set full at 16384 envs: DRAM 10.82 MB read + 0.98 MB written per launch; the 46 MB of outputs stay "
                             "L2-resident for the consumer kernels, so DRAM traffic is below the algorithmic bytes; the kernel is issue-bound "
-                            "(1.9 k warp instructions per environment), see profiles/README.md",
+                            "(2.0 k warp instructions per environment), see profiles/README.md",
             "peak_source": peaks["source"]}
 
 

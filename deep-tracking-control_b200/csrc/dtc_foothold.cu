@@ -1052,8 +1052,10 @@ k_foothold_v6(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const i
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   V6Warp& W = S.w[warp];
   const int N = cfg->num_envs;
-  const int c0 = blockIdx.x * per_cta, c1 = min(N, c0 + per_cta);
-  if (c0 >= N) return;
+  // contiguous chunks whose sizes differ by at most one environment (per_cta is the launcher's upper bound): with one wave of
+  // CPS CTAs per SM every SM gets the same work to within CPS environments
+  const int c0 = (int)((int64_t)blockIdx.x * N / gridDim.x), c1 = (int)((int64_t)(blockIdx.x + 1) * N / gridDim.x);
+  if (c0 >= c1 || c1 - c0 > per_cta) return;
   const int rows = cfg->map_rows, cols = cfg->map_cols;
   const float border = cfg->border_size, hscale = cfg->horizontal_scale, vscale = cfg->vertical_scale;
   if (threadIdx.x < GXN) S.gx[threadIdx.x] = cfg->grid_x[threadIdx.x];
@@ -1344,11 +1346,11 @@ static int launch_v6(dtc_env* e, const V5Params& P, cudaStream_t st) {
     if (ctas < 1) { sms = 0; DTC_FAIL(DTC_ERR_CUDA, "k_foothold_v6 does not fit on this device"); }
   }
   const int N = e->cfg.num_envs;
-  // contiguous chunks, a whole number of environments per warp, one wave of CTAs
-  int per = ceil_div(N, sms * CPS);
-  per = ceil_div(per, V6_WARPS) * V6_WARPS;
+  // one wave: as many CTAs as fit at once (CPS per SM) once every CTA has at least two environments per warp; the kernel cuts N
+  // into gridDim.x contiguous chunks of floor / ceil (N / gridDim.x) environments
+  const int grid = max(1, min(sms * CPS, ceil_div(N, 2 * V6_WARPS)));
   if (!e->min3_map_ok) DTC_FAIL(DTC_ERR_STATE, "dtc_foothold_step: tensor map of the min3 table missing (dtc_env_bind builds it)");
-  k_foothold_v6<SEP, CPS><<<ceil_div(N, per), V6_WARPS * 32, smem, st>>>(e->d_cfg, e->buf, e->min3, P, per, e->min3_map);
+  k_foothold_v6<SEP, CPS><<<grid, V6_WARPS * 32, smem, st>>>(e->d_cfg, e->buf, e->min3, P, ceil_div(N, grid), e->min3_map);
   return DTC_OK;
 }
 static int v6_cps() {  // resident CTAs per SM the kernel is compiled for (env DTC_FH_CPS = 4 | 5 | 6, tuning knob)

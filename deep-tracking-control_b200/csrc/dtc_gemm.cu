@@ -381,24 +381,28 @@ int dtc_gemm_launch(GemmArgs a, cudaStream_t st) {
 }
 
 // out[n] = sum over the per-32-row-block partial column sums written by the tensor-core epilogue (GemmArgs::colsum_part)
-__global__ void __launch_bounds__(256) k_colsum_part(const float* __restrict__ part, int nblk, int ld, int ncols, float* __restrict__ out) {
-  __shared__ float sh[8][33];
+// 1024 threads = 32 columns x 32 row groups: each thread adds nblk / 32 partials (24 at 24 576 rows) with its loads unrolled, so the
+// kernel is a few L2 round trips instead of ~100 dependent ones; fixed summation order (deterministic)
+__global__ void __launch_bounds__(1024) k_colsum_part(const float* __restrict__ part, int nblk, int ld, int ncols, float* __restrict__ out) {
+  __shared__ float sh[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
   float s = 0.f;
-  if (n < ncols)
-    for (int b = ty; b < nblk; b += 8) s += __ldg(part + (size_t)b * ld + n);
+  if (n < ncols) {
+#pragma unroll 8
+    for (int b = ty; b < nblk; b += 32) s += __ldg(part + (size_t)b * ld + n);
+  }
   sh[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && n < ncols) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += sh[k][tx];
+    for (int k = 0; k < 32; ++k) t += sh[k][tx];
     out[n] = t;
   }
 }
 int dtc_colsum_part_launch(const float* part, int nblk, int ld, int ncols, float* out, cudaStream_t st) {
-  k_colsum_part<<<ceil_div(ncols, 32), 256, 0, st>>>(part, nblk, ld, ncols, out);
+  k_colsum_part<<<ceil_div(ncols, 32), 1024, 0, st>>>(part, nblk, ld, ncols, out);
   DTC_CHECK_LAUNCH("k_colsum_part");
   return DTC_OK;
 }

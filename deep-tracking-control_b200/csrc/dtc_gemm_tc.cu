@@ -1179,8 +1179,8 @@ extern "C" int dtc_get_gemm_pair(void) { return tc_pair_mode(); }
 // side streams' small kernels run.
 static int g_tc_pdl = -1;
 static int tc_pdl_on() {
-  if (g_tc_pdl < 0) { const char* e = getenv("DTC_PDL"); g_tc_pdl = (e && e[0] == '1') ? 1 : 0; }
-  return g_tc_pdl;
+  if (g_tc_pdl < 0) { const char* e = getenv("DTC_PDL"); g_tc_pdl = !e ? 0 : e[0] == '1' ? 1 : e[0] == '2' ? 2 : 0; }
+  return g_tc_pdl;  // 2: only grids that leave SMs free (the 4096-row rollout shapes)
 }
 template <typename K>
 static int tc_launch_pdl(K kernel, dim3 grid, int smem, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB,
@@ -1191,7 +1191,7 @@ static int tc_launch_pdl(K kernel, dim3 grid, int smem, cudaStream_t st, const C
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = tc_pdl_on() ? 1 : 0;
+  cfg.numAttrs = (tc_pdl_on() == 1 || (tc_pdl_on() == 2 && grid.x <= 128)) ? 1 : 0;
   DTC_CUDA(cudaLaunchKernelEx(&cfg, kernel, mA, mAlo, mB, mBlo, mC, mClo, p));
   return DTC_OK;
 }

@@ -898,19 +898,24 @@ __global__ void __launch_bounds__(256) k_vae_loss_height(int M, float inv_count,
                                                          const float* __restrict__ xc, float* __restrict__ dHR,
                                                          float* __restrict__ dHR_lo, double* __restrict__ stats) {
   __shared__ double sh[32];
-  const long long total = (long long)M * 696;
+  const long long total4 = (long long)M * 174;  // 696 = 174 float4 per row; HR / dHR rows are 16-byte aligned
   double s = 0.0;
   const float c = 2.0f * inv_count;
-  for (long long e = blockIdx.x * 256ll + threadIdx.x; e < total; e += gridDim.x * 256ll) {
-    int m = (int)(e / 696), j = (int)(e - (long long)m * 696);
-    float g = 0.f;
-    if (j < 693) {
-      float d = HR[e] - xc[(size_t)m * LD_XC + 3 + j];
-      s += (double)d * (double)d;
-      g = c * d;
-    }
-    dHR[e] = g;
-    if (dHR_lo) dHR_lo[e] = tf32_lo(g);
+  for (long long e4 = blockIdx.x * 256ll + threadIdx.x; e4 < total4; e4 += gridDim.x * 256ll) {
+    const int m = (int)(e4 / 174), j = (int)(e4 - (long long)m * 174) * 4;
+    const float4 h = *reinterpret_cast<const float4*>(HR + e4 * 4);
+    const float* x = xc + (size_t)m * LD_XC + 3 + j;  // the target starts at column 3 of the packed critic row: scalar loads
+    float d[4] = {h.x - x[0], h.y - x[1], h.z - x[2], 0.f};
+    if (j + 3 < 693) d[3] = h.w - x[3];
+    if (j + 2 >= 693) d[2] = 0.f;
+    if (j + 1 >= 693) d[1] = 0.f;
+    float part = 0.f;  // four squares in fp32, the running sum in fp64 (as before to ~1e-7 relative)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) part = fmaf(d[k], d[k], part);
+    s += (double)part;
+    const float4 g = make_float4(c * d[0], c * d[1], c * d[2], c * d[3]);
+    *reinterpret_cast<float4*>(dHR + e4 * 4) = g;
+    if (dHR_lo) *reinterpret_cast<float4*>(dHR_lo + e4 * 4) = make_float4(tf32_lo(g.x), tf32_lo(g.y), tf32_lo(g.z), tf32_lo(g.w));
   }
   s = block_sum(s, sh);
   if (threadIdx.x == 0) atomicAdd(&stats[ST_HEIGHT], s * (double)inv_count);
@@ -1408,7 +1413,7 @@ extern "C" int dtc_vae_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
   k_vae_loss_rows<<<ceil_div(M, 128), 128, 0, sc>>>(M, inv_rows, l->REC, next_obs, l->ML, xc, l->dREC, l->dML, l->stats);
   DTC_CHECK_LAUNCH("k_vae_loss_rows");
   RET_IF(split_lo(l->dREC, lo_of(l, l->dREC), (int64_t)M * 56, sc));
-  k_vae_loss_height<<<grid1d((long long)M * 696, 256), 256, 0, st>>>(M, 1.0f / ((float)M * 693.0f), l->HR, xc, l->dHR, lo_of(l, l->dHR),
+  k_vae_loss_height<<<grid1d((long long)M * 174, 256), 256, 0, st>>>(M, 1.0f / ((float)M * 693.0f), l->HR, xc, l->dHR, lo_of(l, l->dHR),
                                                                      l->stats);
   DTC_CHECK_LAUNCH("k_vae_loss_height");
   // backward: cenet decoder (stream c), terrain decoder (caller's stream), weight gradients (stream w)

@@ -1,3 +1,4 @@
+"""One tensor-core GEMM launched four times (ncu capture target): python tools/one_gemm.py M N K"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, dtc_b200
