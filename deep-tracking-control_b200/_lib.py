@@ -76,7 +76,8 @@ class ParamInfo(C.Structure):
 
 
 # every entry point include/dtc_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
-EXPORTED_SYMBOLS = ['dtc_env_bind', 'dtc_env_create', 'dtc_env_destroy', 'dtc_env_heightmap_updated', 'dtc_env_observe', 'dtc_env_pre_physics', 'dtc_env_reward_reset', 'dtc_env_set_step_base', 'dtc_env_state_prep', 'dtc_counter_add', 'dtc_count_launches', 'dtc_learner_set_act_counter_base', 'dtc_foothold_step', 'dtc_gae', 'dtc_gae_normalize', 'dtc_gather_minibatch', 'dtc_gemm_debug', 'dtc_get_gemm_mode', 'dtc_get_gemm_pair', 'dtc_get_overlap', 'dtc_gru_forward', 'dtc_gru_param_floats', 'dtc_gru_reset', 'dtc_last_error', 'dtc_launch_count', 'dtc_learner_create', 'dtc_learner_debug_buffer', 'dtc_learner_destroy', 'dtc_learner_get_adam_steps', 'dtc_learner_grad_bucket', 'dtc_learner_wait_bucket', 'dtc_learner_refresh_params', 'dtc_learner_reset_stats', 'dtc_learner_set_adam_steps', 'dtc_learner_set_lr', 'dtc_learner_stats', 'dtc_learner_workspace_bytes', 'dtc_linear_forward', 'dtc_optimizer_apply', 'dtc_param_count', 'dtc_param_get', 'dtc_param_range', 'dtc_param_total_floats', 'dtc_policy_act', 'dtc_policy_act_teacher', 'dtc_policy_evaluate', 'dtc_ppo_step', 'dtc_profile_enable', 'dtc_profile_kind', 'dtc_profile_read', 'dtc_set_gemm_mode', 'dtc_set_gemm_pair', 'dtc_set_overlap', 'dtc_store_transition', 'dtc_struct_size', 'dtc_terrain_paint', 'dtc_terrain_rasterize', 'dtc_vae_step', 'dtc_version']
+EXPORTED_SYMBOLS = ['dtc_env_bind', 'dtc_env_create', 'dtc_env_destroy', 'dtc_env_heightmap_updated', 'dtc_env_observe', 'dtc_env_pre_physics', 'dtc_env_reward_reset', 'dtc_env_set_step_base', 'dtc_env_state_prep', 'dtc_counter_add', 'dtc_count_launches', 'dtc_learner_set_act_counter_base', 'dtc_foothold_step', 'dtc_gae', 'dtc_gae_normalize', 'dtc_gather_minibatch', 'dtc_gemm_debug', 'dtc_get_gemm_mode', 'dtc_get_gemm_pair', 'dtc_get_overlap', 'dtc_gru_forward', 'dtc_gru_param_floats', 'dtc_gru_reset', 'dtc_last_error', 'dtc_launch_count', 'dtc_learner_create', 'dtc_learner_debug_buffer', 'dtc_learner_destroy', 'dtc_learner_get_adam_steps', 'dtc_learner_grad_bucket', 'dtc_learner_wait_bucket', 'dtc_learner_refresh_params', 'dtc_learner_reset_stats', 'dtc_learner_set_adam_steps', 'dtc_learner_set_lr', 'dtc_learner_stats', 'dtc_learner_workspace_bytes', 'dtc_linear_forward', 'dtc_optimizer_apply', 'dtc_param_count', 'dtc_param_get', 'dtc_param_range', 'dtc_param_total_floats', 'dtc_policy_act', 'dtc_policy_act_teacher', 'dtc_policy_evaluate', 'dtc_ppo_step', 'dtc_profile_enable', 'dtc_profile_kind', 'dtc_profile_read', 'dtc_set_gemm_mode', 'dtc_set_gemm_pair', 'dtc_set_overlap', 'dtc_store_transition', 'dtc_struct_size', 'dtc_terrain_paint', 'dtc_terrain_rasterize', 'dtc_vae_step', 'dtc_version', 'dtc_dp_create', 'dtc_dp_handles', 'dtc_dp_open', 'dtc_dp_allreduce', 'dtc_dp_error', 'dtc_dp_register', 'dtc_dp_open_registered',
+                    'dtc_dp_destroy']
 
 
 class DtcError(RuntimeError):
@@ -137,6 +138,15 @@ def lib():
     L.dtc_gru_param_floats.argtypes = [i32, i32, i32]
     L.dtc_gru_forward.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     L.dtc_gru_reset.argtypes = [i32, i32, i32, vp, vp, vp]
+    L.dtc_dp_create.argtypes = [i32, i32, C.c_int64, C.POINTER(vp)]
+    L.dtc_dp_handles.argtypes = [vp, C.c_char_p, C.c_char_p]
+    L.dtc_dp_open.argtypes = [vp, i32, C.c_char_p, C.c_char_p]
+    L.dtc_dp_allreduce.argtypes = [vp, vp, C.c_int64, vp]
+    L.dtc_dp_register.argtypes = [vp, vp, C.c_int64, C.c_char_p, C.POINTER(C.c_int64)]
+    L.dtc_dp_open_registered.argtypes = [vp, i32, C.c_char_p, C.c_int64]
+    L.dtc_dp_error.argtypes = [vp, vp]
+    L.dtc_dp_destroy.argtypes = [vp]
+    L.dtc_dp_destroy.restype = None
     L.dtc_profile_kind.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.dtc_gae_normalize.argtypes = [SP, vp, vp]
     L.dtc_gather_minibatch.argtypes = [SP, SP, vp, C.c_int64, vp]

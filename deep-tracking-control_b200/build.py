@@ -6,7 +6,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libdtc_b200.so")
-SOURCES = ["dtc_env.cu", "dtc_foothold.cu", "dtc_gemm.cu", "dtc_gemm_tc.cu", "dtc_learner.cu", "dtc_gru.cu", "dtc_terrain.cu"]
+SOURCES = ["dtc_env.cu", "dtc_foothold.cu", "dtc_gemm.cu", "dtc_gemm_tc.cu", "dtc_learner.cu", "dtc_gru.cu", "dtc_terrain.cu", "dtc_dp.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

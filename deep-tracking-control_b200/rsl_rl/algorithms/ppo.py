@@ -13,6 +13,7 @@ after backward, the flat gradient range (plus the KL sum riding behind it) is al
 dtc_optimizer_apply finishes with grad_scale = 1/world.  The advantage moments are all-reduced once per iteration.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -139,6 +140,7 @@ class PPO:
         self._update_calls = 0
         self._grad_tap = None  # tests: callable(which) invoked between backward and the optimizer step (0 = vae, 1 = policy)
         self.group = None  # torch.distributed process group for data parallel training (None = default group)
+        self._peer = None  # rsl_rl.utils.dp.PeerAllReduce, created on first use (False: not available, NCCL instead)
         self._comm = None  # communication stream of the bucketed gradient all-reduce (created on first use)
 
     # ------------------------------------------------------------------ learning rate lives on the device
@@ -244,6 +246,29 @@ class PPO:
                     B.check(lib.dtc_learner_grad_bucket(w, k, C.byref(b0), C.byref(b1)), "dtc_learner_grad_bucket")
                     self._buckets[(w, k)] = (b0.value, b1.value)
         comm = self._comm
+        # DTC_DP = p2p (default on one NVLink node: csrc/dtc_dp.cu, one peer-memory all-reduce of the whole range at step end) |
+        #          nccl1 (one NCCL all-reduce at step end) | nccl2 (two NCCL buckets on a communication stream).
+        # Measured, 2 x B200 (gpurun_out/r2r): nccl2 87.1 / 86.8 ms per iteration, nccl1 86.5 / 86.9 - the bucket that could overlap
+        # does not (the persistent GEMM grids leave NCCL no SMs until they drain), so what matters is the latency of the one
+        # exposed collective per optimizer step.
+        mode = os.environ.get("DTC_DP", "p2p")
+        lo = min(self._buckets[(which, 0)][0], self._buckets[(which, 1)][0])
+        hi = max(self._buckets[(which, 0)][1], self._buckets[(which, 1)][1])
+        if mode == "p2p":
+            if self._peer is None:
+                n = ac._grads.numel()
+                ok = dp.PeerAllReduce.available(self.device, self.group) and lo % 4 == 0 and ac._grads.data_ptr() % 16 == 0
+                self._peer = dp.PeerAllReduce((n + 3) // 4 * 4, self.device, self.group) if ok else False
+                if self._peer and os.environ.get("DTC_DP_INPLACE", "1") != "0":
+                    self._peer.register(ac._grads)  # all-reduce straight out of / into every rank's gradient buffer
+            if self._peer:
+                hi4 = min((hi + 3) // 4 * 4, ac._grads.numel() // 4 * 4)  # a few floats past the range may ride along: they are rewritten before use
+                self._peer.allreduce_sum_(ac._grads[lo:hi4])
+                return
+            mode = "nccl1"
+        if mode == "nccl1":
+            dp.allreduce_sum_(ac._grads[lo:hi], self.group)
+            return
         for k in (0, 1):
             b0, b1 = self._buckets[(which, k)]
             B.check(lib.dtc_learner_wait_bucket(h, which, k, C.c_void_p(comm.cuda_stream)), "dtc_learner_wait_bucket")
@@ -274,7 +299,7 @@ class PPO:
         hp = self._hparams()
         world = self._world()
         tap = self._grad_tap
-        sync = 1 if (world > 1 or tap is not None) else 0
+        sync = 1 if (world > 1 or tap is not None or os.environ.get("DTC_FORCE_SYNC") == "1") else 0  # env: measurement switch
         tab = ac._table
         self._update_calls += 1
         k = 0
@@ -299,6 +324,8 @@ class PPO:
                     self._allreduce_buckets(h, 1)
                     B.check(lib.dtc_optimizer_apply(h, 1, C.byref(hp), 1.0 / world, mbs * world, stream), "dtc_optimizer_apply")
         s = ac.stats().tolist()  # the one device->host read of update()
+        if self._peer:
+            self._peer.check()  # no rank ever timed out waiting for a peer's flag
         n = self.num_learning_epochs * self.num_mini_batches
         self._lr_host = s[8]
         self.last_stats = dict(value=s[0] / n, surrogate=s[1] / n, recons=s[2] / n, vel=s[3] / n, kld=s[4] / n, height=s[5] / n,

@@ -46,3 +46,70 @@ def shard_envs(total_envs, group=None):
     w, r = world_size(group), rank(group)
     per = total_envs // w
     return r * per, (r + 1) * per if r < w - 1 else total_envs
+
+
+class PeerAllReduce:
+    """SUM all-reduce of a flat float32 CUDA range over NVLink peer memory (include/dtc_b200.h: dtc_dp_*; csrc/dtc_dp.cu): three
+    launches on the caller's stream, device-side flag handshakes, no NCCL call.  torch.distributed is only the channel that carries
+    the two CUDA IPC handles of every rank to the others, once.  `available()` says whether this process group can use it (CUDA,
+    world size 2..16, one node)."""
+
+    def __init__(self, max_floats, device, group=None):
+        import ctypes as C
+        from ... import _lib as B
+        self._B, self._C = B, C
+        self.world, self.rank, self.device = world_size(group), rank(group), torch.device(device)
+        lib = B.lib()
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            B.check(lib.dtc_dp_create(self.rank, self.world, int(max_floats), C.byref(self._h)), "dtc_dp_create")
+            hb, hf = C.create_string_buffer(64), C.create_string_buffer(64)
+            B.check(lib.dtc_dp_handles(self._h, hb, hf), "dtc_dp_handles")
+            mine = (self.rank, hb.raw, hf.raw)
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine, group=group)
+            for r, b, f in everyone:
+                if r != self.rank:
+                    B.check(lib.dtc_dp_open(self._h, int(r), b, f), "dtc_dp_open")
+        dist.barrier(group=group)  # every rank has mapped every buffer before the first flag is raised
+        self.max_floats = int(max_floats)
+        self._group = group
+
+    def register(self, flat):
+        """Maps `flat` (this rank's own buffer, same size on every rank; e.g. the flat gradient buffer) into every other rank, so
+        that all-reduces of its sub-ranges run as one in-place kernel.  Collective: every rank calls it once."""
+        B, C = self._B, self._C
+        assert flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous()
+        hb, off = C.create_string_buffer(64), C.c_int64()
+        B.check(B.lib().dtc_dp_register(self._h, B.ptr(flat), flat.numel(), hb, C.byref(off)), "dtc_dp_register")
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, (self.rank, hb.raw, int(off.value), flat.numel()), group=self._group)
+        assert all(e[3] == flat.numel() for e in everyone), "every rank must register a range of the same size"
+        with torch.cuda.device(self.device):
+            for r, h, o, _ in everyone:
+                if r != self.rank:
+                    B.check(B.lib().dtc_dp_open_registered(self._h, int(r), h, o), "dtc_dp_open_registered")
+        dist.barrier(group=self._group)
+        self._registered = flat  # keeps the tensor (and with it the peers' view of this memory) alive
+
+    @staticmethod
+    def available(device, group=None):
+        w = world_size(group)
+        return torch.device(device).type == "cuda" and 2 <= w <= 16 and dist.get_backend(group) == "nccl"
+
+    def allreduce_sum_(self, flat):
+        B = self._B
+        n = flat.numel()
+        assert flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous() and n % 4 == 0
+        B.check(B.lib().dtc_dp_allreduce(self._h, B.ptr(flat), n, B.stream_ptr(self.device)), "dtc_dp_allreduce")
+        return flat
+
+    def check(self):
+        """Synchronises the current stream; raises if any rank ever timed out waiting for a peer."""
+        B = self._B
+        B.check(B.lib().dtc_dp_error(self._h, B.stream_ptr(self.device)), "dtc_dp_error")
+
+    def close(self):
+        if self._h:
+            self._B.lib().dtc_dp_destroy(self._h)
+            self._h = None

@@ -352,6 +352,30 @@ int dtc_terrain_paint(int32_t rows, int32_t cols, int32_t border_px, int32_t len
                       const dtc_subterrain* subs, const int32_t* rects, const int32_t origin_window[4], double terrain_length,
                       double terrain_width, double vertical_scale, int16_t* height_samples, float* terrain_origins, void* stream);
 
+/* ------------------------------------------------------------------ C1: gradient all-reduce over NVLink peer memory
+ * (the reference is single-process and has no collective - this replaces the torch.distributed / NCCL all-reduce
+ * a data-parallel port of rsl_rl/algorithms/ppo.py:254,338 would call between backward and optimizer.step()).
+ * One process per GPU.  dtc_dp_create allocates this rank's exchange buffer and flag words with cudaMalloc; dtc_dp_handles returns
+ * their two 64-byte cudaIpcMemHandle_t, which the host side passes to the other ranks by any channel (torch.distributed
+ * all_gather_object in rsl_rl/utils/dp.py) and every rank maps with dtc_dp_open.  dtc_dp_allreduce(data, n) is then three launches on
+ * `stream` - publish, reduce-scatter + all-gather through P2P loads / stores, collect - with device-side flag handshakes only: no host
+ * synchronisation, no NCCL.  Every element is summed by one rank in rank order: all replicas get bit-identical sums.  n % 4 == 0,
+ * data 16-byte aligned, n <= max_floats; all ranks must issue the same sequence of calls.  dtc_dp_error synchronises `stream` and
+ * reports whether any wait ever exceeded ~2 s (then the data is not a sum and the run should stop). */
+typedef struct dtc_dp dtc_dp;
+int dtc_dp_create(int32_t rank, int32_t world, int64_t max_floats, dtc_dp** out);
+int dtc_dp_handles(dtc_dp* d, void* buf_handle64, void* flags_handle64);
+int dtc_dp_open(dtc_dp* d, int32_t peer, const void* buf_handle64, const void* flags_handle64);
+ /* Registered in-place variant (what training uses): dtc_dp_register(base, nfloats) returns the IPC handle of the cudaMalloc allocation
+ * that contains this rank's own buffer (e.g. the flat gradient buffer inside a block of torch's caching allocator) and base's byte
+ * offset in it; after every rank has mapped every other rank's range with dtc_dp_open_registered, dtc_dp_allreduce on a sub-range of
+ * the registered buffer is ONE cooperative kernel that sums straight out of / into all ranks' buffers (no staging copies). */
+int dtc_dp_register(dtc_dp* d, float* base, int64_t nfloats, void* handle64, int64_t* offset_bytes);
+int dtc_dp_open_registered(dtc_dp* d, int32_t peer, const void* handle64, int64_t offset_bytes);
+int dtc_dp_allreduce(dtc_dp* d, float* data, int64_t n, void* stream);
+int dtc_dp_error(dtc_dp* d, void* stream);
+void dtc_dp_destroy(dtc_dp* d);
+
 /* ------------------------------------------------------------------ P14 / SURVEY 8f N2: the optional GRU `Memory`
  * Memory.forward / Memory.reset (rsl_rl/rsl_rl/modules/actor_critic_decoder.py:584-614): nn.GRU(input_size, hidden_size,
  * num_layers) over T time steps for N rows.  `weights`: per layer weight_ih_l [3H,in_l] | weight_hh_l [3H,H] | bias_ih_l [3H] |

@@ -80,3 +80,61 @@ def test_two_gpu_policy_step_matches_single_gpu():
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def _peer_worker(rank, world, port):
+    """csrc/dtc_dp.cu: the peer-memory all-reduce against NCCL's on the same data, repeated (epochs, buffer reuse), on ragged sizes
+    and on a sub-range; then the training step above with the peer all-reduce in place of NCCL."""
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        from dtc_b200.rsl_rl.utils import dp
+        dev = torch.device(f"cuda:{rank}")
+        assert dp.PeerAllReduce.available(dev)
+        n_max = 1 << 21
+        peer = dp.PeerAllReduce(n_max, dev)
+        g = torch.Generator().manual_seed(100 + rank)
+        for it, n in enumerate((4, 1024, 4100, 1 << 20, n_max, 262148, 1 << 21, 8)):
+            x = torch.randn(n, generator=g).to(dev)
+            ref = x.clone()
+            dist.all_reduce(ref)
+            buf = torch.zeros(n + 16, device=dev)
+            buf[8:8 + n] = x           # a 32-byte-aligned sub-range: the neighbours must stay untouched
+            peer.allreduce_sum_(buf[8:8 + n])
+            torch.cuda.synchronize()
+            # two ranks: a + b is the same in either order -> bit-equal to NCCL; more ranks: same sum up to association
+            assert torch.equal(buf[8:8 + n], ref) if world == 2 else torch.allclose(buf[8:8 + n], ref, rtol=1e-6, atol=1e-6), (it, n)
+            assert float(buf[:8].abs().sum()) == 0.0 and float(buf[8 + n:].abs().sum()) == 0.0, (it, n)
+        # registered in-place path: one cooperative kernel straight out of / into every rank's own buffer
+        big = torch.zeros(n_max + 64, device=dev)
+        peer.register(big)
+        for it, (off, n) in enumerate(((0, 4), (8, 4100), (16, 1 << 20), (0, n_max), (64, 1851000), (4, 1950000), (32, 8))):
+            x = torch.randn(n, generator=g).to(dev)
+            ref = x.clone()
+            dist.all_reduce(ref)
+            big.zero_()
+            big[off:off + n] = x
+            peer.allreduce_sum_(big[off:off + n])
+            torch.cuda.synchronize()
+            assert torch.equal(big[off:off + n], ref) if world == 2 else torch.allclose(big[off:off + n], ref, rtol=1e-6, atol=1e-6), ("inplace", it, n)
+            assert float(big[:off].abs().sum()) == 0.0 and float(big[off + n:].abs().sum()) == 0.0, ("inplace", it, n)
+        # every replica holds the same bits (each element is summed by exactly one rank)
+        y = torch.randn(4096, generator=g).to(dev)
+        peer.allreduce_sum_(y)
+        ys = [torch.empty_like(y) for _ in range(world)]
+        dist.all_gather(ys, y)
+        assert all(torch.equal(ys[0], t) for t in ys[1:])
+        peer.check()
+        peer.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_memory_allreduce_matches_nccl():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_peer_worker, args=(2, _free_port()), nprocs=2, join=True)
