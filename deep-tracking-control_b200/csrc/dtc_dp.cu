@@ -62,16 +62,21 @@ __device__ __forceinline__ float4 dp_load_peer(const float* p) {  // never serve
 }
 // thread 0 of every CTA waits until all `world` flags of the own array reached `epoch`, then the CTA proceeds
 __device__ __forceinline__ void dp_wait_all(uint32_t* own_flags, int which, int world, uint32_t epoch) {
-  if (threadIdx.x == 0) {
+  if ((int)threadIdx.x < world) {  // one thread per peer: the polls run side by side
     const long long t0 = clock64();
-    for (int p = 0; p < world; ++p) {
-      while ((int32_t)(dp_load_acquire_sys(own_flags + which + p) - epoch) < 0) {
-        if (clock64() - t0 > 4000000000ll) { own_flags[DP_ERROR] = 1u; break; }  // ~2 s: give up rather than hang the device
-        __nanosleep(64);
-      }
+    while ((int32_t)(dp_load_acquire_sys(own_flags + which + threadIdx.x) - epoch) < 0) {
+      if (clock64() - t0 > 4000000000ll) { own_flags[DP_ERROR] = 1u; break; }  // ~2 s: give up rather than hang the device
+      __nanosleep(20);
     }
   }
   __syncthreads();
+}
+// one thread per peer raises flag[which][rank] = epoch there; the caller has fenced (system scope) whatever the flag publishes
+__device__ __forceinline__ void dp_raise(const DpPeers& P, int which, int rank, int world, uint32_t epoch) {
+  if ((int)threadIdx.x < world) {
+    volatile uint32_t* f = P.flags[threadIdx.x] + which + rank;
+    *f = epoch;
+  }
 }
 // the last CTA of the grid to get here raises flag[which][rank] = epoch in every rank's flag array
 __device__ __forceinline__ void dp_signal_all(const DpPeers& P, uint32_t* own_flags, int which, int rank, int world, uint32_t epoch) {
@@ -81,8 +86,8 @@ __device__ __forceinline__ void dp_signal_all(const DpPeers& P, uint32_t* own_fl
     const uint32_t prev = atomicAdd(own_flags + DP_COUNTER, 1u);
     if (prev == gridDim.x - 1) {
       own_flags[DP_COUNTER] = 0u;
-      __threadfence_system();
-      for (int p = 0; p < world; ++p) dp_store_release_sys(P.flags[p] + which + rank, epoch);
+      __threadfence_system();  // one fence, then posted stores: a release per flag would serialise world round trips
+      for (int p = 0; p < world; ++p) *((volatile uint32_t*)(P.flags[p] + which + rank)) = epoch;
     }
   }
 }
@@ -133,9 +138,9 @@ __global__ void __launch_bounds__(512) k_dp_allreduce_inplace(DpPeers P /* buf[]
                                                               int rank, uint32_t epoch, uint32_t barrier_target) {
   uint32_t* own = P.flags[rank];
   // A: this rank's gradients are complete (stream order) -> tell everyone; wait until everyone's are
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0) {
     __threadfence_system();
-    for (int p = 0; p < WORLD; ++p) dp_store_release_sys(P.flags[p] + DP_FLAG_A + rank, epoch);
+    dp_raise(P, DP_FLAG_A, rank, WORLD, epoch);
   }
   dp_wait_all(own, DP_FLAG_A, WORLD, epoch);
   const int64_t s0 = n4 * rank / WORLD, s1 = n4 * (rank + 1) / WORLD;
@@ -163,8 +168,10 @@ __global__ void __launch_bounds__(512) k_dp_allreduce_inplace(DpPeers P /* buf[]
   }
   // B: every CTA's stores are out -> one signal per rank -> wait until every rank's slice has landed here
   dp_grid_barrier(own + DP_GRIDBAR, barrier_target);
-  if (blockIdx.x == 0 && threadIdx.x == 0)
-    for (int p = 0; p < WORLD; ++p) dp_store_release_sys(P.flags[p] + DP_FLAG_B + rank, epoch);
+  if (blockIdx.x == 0) {
+    __threadfence_system();  // orders the flags after everything the grid barrier made visible to this CTA (cumulativity)
+    dp_raise(P, DP_FLAG_B, rank, WORLD, epoch);
+  }
   dp_wait_all(own, DP_FLAG_B, WORLD, epoch);
 }
 template <int WORLD>
