@@ -379,7 +379,7 @@ def run_cuda(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(sample_envs=args.cpu_envs, iters=1)
+        cpu = cpu_baseline(sample_envs=args.cpu_envs, iters=5)  # ~2.3 s per iteration on 16 host cores: 10-12 s of CPU work
 
     if rank == 0:
         out = {

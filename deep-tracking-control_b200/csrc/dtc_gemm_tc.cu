@@ -43,6 +43,7 @@ struct TcParams {
   int splits, has_alo, has_blo;
   int split_a, split_b;  // 1: that operand's TF32 companion tile is computed in shared memory by the splitter warps (no *_lo array in HBM)
   int neff;   // 1: the MMA of a ragged / narrow n-tile covers only the live columns rounded up to the instruction granularity
+  int lo_direct;  // TMA-store epilogue: 1 = the companion output leaves from registers (env DTC_TC_LO=direct)
   int direct; // epilogue variant: 1 = registers -> global without the shared-memory transpose (env DTC_TC_EPI=direct|staged)
   int debug;  // timing experiments only (env DTC_TC_DEBUG): 1 = epilogue skips its stores, 2 = producer stops loading after the first ring fill
 };
@@ -340,11 +341,21 @@ __device__ __forceinline__ void tc_epilogue_tma(const TcParams& p, const CUtenso
     if (want_lo) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = tf32_lo(v[i]);
-      stg = stg_base + (stg_turn % NBUF) * (32 * 32);
-      tc_stg_acquire<NBUF>(lane);
-      tc_stage_rows(v, stg, lane);
-      tc_store_chunk(stg, lane, box_ok, mapClo, false, gn, gm_box, 0);
-      ++stg_turn;
+      if (p.lo_direct) {
+        // companion straight from registers (lane = row, 8 x 16 bytes): no second wait on the staging chunk's TMA store
+        if (row_ok) {
+          float* lrow = p.C_lo + (size_t)gm * p.ldc + gn;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            if (gn + 4 * j4 < n4) *(reinterpret_cast<float4*>(lrow) + j4) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+        }
+      } else {
+        stg = stg_base + (stg_turn % NBUF) * (32 * 32);
+        tc_stg_acquire<NBUF>(lane);
+        tc_stage_rows(v, stg, lane);
+        tc_store_chunk(stg, lane, box_ok, mapClo, false, gn, gm_box, 0);
+        ++stg_turn;
+      }
     }
   }
 }
@@ -1272,6 +1283,7 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   { static int direct = -1; if (direct < 0) { const char* e = getenv("DTC_TC_EPI"); direct = !e ? 2 : e[0] == 'd' ? 1 : e[0] == 's' ? 0 : 2; } p.direct = direct; }
   // Measured in the training step (gpurun_out/r2q, ms per iteration / in-step TFLOP/s of the pair kernel): tma 86.7 / 138.7, staged
   // 95.8 / 117.1, tma for forward + staged for the mask / fan-in epilogues 88.4 / 127.7.
+  { static int lod = -1; if (lod < 0) { const char* e = getenv("DTC_TC_LO"); lod = (e && e[0] == 'd') ? 1 : 0; } p.lo_direct = lod; }
   { static int neff = -1; if (neff < 0) { const char* e = getenv("DTC_TC_NEFF"); neff = e ? atoi(e) : 1; } p.neff = neff; }  // DTC_TC_NEFF=0: always 128-column MMAs
   const int amaj = a.a_kc ? 0 : 1, bmaj = a.b_kc ? 0 : 1;
   static int num_sms = 0;

@@ -81,9 +81,12 @@ class PeerAllReduce:
         B, C = self._B, self._C
         assert flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous()
         hb, off = C.create_string_buffer(64), C.c_int64()
-        B.check(B.lib().dtc_dp_register(self._h, B.ptr(flat), flat.numel(), hb, C.byref(off)), "dtc_dp_register")
+        rc = B.lib().dtc_dp_register(self._h, B.ptr(flat), flat.numel(), hb, C.byref(off))
+        mine = (self.rank, hb.raw, int(off.value), flat.numel()) if rc == 0 else None  # e.g. memory that has no IPC handle
         everyone = [None] * self.world
-        dist.all_gather_object(everyone, (self.rank, hb.raw, int(off.value), flat.numel()), group=self._group)
+        dist.all_gather_object(everyone, mine, group=self._group)
+        if any(e is None for e in everyone):
+            return False  # every rank takes the same decision: the exchange-buffer path stays in use
         assert all(e[3] == flat.numel() for e in everyone), "every rank must register a range of the same size"
         with torch.cuda.device(self.device):
             for r, h, o, _ in everyone:
@@ -91,6 +94,7 @@ class PeerAllReduce:
                     B.check(B.lib().dtc_dp_open_registered(self._h, int(r), h, o), "dtc_dp_open_registered")
         dist.barrier(group=self._group)
         self._registered = flat  # keeps the tensor (and with it the peers' view of this memory) alive
+        return True
 
     @staticmethod
     def available(device, group=None):
