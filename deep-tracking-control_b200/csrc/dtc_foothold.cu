@@ -1335,11 +1335,13 @@ k_foothold_v6(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const i
 
 template <bool SEP, int CPS>
 static int launch_v6(dtc_env* e, const V5Params& P, cudaStream_t st) {
-  static int sms = 0;
+  static int sms_dev[64] = {};  // per device: cudaFuncSetAttribute and the SM count belong to the current device
+  int dev = 0;
+  DTC_CUDA(cudaGetDevice(&dev));
+  int& sms = sms_dev[dev & 63];
   const int smem = (int)sizeof(V6Cta);
   if (!sms) {
-    int dev = 0, ctas = 0;
-    DTC_CUDA(cudaGetDevice(&dev));
+    int ctas = 0;
     DTC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     DTC_CUDA(cudaFuncSetAttribute(k_foothold_v6<SEP, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     DTC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_foothold_v6<SEP, CPS>, V6_WARPS * 32, smem));
@@ -1431,11 +1433,13 @@ static V5Params v5_params(const dtc_env_config& c, bool* separable) {
 
 template <bool SEP>
 static int launch_v5(dtc_env* e, const V5Params& P, cudaStream_t st) {
-  static int ctas_per_sm = 0, sms = 0;
+  static int ctas_dev[64] = {}, sms_dev[64] = {};  // per device
+  int dev = 0;
+  DTC_CUDA(cudaGetDevice(&dev));
+  int& ctas_per_sm = ctas_dev[dev & 63];
+  int& sms = sms_dev[dev & 63];
   const int smem = V5_WARPS * (int)sizeof(V5Smem);
   if (!ctas_per_sm) {
-    int dev = 0;
-    DTC_CUDA(cudaGetDevice(&dev));
     DTC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     DTC_CUDA(cudaFuncSetAttribute(k_foothold_v5<SEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     DTC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_foothold_v5<SEP>, V5_WARPS * 32, smem));

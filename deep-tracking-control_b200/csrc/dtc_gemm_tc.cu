@@ -17,6 +17,7 @@
 // 32-byte atoms - the only MN-major layout kind::tf32 accepts).  Out-of-range rows / k-tails are zero-filled by TMA.
 #include <cuda.h>
 
+#include <mutex>
 #include <unordered_map>
 
 #include "dtc_gemm.cuh"
@@ -43,6 +44,7 @@ struct TcParams {
   int splits, has_alo, has_blo;
   int split_a, split_b;  // 1: that operand's TF32 companion tile is computed in shared memory by the splitter warps (no *_lo array in HBM)
   int neff;   // 1: the MMA of a ragged / narrow n-tile covers only the live columns rounded up to the instruction granularity
+  int splitk_atomic;  // TMA-store epilogue, splits > 1: partial tiles are ADDED into C by the TMA unit (no workspace, no reduce kernel)
   int lo_direct;  // TMA-store epilogue: 1 = the companion output leaves from registers (env DTC_TC_LO=direct)
   int direct; // epilogue variant: 1 = registers -> global without the shared-memory transpose (env DTC_TC_EPI=direct|staged)
   int debug;  // timing experiments only (env DTC_TC_DEBUG): 1 = epilogue skips its stores, 2 = producer stops loading after the first ring fill
@@ -157,6 +159,12 @@ __device__ __forceinline__ void tc_tma_store_3d(const CUtensorMap* map, uint32_t
                "r"(c1), "r"(c2)
                : "memory");
 }
+// shared -> global with an fp32 ADD at the destination (L2 reduction): split-K partial tiles accumulate straight into C
+__device__ __forceinline__ void tc_tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tc_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tc_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // A warp owns NBUF staging chunks of 4 KB used round-robin, one TMA store per use: before a chunk is rewritten at most NBUF - 1 of the
@@ -171,11 +179,13 @@ __device__ __forceinline__ void tc_stage_rows(const float (&v)[32], float* stg, 
   for (int j4 = 0; j4 < 8; ++j4)
     *reinterpret_cast<float4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2)) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
 }
-__device__ __forceinline__ void tc_store_chunk(float* stg, int lane, bool issue, const CUtensorMap* map, bool is3d, int gn, int gm_box, int z) {
+// mode 0: 2-D store, 1: 3-D store into plane z (split-K workspace), 2: 2-D reduce-add (split-K partials summed in L2)
+__device__ __forceinline__ void tc_store_chunk(float* stg, int lane, bool issue, const CUtensorMap* map, int mode, int gn, int gm_box, int z) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA unit
   __syncwarp();
   if (lane == 0 && issue) {
-    if (is3d) tc_tma_store_3d(map, tc_smem_u32(stg), gn, gm_box, z);
+    if (mode == 1) tc_tma_store_3d(map, tc_smem_u32(stg), gn, gm_box, z);
+    else if (mode == 2) tc_tma_reduce_add_2d(map, tc_smem_u32(stg), gn, gm_box);
     else tc_tma_store_2d(map, tc_smem_u32(stg), gn, gm_box);
   }
   if (lane == 0) tc_bulk_commit();  // an (empty) group even when nothing was issued keeps the round-robin count in step
@@ -328,7 +338,7 @@ __device__ __forceinline__ void tc_epilogue_tma(const TcParams& p, const CUtenso
       for (int i = 0; i < 32; ++i) v[i] = 0.f;
     }
     tc_stage_rows(v, stg, lane);
-    tc_store_chunk(stg, lane, box_ok, mapC, partial, gn, gm_box, z);
+    tc_store_chunk(stg, lane, box_ok, mapC, partial ? (p.splitk_atomic ? 2 : 1) : 0, gn, gm_box, z);
     ++stg_turn;
     if (colsum) {
       // column sums of the 32 staged rows, lane = column: piece (lane >> 2) ^ (r & 7) of row r - 32 distinct banks per read.  The
@@ -353,7 +363,7 @@ __device__ __forceinline__ void tc_epilogue_tma(const TcParams& p, const CUtenso
         stg = stg_base + (stg_turn % NBUF) * (32 * 32);
         tc_stg_acquire<NBUF>(lane);
         tc_stage_rows(v, stg, lane);
-        tc_store_chunk(stg, lane, box_ok, mapClo, false, gn, gm_box, 0);
+        tc_store_chunk(stg, lane, box_ok, mapClo, 0, gn, gm_box, 0);
         ++stg_turn;
       }
     }
@@ -1114,10 +1124,12 @@ struct MapKeyHash {
   }
 };
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+static std::mutex g_maps_mu;  // the cache is shared by every host thread that launches GEMMs
 
 // operand X(r, k): maj 0 -> X = base[r*ld + k] (box 32 k x 128 r); maj 1 -> X = base[k*ld + r] (box 32 r x 32 k)
 static int tc_get_map(const float* base, int rows, int k, int ld, int maj, CUtensorMap* out) {
   MapKey key{base, rows, k, ld, maj};
+  std::lock_guard<std::mutex> lock(g_maps_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return DTC_OK; }
   if (!g_encode) {
@@ -1146,6 +1158,7 @@ static int tc_get_map(const float* base, int rows, int k, int ld, int maj, CUten
 // unit clips the ragged edges); planes > 0: the split-K workspace [planes][rows][cols] as a 3-D tensor (a box never crosses a plane)
 static int tc_get_out_map(const float* base, int rows, int cols, int ld, int planes, CUtensorMap* out) {
   MapKey key{base, rows, cols, planes > 0 ? planes : ld, planes > 0 ? 4 : 3};
+  std::lock_guard<std::mutex> lock(g_maps_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return DTC_OK; }
   if (!g_encode) {
@@ -1211,7 +1224,9 @@ template <int AMAJ, int BMAJ>
 static int tc2_launch_t(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB, const CUtensorMap& mBlo, const CUtensorMap& mC,
                         const CUtensorMap& mClo, const TcParams& p,
                         dim3 grid, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device
+  int dev_ = 0; cudaGetDevice(&dev_);
+  bool& attr_set = attr_set_dev[dev_ & 63];
   if (!attr_set) {
     DTC_CUDA(cudaFuncSetAttribute(k_gemm_tc2<AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
     attr_set = true;
@@ -1223,7 +1238,9 @@ template <int AMAJ, int BMAJ>
 static int tc3_launch_t(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB, const CUtensorMap& mBlo, const CUtensorMap& mC,
                         const CUtensorMap& mClo, const TcParams& p,
                         dim3 grid, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device
+  int dev_ = 0; cudaGetDevice(&dev_);
+  bool& attr_set = attr_set_dev[dev_ & 63];
   if (!attr_set) {
     DTC_CUDA(cudaFuncSetAttribute(k_gemm_tc3<AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
     attr_set = true;
@@ -1248,7 +1265,9 @@ template <int AMAJ, int BMAJ>
 static int tc_launch_t(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB, const CUtensorMap& mBlo, const CUtensorMap& mC,
                         const CUtensorMap& mClo, const TcParams& p,
                        dim3 grid, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device
+  int dev_ = 0; cudaGetDevice(&dev_);
+  bool& attr_set = attr_set_dev[dev_ & 63];
   if (!attr_set) {
     DTC_CUDA(cudaFuncSetAttribute(k_gemm_tc<AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set = true;
@@ -1300,13 +1319,19 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   RETURN_IF_ERR(tc_get_map(a.B, a.N, a.K, a.ldb, bmap, &mB));
   if (a.A_lo && !a.a_split) RETURN_IF_ERR(tc_get_map(a.A_lo, a.M, a.K, a.lda, amaj, &mAlo)); else mAlo = mA;
   if (a.B_lo && !a.b_split) RETURN_IF_ERR(tc_get_map(a.B_lo, a.N, a.K, a.ldb, bmap, &mBlo)); else mBlo = mB;
+  // split-K through L2 reductions (default; env DTC_TC_SPLITK=ws restores workspace + reduce kernel): needs the TMA epilogue, no
+  // companion output, a destination whose padding columns may be written (see below).  The summation order of the partial tiles is
+  // then whatever order the CTAs finish in: fp32-round-off differences from run to run.
+  { static int sk = -1; if (sk < 0) { const char* e = getenv("DTC_TC_SPLITK"); sk = (e && e[0] == 'w') ? 0 : 1; }
+    p.splitk_atomic = (sk && splits > 1 && p.direct == 2 && !a.C_lo && (!(a.N & 3) || a.ldc == ((a.N + 3) & ~3))) ? 1 : 0; }
+  if (p.splitk_atomic && !a.accumulate) DTC_CUDA(cudaMemsetAsync(a.C, 0, (size_t)(a.M - 1) * a.ldc * sizeof(float) + (size_t)((a.N + 3) & ~3) * sizeof(float), st));
   CUtensorMap mC = mA, mClo = mA;
   // the TMA unit clips a store at 16-byte granularity: with N % 4 != 0 it writes zeros into the columns up to round4(N).  Harmless when
   // those are this matrix's own padding (ldc == round4(N)); a narrower view into a wider buffer keeps the element-exact staged epilogue
   if (p.direct == 2 && (a.N & 3) && splits == 1 && a.ldc != ((a.N + 3) & ~3)) p.direct = 0;
   if (p.direct == 2) {
     const int n4 = (a.N + 3) & ~3;
-    if (splits > 1) RETURN_IF_ERR(tc_get_out_map(a.ws, a.M, n4, n4, splits, &mC));
+    if (splits > 1 && !p.splitk_atomic) RETURN_IF_ERR(tc_get_out_map(a.ws, a.M, n4, n4, splits, &mC));
     else {
       RETURN_IF_ERR(tc_get_out_map(a.C, a.M, a.N, a.ldc, 0, &mC));
       if (a.C_lo) RETURN_IF_ERR(tc_get_out_map(a.C_lo, a.M, a.N, a.ldc, 0, &mClo));
@@ -1339,7 +1364,7 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   else DTC_FAIL(DTC_ERR_ARG, "gemm_tc: unsupported operand layout");
   if (rc) return rc;
   DTC_CHECK_LAUNCH("k_gemm_tc");
-  if (splits > 1) k_splitk_reduce_launch(a.ws, a.C, a.C_lo, a.M, a.N, a.ldc, splits, a.accumulate ? 1 : 0, st);
+  if (splits > 1 && !p.splitk_atomic) k_splitk_reduce_launch(a.ws, a.C, a.C_lo, a.M, a.N, a.ldc, splits, a.accumulate ? 1 : 0, st);
   dtc_prof_end(st);
   return DTC_OK;
 }

@@ -126,7 +126,8 @@ def test_gemm_wgrad_splitk(M, N, K, mode):
                                                      (19000, 256, 512, 1, 1, 1)])
 def test_gemm_cta_pair_matches_single(M, N, K, a_kc, b_kc, splits):
     """The cta_group::2 kernel (256x128 pair tiles, B halves shared between the two SMs of a TPC) issues the same MMAs in the
-    same order as the single-CTA kernel: results must be bit-identical, including ragged last tiles and split-K partials."""
+    same order as the single-CTA kernel: results must be bit-identical, including ragged last tiles.  Split-K partial tiles are
+    summed by the TMA unit's L2 reduction in the order the CTAs finish: equal to fp32 round-off there."""
     lib = B.lib()
     g = torch.Generator().manual_seed(M + 7 * N + K)
     r4 = lambda x: (x + 3) // 4 * 4
@@ -148,8 +149,13 @@ def test_gemm_cta_pair_matches_single(M, N, K, a_kc, b_kc, splits):
     Ar = (A[:, :K] if a_kc else A[:, :M].T).double()
     Br = (Bm[:, :K] if b_kc else Bm[:, :N].T).double()
     _close(out[1][0][:, :N], Ar @ Br.T, "pair vs fp64")
-    assert torch.equal(out[0][0], out[1][0]), f"pair kernel differs: {(out[0][0] - out[1][0]).abs().max().item()}"
-    assert torch.equal(out[0][1], out[1][1]), "companion output differs"
+    if splits == 1:
+        assert torch.equal(out[0][0], out[1][0]), f"pair kernel differs: {(out[0][0] - out[1][0]).abs().max().item()}"
+        assert torch.equal(out[0][1], out[1][1]), "companion output differs"
+    else:
+        scale = float(out[0][0][:, :N].abs().max())
+        assert float((out[0][0] - out[1][0]).abs().max()) <= 2e-6 * scale, "split-K: pair vs single beyond summation-order round-off"
+        assert bool((out[1][0][:, N:] == 0).all() | (out[1][0][:, N:] == 5.0).all()), "pad columns: zeroed (L2-reduction path) or untouched"
 
 
 # ------------------------------------------------------------------ policy forward
