@@ -34,6 +34,10 @@ struct GemmArgs {
   // tensor-core path only, splits == 1: when set, the epilogue also writes the column sums of every 32-row block of the final C
   // to colsum_part[ceil(M/32)][round4(N)] (the bias gradient of the layer below a dgrad, without re-reading C from HBM)
   float* colsum_part;
+  // alternative (tensor-core path, splits == 1): the epilogue ADDS the column sums of C[:, :colsum_n] into colsum_out[0, colsum_n)
+  // with L2 reductions (red.global.add.f32) - the caller zeroes colsum_out beforehand; no partial buffer, no reduce kernel
+  float* colsum_out; int colsum_n;
+  bool c_zeroed;  // split-K through L2 reductions: C is already zero (skip the launcher's memset)
 };
 // out[n] = sum_b part[b*ld + n], b < nblk (deterministic order)
 int dtc_colsum_part_launch(const float* part, int nblk, int ld, int ncols, float* out, cudaStream_t st);

@@ -41,6 +41,7 @@ struct TcParams {
   const float* bias; const float* act_src; int ld_act; int epi; int accumulate;
   float* ws;
   float* colsum_part;  // [ceil(M/32)][round4(N)] column sums per 32-row block of the final output, or NULL
+  float* colsum_out; int colsum_n;  // or: column sums of C[:, :colsum_n] ADDED into colsum_out (pre-zeroed) with L2 reductions
   int splits, has_alo, has_blo;
   int split_a, split_b;  // 1: that operand's TF32 companion tile is computed in shared memory by the splitter warps (no *_lo array in HBM)
   int neff;   // 1: the MMA of a ragged / narrow n-tile covers only the live columns rounded up to the instruction granularity
@@ -234,7 +235,7 @@ __device__ __forceinline__ void tc_epilogue_tma(const TcParams& p, const CUtenso
   const bool accum = !partial && p.accumulate;
   const bool has_corr = p.has_alo || p.has_blo;
   const bool want_lo = !partial && p.C_lo != nullptr;
-  const bool colsum = p.colsum_part && !partial;
+  const bool colsum = (p.colsum_part || p.colsum_out) && !partial;
   int nchunks = (p.N - n0 + 31) / 32;  // live 32-column chunks of this tile
   nchunks = nchunks > BN / 32 ? BN / 32 : nchunks;
   const int ch_first = (BN / 64) * half;
@@ -346,7 +347,8 @@ __device__ __forceinline__ void tc_epilogue_tma(const TcParams& p, const CUtenso
       float cs = 0.f;
 #pragma unroll
       for (int r = 0; r < 32; ++r) cs += stg[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
-      if (box_ok && gn + lane < n4) p.colsum_part[(size_t)(gm_box >> 5) * n4 + gn + lane] = cs;
+      if (p.colsum_out) { if (box_ok && gn + lane < p.colsum_n) atomicAdd(p.colsum_out + gn + lane, cs); }
+      else if (box_ok && gn + lane < n4) p.colsum_part[(size_t)(gm_box >> 5) * n4 + gn + lane] = cs;
     }
     if (want_lo) {
 #pragma unroll
@@ -490,7 +492,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
             *(reinterpret_cast<float4*>(lrow) + j4) = make_float4(tf32_lo(v[j4 * 4]), tf32_lo(v[j4 * 4 + 1]), tf32_lo(v[j4 * 4 + 2]), tf32_lo(v[j4 * 4 + 3]));
         }
       }
-      if (p.colsum_part && !partial) {
+      if ((p.colsum_part || p.colsum_out) && !partial) {
         // column sums of the 32 rows: butterfly transpose-reduce (31 shuffles), lane l ends up with column l
         if (!row_ok) {
 #pragma unroll
@@ -505,7 +507,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
             v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
           }
         }
-        if (m0 + q * 32 < p.M) p.colsum_part[(size_t)((m0 + q * 32) >> 5) * n4 + gn + lane] = v[0];
+        if (p.colsum_out) { if (m0 + q * 32 < p.M && gn + lane < p.colsum_n) atomicAdd(p.colsum_out + gn + lane, v[0]); }
+        else if (m0 + q * 32 < p.M) p.colsum_part[(size_t)((m0 + q * 32) >> 5) * n4 + gn + lane] = v[0];
       }
       continue;
     }
@@ -564,13 +567,20 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, uint32_t tme
       }
     }
     __syncwarp();
-    if (p.colsum_part && !partial) {  // warp-uniform, outside the per-lane branches above: every lane takes part in the shuffles
+    if ((p.colsum_part || p.colsum_out) && !partial) {  // warp-uniform, outside the per-lane branches above: every lane takes part in the shuffles
       // lanes with the same column block (lane & 7) hold the four row groups: fold them, lanes 0..7 store (n4 covers gn + 3)
       cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
       cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
       cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
       cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
-      if (lane < 8 && gn < p.N && m0 + q * 32 < p.M)
+      if (p.colsum_out) {
+        if (lane < 8 && m0 + q * 32 < p.M) {
+          if (gn < p.colsum_n) atomicAdd(p.colsum_out + gn, cs.x);
+          if (gn + 1 < p.colsum_n) atomicAdd(p.colsum_out + gn + 1, cs.y);
+          if (gn + 2 < p.colsum_n) atomicAdd(p.colsum_out + gn + 2, cs.z);
+          if (gn + 3 < p.colsum_n) atomicAdd(p.colsum_out + gn + 3, cs.w);
+        }
+      } else if (lane < 8 && gn < p.N && m0 + q * 32 < p.M)
         *reinterpret_cast<float4*>(p.colsum_part + (size_t)((m0 + q * 32) >> 5) * n4 + gn) = cs;
     }
   }
@@ -1292,6 +1302,7 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   p.bias = a.bias; p.act_src = a.act_src; p.ld_act = a.ld_act; p.epi = a.epi; p.accumulate = a.accumulate ? 1 : 0;
   p.ws = a.ws;
   p.colsum_part = (splits == 1) ? a.colsum_part : nullptr;
+  p.colsum_out = (splits == 1) ? a.colsum_out : nullptr; p.colsum_n = a.colsum_n;
   p.split_a = a.a_split ? 1 : 0; p.split_b = a.b_split ? 1 : 0;
   p.has_alo = (a.A_lo || a.a_split) ? 1 : 0; p.has_blo = (a.B_lo || a.b_split) ? 1 : 0;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DTC_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
@@ -1324,7 +1335,7 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   // then whatever order the CTAs finish in: fp32-round-off differences from run to run.
   { static int sk = -1; if (sk < 0) { const char* e = getenv("DTC_TC_SPLITK"); sk = (e && e[0] == 'w') ? 0 : 1; }
     p.splitk_atomic = (sk && splits > 1 && p.direct == 2 && !a.C_lo && (!(a.N & 3) || a.ldc == ((a.N + 3) & ~3))) ? 1 : 0; }
-  if (p.splitk_atomic && !a.accumulate) DTC_CUDA(cudaMemsetAsync(a.C, 0, (size_t)(a.M - 1) * a.ldc * sizeof(float) + (size_t)((a.N + 3) & ~3) * sizeof(float), st));
+  if (p.splitk_atomic && !a.accumulate && !a.c_zeroed) DTC_CUDA(cudaMemsetAsync(a.C, 0, (size_t)(a.M - 1) * a.ldc * sizeof(float) + (size_t)((a.N + 3) & ~3) * sizeof(float), st));
   CUtensorMap mC = mA, mClo = mA;
   // the TMA unit clips a store at 16-byte granularity: with N % 4 != 0 it writes zeros into the columns up to round4(N).  Harmless when
   // those are this matrix's own padding (ldc == round4(N)); a narrower view into a wider buffer keeps the element-exact staged epilogue

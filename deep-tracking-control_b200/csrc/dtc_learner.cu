@@ -403,6 +403,14 @@ extern "C" int dtc_learner_debug_buffer(dtc_learner* l, const char* name, float*
 // ------------------------------------------------------------------ GEMM helpers
 #define RET_IF(x) RETURN_IF_ERR(x)
 
+// Gradient buffer zeroed once at the start of every optimizer step (default; env DTC_GRAD_PREZERO=0 restores per-GEMM handling): the
+// split-K weight gradients and the bias column sums are then ADDED into it by L2 reductions straight from the GEMM epilogues - no
+// per-GEMM memset, no partial-sum buffers, no reduce kernels.
+static int g_prezero = -1;
+static bool grads_prezeroed() {
+  if (g_prezero < 0) { const char* e = getenv("DTC_GRAD_PREZERO"); g_prezero = (e && e[0] == '0') ? 0 : 1; }
+  return g_prezero != 0;
+}
 // need_lo = false for outputs no GEMM reads (reconstructions, heads, latent statistics): their TF32 companion is never used
 static int fwd(dtc_learner* l, int id, const float* A, int lda, float* C, int ldc, int act, int M, cudaStream_t st, bool need_lo = true) {
   const Layer& L = g_layers[id];
@@ -425,6 +433,7 @@ static int wgrad(dtc_learner* l, int id, const float* dY, int ldy, const float* 
   g.B = X; g.ldb = ldx; g.b_kc = false;
   g.A_lo = lo_of(l, dY); g.B_lo = lo_of(l, X);
   g.a_split = g.b_split = split_sm();
+  g.c_zeroed = grads_prezeroed();
   g.C = l->grads + L.w; g.ldc = L.ld; g.M = L.out; g.N = L.in; g.K = M;
   g.epi = EPI_STORE;
   g.splits = dtc_gemm_pick_splits(L.out, L.in, M);
@@ -448,11 +457,14 @@ static int dgrad(dtc_learner* l, int id, const float* dY, int ldy, float* dX, in
   g.act_src = act_src; g.ld_act = ld_act; g.epi = epi; g.accumulate = accumulate;
   g.splits = 1;
   const bool fuse = bias_layer >= 0 && dtc_gemm_mode() == 1 && dtc_gemm_tc_eligible(g) && g_layers[bias_layer].out <= ncols && ncols <= 768;
-  if (fuse) g.colsum_part = l->cspart[slot];
+  if (fuse) {
+    if (grads_prezeroed()) { g.colsum_out = l->grads + g_layers[bias_layer].b; g.colsum_n = g_layers[bias_layer].out; }  // added in L2
+    else g.colsum_part = l->cspart[slot];
+  }
   RET_IF(dtc_gemm_launch(g, st));
   if (fuse) {
     const Layer& Lb = g_layers[bias_layer];
-    RET_IF(dtc_colsum_part_launch(l->cspart[slot], (M + 31) / 32, round4(ncols), Lb.out, l->grads + Lb.b, st));
+    if (!grads_prezeroed()) RET_IF(dtc_colsum_part_launch(l->cspart[slot], (M + 31) / 32, round4(ncols), Lb.out, l->grads + Lb.b, st));
     l->bias_done[bias_layer] = true;
   }
   return DTC_OK;
@@ -1386,6 +1398,7 @@ extern "C" int dtc_vae_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
   if (!hp) DTC_FAIL(DTC_ERR_ARG, "dtc_vae_step: null hparams");
   cudaStream_t st = (cudaStream_t)stream;
   l->last_M = M;
+  if (grads_prezeroed()) DTC_CUDA(cudaMemsetAsync(l->grads, 0, (size_t)g_vae_end * sizeof(float), st));  // [decoders | shared encoders]
   const float* hist = batch->hist + row0 * LD_HIST;
   const float* priv_a = batch->priv_a + row0 * LD_PRIVA;
   const float* xc = batch->xc + row0 * LD_XC;
@@ -1451,6 +1464,8 @@ extern "C" int dtc_ppo_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
   if (!hp) DTC_FAIL(DTC_ERR_ARG, "dtc_ppo_step: null hparams");
   cudaStream_t st = (cudaStream_t)stream;
   l->last_M = M;
+  if (grads_prezeroed())  // [shared encoders | actor, critic, std | piggy-back scalars]
+    DTC_CUDA(cudaMemsetAsync(l->grads + g_pol_begin, 0, (size_t)(g_off_piggy + NPIGGY - g_pol_begin) * sizeof(float), st));
   const float* hist = batch->hist + row0 * LD_HIST;
   const float* priv_a = batch->priv_a + row0 * LD_PRIVA;
   const float* xc = batch->xc + row0 * LD_XC;
