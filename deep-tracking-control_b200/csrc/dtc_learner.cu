@@ -853,56 +853,51 @@ __global__ void __launch_bounds__(128) k_ppo_loss(int M, float inv_rows, const f
   }
 }
 
-// VAE losses with per-row reductions (ppo.py:213-247): reconstruction, velocity, KL.  Writes dREC and the direct terms of
-// dML.  One thread per row.
-__global__ void __launch_bounds__(128) k_vae_loss_rows(int M, float inv_rows, const float* __restrict__ REC,
+// VAE losses (ppo.py:213-247): reconstruction, velocity, KL.  Writes dREC and the direct terms of dML.  Element-wise over the
+// [M, 56] and [M, 36] arrays with coalesced accesses (one thread per row walked 224-byte strides: 0.6 ms under the GEMMs); every
+// term of the three sums belongs to exactly one element, fp32 products summed in fp64.
+__global__ void __launch_bounds__(256) k_vae_loss_rows(int M, float inv_rows, const float* __restrict__ REC,
                                                        const float* __restrict__ next_obs, const float* __restrict__ ML,
                                                        const float* __restrict__ xc, float* __restrict__ dREC,
                                                        float* __restrict__ dML, double* __restrict__ stats) {
   __shared__ double sh[32];
-  const int row = blockIdx.x * 128 + threadIdx.x;
   double s_rec = 0.0, s_vel = 0.0, s_kld = 0.0;
-  if (row < M) {
-    const float* rec = REC + (size_t)row * 56;
-    const float* nx = next_obs + (size_t)row * 56;
-    float* dr = dREC + (size_t)row * 56;
-    float acc = 0.f;
-    const float cr = 2.0f * inv_rows / 53.0f;
-    for (int j = 0; j < 53; ++j) {
-      float d = rec[j] - nx[j];
-      acc += d * d;
-      dr[j] = cr * d;
+  const float cr = 2.0f * inv_rows / 53.0f, cv = 2.0f * inv_rows / 3.0f;
+  const long long stride = (long long)gridDim.x * 256, t0 = blockIdx.x * 256ll + threadIdx.x;
+  for (long long e4 = t0; e4 < (long long)M * 14; e4 += stride) {  // 56 = 14 float4 per row, rows 16-byte aligned
+    const int j = (int)(e4 % 14) * 4;
+    const float4 r = *reinterpret_cast<const float4*>(REC + e4 * 4), x = *reinterpret_cast<const float4*>(next_obs + e4 * 4);
+    float d[4] = {r.x - x.x, r.y - x.y, r.z - x.z, r.w - x.w};
+    if (j + 3 >= 53) d[3] = 0.f;
+    if (j + 2 >= 53) d[2] = 0.f;
+    if (j + 1 >= 53) d[1] = 0.f;
+    s_rec += (double)(d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3]);
+    *reinterpret_cast<float4*>(dREC + e4 * 4) = make_float4(cr * d[0], cr * d[1], cr * d[2], cr * d[3]);
+  }
+  for (long long e = t0; e < (long long)M * LD_ML; e += stride) {
+    const int row = (int)(e / LD_ML), j = (int)(e - (long long)row * LD_ML);
+    if (j >= ML_LV + 16) continue;  // the pad column
+    const float v = ML[e];
+    if (j < 3) {
+      const float dv = v - xc[(size_t)row * LD_XC + XC_BV + j];
+      s_vel += (double)(dv * dv);
+      dML[e] = cv * dv;
+    } else if (j < ML_LV) {
+      s_kld += (double)(-v * v);
+      dML[e] = 4.0f * inv_rows * v;
+    } else {
+      const float ex = expf(v);
+      s_kld += (double)(1.0f + v - ex);
+      dML[e] = -2.0f * inv_rows * (1.0f - ex);
     }
-    dr[53] = dr[54] = dr[55] = 0.f;
-    s_rec = (double)(acc / 53.0f);
-    const float* ml = ML + (size_t)row * LD_ML;
-    float* d = dML + (size_t)row * LD_ML;
-    const float* bv = xc + (size_t)row * LD_XC + XC_BV;
-    float vel = 0.f;
-    const float cv = 2.0f * inv_rows / 3.0f;
-    for (int j = 0; j < 3; ++j) {
-      float e = ml[j] - bv[j];
-      vel += e * e;
-      d[j] = cv * e;
-    }
-    s_vel = (double)(vel / 3.0f);
-    float ksum = 0.f;
-    for (int j = 0; j < 16; ++j) {
-      float m = ml[3 + j], lv = ml[ML_LV + j];
-      float ex = expf(lv);
-      ksum += 1.0f + lv - m * m - ex;
-      d[3 + j] = 4.0f * inv_rows * m;
-      d[ML_LV + j] = -2.0f * inv_rows * (1.0f - ex);
-    }
-    s_kld = (double)(-0.5f * ksum);
   }
   s_rec = block_sum(s_rec, sh);
   s_vel = block_sum(s_vel, sh);
   s_kld = block_sum(s_kld, sh);
   if (threadIdx.x == 0) {
-    atomicAdd(&stats[ST_RECONS], s_rec * (double)inv_rows);
-    atomicAdd(&stats[ST_VEL], s_vel * (double)inv_rows);
-    atomicAdd(&stats[ST_KLD], s_kld * (double)inv_rows);
+    atomicAdd(&stats[ST_RECONS], s_rec / 53.0 * (double)inv_rows);
+    atomicAdd(&stats[ST_VEL], s_vel / 3.0 * (double)inv_rows);
+    atomicAdd(&stats[ST_KLD], -0.5 * s_kld * (double)inv_rows);
   }
 }
 // height reconstruction loss (ppo.py:218-223): mse(terrain_decoder(l_t), priv[:, 696:]) and its gradient
@@ -1423,7 +1418,7 @@ extern "C" int dtc_vae_step(dtc_learner* l, const dtc_storage* batch, int64_t ro
   RET_IF(fwd(l, TD2, l->U1, 512, l->U2, 512, 1, M, st));
   RET_IF(fwd(l, TD4, l->U2, 512, l->HR, 696, 0, M, st, false));
   // losses and output gradients (ppo.py:213-247)
-  k_vae_loss_rows<<<ceil_div(M, 128), 128, 0, sc>>>(M, inv_rows, l->REC, next_obs, l->ML, xc, l->dREC, l->dML, l->stats);
+  k_vae_loss_rows<<<grid1d((long long)M * 14, 256, 148 * 2), 256, 0, sc>>>(M, inv_rows, l->REC, next_obs, l->ML, xc, l->dREC, l->dML, l->stats);
   DTC_CHECK_LAUNCH("k_vae_loss_rows");
   RET_IF(split_lo(l->dREC, lo_of(l, l->dREC), (int64_t)M * 56, sc));
   k_vae_loss_height<<<grid1d((long long)M * 174, 256), 256, 0, st>>>(M, 1.0f / ((float)M * 693.0f), l->HR, xc, l->dHR, lo_of(l, l->dHR),
