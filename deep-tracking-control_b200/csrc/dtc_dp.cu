@@ -7,7 +7,7 @@
 //   collect : waits for every peer's flagB, copies the exchange buffer (now the full sum) back into grads
 // Every element is summed by exactly one rank in a fixed order, so all replicas receive bit-identical gradients (NCCL's ring / tree
 // order is not specified).  When a rank passes collect, every peer has finished reading this rank's buffer and writing into it, so
-// the next publish may overwrite it.  A spin that exceeds ~2 s (a rank that never arrives) sets an error word instead of hanging the GPU.
+// the next publish may overwrite it.  A spin that exceeds ~20 s (a rank that never arrives) sets an error word instead of hanging the GPU.
 //
 // Registered, in-place variant (the one training uses): dtc_dp_register maps every rank's GRADIENT BUFFER itself into the others
 // (IPC handle of the allocation that contains it + offset), and the all-reduce is ONE cooperative kernel with no staging copies:
@@ -65,7 +65,7 @@ __device__ __forceinline__ void dp_wait_all(uint32_t* own_flags, int which, int 
   if ((int)threadIdx.x < world) {  // one thread per peer: the polls run side by side
     const long long t0 = clock64();
     while ((int32_t)(dp_load_acquire_sys(own_flags + which + threadIdx.x) - epoch) < 0) {
-      if (clock64() - t0 > 4000000000ll) { own_flags[DP_ERROR] = 1u; break; }  // ~2 s: give up rather than hang the device
+      if (clock64() - t0 > 40000000000ll) { own_flags[DP_ERROR] = 1u; break; }  // ~20 s: give up rather than hang the device
       __nanosleep(20);
     }
   }
@@ -305,7 +305,7 @@ extern "C" int dtc_dp_error(dtc_dp* d, void* stream) {
   uint32_t e = 0;
   if (cudaMemcpyAsync(&e, d->flags[d->rank] + DP_ERROR, sizeof(e), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess) return DTC_ERR_CUDA;
   if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return DTC_ERR_CUDA;
-  if (e) DTC_FAIL(DTC_ERR_STATE, "dtc_dp: a rank waited more than ~2 s for a peer's flag (mismatched all-reduce sequence?)");
+  if (e) DTC_FAIL(DTC_ERR_STATE, "dtc_dp: a rank waited more than ~20 s for a peer's flag (mismatched all-reduce sequence?)");
   return DTC_OK;
 }
 extern "C" void dtc_dp_destroy(dtc_dp* d) {

@@ -361,7 +361,7 @@ int dtc_terrain_paint(int32_t rows, int32_t cols, int32_t border_px, int32_t len
  * `stream` - publish, reduce-scatter + all-gather through P2P loads / stores, collect - with device-side flag handshakes only: no host
  * synchronisation, no NCCL.  Every element is summed by one rank in rank order: all replicas get bit-identical sums.  n % 4 == 0,
  * data 16-byte aligned, n <= max_floats; all ranks must issue the same sequence of calls.  dtc_dp_error synchronises `stream` and
- * reports whether any wait ever exceeded ~2 s (then the data is not a sum and the run should stop). */
+ * reports whether any wait ever exceeded ~20 s (then the data is not a sum and the run should stop). */
 typedef struct dtc_dp dtc_dp;
 int dtc_dp_create(int32_t rank, int32_t world, int64_t max_floats, dtc_dp** out);
 int dtc_dp_handles(dtc_dp* d, void* buf_handle64, void* flags_handle64);
