@@ -583,6 +583,7 @@ extern "C" int dtc_env_create(const dtc_env_config* cfg, dtc_env** out) {
   e->cfg = *cfg;
   e->bound = false;
   e->min3 = nullptr;
+  e->gtab = nullptr;
   e->min3_bytes = 0;
   e->min3_map_ok = false;
   e->step_base = nullptr;
@@ -596,6 +597,7 @@ extern "C" void dtc_env_destroy(dtc_env* e) {
   if (!e) return;
   cudaFree(e->d_cfg);
   if (e->min3) cudaFree(e->min3);
+  if (e->gtab) cudaFree(e->gtab);
   delete e;
 }
 extern "C" int dtc_env_bind(dtc_env* e, const dtc_env_buffers* buf) {

@@ -12,5 +12,6 @@ struct dtc_env {
   CUtensorMap min3_map;   // variant 6: 2-D tensor map of min3 (box = one 42 x 48-cell patch) for the TMA patch loads
   bool min3_map_ok;
   const int64_t* step_base;  // optional device-side counter added to every launch's step argument (dtc_env_set_step_base)
+  float4* gtab;              // variant 6 with 7 CTAs / SM: grid-point table in global memory (dtc_foothold.cu: k_v6_gtab)
 };
 int dtc_env_build_min3(dtc_env* e);  // dtc_foothold.cu

@@ -965,10 +965,13 @@ struct __align__(128) V6Warp {
   float gc[NP + 3];              // clamped relative heights
   uint64_t mbar;                 // completion barrier of the patch load
 };
-struct __align__(16) V6Cta {
+// GG: the grid-point table lives in global memory (read through L1 with __ldg) instead of shared memory - 5.6 KB less per CTA, which
+// is what lets a seventh CTA fit on an SM (CPS = 7)
+template <bool GG>
+struct __align__(16) V6CtaT {
   V6Warp w[V6_WARPS];
   V6Rec rec[V6_BATCH];
-  float4 gtab[V6_NK / 2][32];    // (gx_k, gx_k+1, gy_k, gy_k+1) of the sample pair p = 32 k + lane, k even (p clamped to 692)
+  float4 gtab[GG ? 1 : V6_NK / 2][32];    // (gx_k, gx_k+1, gy_k, gy_k+1) of the sample pair p = 32 k + lane, k even (p clamped to 692)
   float gx[GXN + 3], gy[GYN + 3];
 };
 
@@ -1046,9 +1049,10 @@ __device__ __forceinline__ void v6_wait_patch(V6Warp& W, uint32_t parity) {
 template <bool SEP, int CPS>
 __global__ void __launch_bounds__(V6_WARPS * 32, CPS)
 k_foothold_v6(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const int16_t* __restrict__ min3, const V5Params P, int per_cta,
-              const __grid_constant__ CUtensorMap tmap) {
+              const __grid_constant__ CUtensorMap tmap, const float4* __restrict__ gtab_g) {
+  constexpr bool GG = CPS >= 7;
   extern __shared__ __align__(128) uint8_t v6_smem_raw[];
-  V6Cta& S = *reinterpret_cast<V6Cta*>(v6_smem_raw);
+  V6CtaT<GG>& S = *reinterpret_cast<V6CtaT<GG>*>(v6_smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   V6Warp& W = S.w[warp];
   const int N = cfg->num_envs;
@@ -1065,10 +1069,13 @@ k_foothold_v6(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const i
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   uint32_t patch_phase = 0;  // parity of the next patch load to complete on this warp's barrier
-  for (int i = threadIdx.x; i < (V6_NK / 2) * 32; i += V6_WARPS * 32) {
-    const int pa_ = min(64 * (i >> 5) + (i & 31), NP - 1), pb_ = min(pa_ + 32, NP - 1);
-    S.gtab[i >> 5][i & 31] = make_float4(cfg->grid_x[pa_ / GYN], cfg->grid_x[pb_ / GYN], cfg->grid_y[pa_ % GYN], cfg->grid_y[pb_ % GYN]);
+  if (!GG) {
+    for (int i = threadIdx.x; i < (V6_NK / 2) * 32; i += V6_WARPS * 32) {
+      const int pa_ = min(64 * (i >> 5) + (i & 31), NP - 1), pb_ = min(pa_ + 32, NP - 1);
+      S.gtab[i >> 5][i & 31] = make_float4(cfg->grid_x[pa_ / GYN], cfg->grid_x[pb_ / GYN], cfg->grid_y[pa_ % GYN], cfg->grid_y[pb_ % GYN]);
+    }
   }
+  auto gtab_at = [&](int kk) -> float4 { return GG ? __ldg(gtab_g + kk * 32 + lane) : S.gtab[GG ? 0 : kk][lane]; };
   // window slots of the per-leg search (see variant 5): the 7x7 lattice window minus its corners = 45 candidates; two legs share
   // three passes (slots 0..31 of each leg, then slots 32..44 of both on lanes 0..12 / 16..28)
   auto slot_offset = [](int s, int& wi, int& wj) {
@@ -1114,7 +1121,7 @@ k_foothold_v6(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const i
 #pragma unroll
         for (int kk = 0; kk < V6_NK / 2; ++kk) {
           const int k = 2 * kk;
-          const float4 g = S.gtab[kk][lane];
+          const float4 g = gtab_at(kk);
           const float2 gx2 = make_float2(g.x, g.y), gy2 = make_float2(g.z, g.w);
           const float2 qx = f2_fma(gx2, ca2, f2_fma(gy2, nsa2, qx02));
           const float2 qy = f2_fma(gx2, sa2, f2_fma(gy2, ca2, qy02));
@@ -1166,7 +1173,7 @@ k_foothold_v6(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const i
             const int k = __ffs(slowm) - 1;
             slowm &= slowm - 1u;
             const int p = 32 * k + lane;
-            const float4 g = S.gtab[k >> 1][lane];
+            const float4 g = gtab_at(k >> 1);
             const float gx = (k & 1) ? g.y : g.x, gy = (k & 1) ? g.w : g.z;
             const float qx = fmaf(gx, R.ca, fmaf(gy, -R.sa, R.qx0)), qy = fmaf(gx, R.sa, fmaf(gy, R.ca, R.qy0));
             const uint32_t off = __float_as_uint(qx + 12582912.0f) * (uint32_t)(V6_PC * 2) + __float_as_uint(qy + 12582912.0f) * 2u + kbase;
@@ -1193,7 +1200,7 @@ k_foothold_v6(const dtc_env_config* __restrict__ cfg, dtc_env_buffers b, const i
         for (int k = 0; k < V6_NK; ++k) {
           const int p = 32 * k + lane;
           if (p < NP) {
-            const float4 g = S.gtab[k >> 1][lane];
+            const float4 g = gtab_at(k >> 1);
             const float gx = (k & 1) ? g.y : g.x, gy = (k & 1) ? g.w : g.z;
             const float mh = v5_exact_sample(min3, rows, cols, gx, gy, yz, yw, root_x, root_y, border, hscale, vscale);
             mh_out[p] = mh;
@@ -1339,7 +1346,7 @@ static int launch_v6(dtc_env* e, const V5Params& P, cudaStream_t st) {
   int dev = 0;
   DTC_CUDA(cudaGetDevice(&dev));
   int& sms = sms_dev[dev & 63];
-  const int smem = (int)sizeof(V6Cta);
+  const int smem = (int)sizeof(V6CtaT<(CPS >= 7)>);
   if (!sms) {
     int ctas = 0;
     DTC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1352,12 +1359,12 @@ static int launch_v6(dtc_env* e, const V5Params& P, cudaStream_t st) {
   // into gridDim.x contiguous chunks of floor / ceil (N / gridDim.x) environments
   const int grid = max(1, min(sms * CPS, ceil_div(N, 2 * V6_WARPS)));
   if (!e->min3_map_ok) DTC_FAIL(DTC_ERR_STATE, "dtc_foothold_step: tensor map of the min3 table missing (dtc_env_bind builds it)");
-  k_foothold_v6<SEP, CPS><<<grid, V6_WARPS * 32, smem, st>>>(e->d_cfg, e->buf, e->min3, P, ceil_div(N, grid), e->min3_map);
+  k_foothold_v6<SEP, CPS><<<grid, V6_WARPS * 32, smem, st>>>(e->d_cfg, e->buf, e->min3, P, ceil_div(N, grid), e->min3_map, e->gtab);
   return DTC_OK;
 }
 static int v6_cps() {  // resident CTAs per SM the kernel is compiled for (env DTC_FH_CPS = 4 | 5 | 6, tuning knob)
   static int cps = 0;
-  if (!cps) { const char* s = getenv("DTC_FH_CPS"); cps = s ? atoi(s) : 6; if (cps < 4 || cps > 6) cps = 6; }
+  if (!cps) { const char* s = getenv("DTC_FH_CPS"); cps = s ? atoi(s) : 6; if (cps < 4 || cps > 7) cps = 6; }
   return cps;
 }
 template <bool SEP>
@@ -1365,6 +1372,7 @@ static int launch_v6_any(dtc_env* e, const V5Params& P, cudaStream_t st) {
   switch (v6_cps()) {
     case 4: return launch_v6<SEP, 4>(e, P, st);
     case 5: return launch_v6<SEP, 5>(e, P, st);
+    case 7: return launch_v6<SEP, 7>(e, P, st);
     default: return launch_v6<SEP, 6>(e, P, st);
   }
 }
@@ -1379,8 +1387,17 @@ __global__ void __launch_bounds__(256) k_min3_map(const int16_t* __restrict__ H,
   }
 }
 
+__global__ void k_v6_gtab(const dtc_env_config* __restrict__ cfg, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (V6_NK / 2) * 32) return;
+  const int pa_ = min(64 * (i >> 5) + (i & 31), NP - 1), pb_ = min(pa_ + 32, NP - 1);
+  out[i] = make_float4(cfg->grid_x[pa_ / GYN], cfg->grid_x[pb_ / GYN], cfg->grid_y[pa_ % GYN], cfg->grid_y[pb_ % GYN]);
+}
 // (re)builds the min3 map of variant 5 from the bound heightmap; synchronous, called from dtc_env_bind
 int dtc_env_build_min3(dtc_env* e) {
+  if (!e->gtab) DTC_CUDA(cudaMalloc(&e->gtab, (V6_NK / 2) * 32 * sizeof(float4)));
+  k_v6_gtab<<<2, 256>>>(e->d_cfg, e->gtab);
+  DTC_CHECK_LAUNCH("k_v6_gtab");
   const size_t bytes = (size_t)e->cfg.map_rows * e->cfg.map_cols * sizeof(int16_t);
   if (e->min3 && e->min3_bytes != bytes) { cudaFree(e->min3); e->min3 = nullptr; }
   if (!e->min3) { DTC_CUDA(cudaMalloc(&e->min3, bytes)); e->min3_bytes = bytes; }
