@@ -26,7 +26,7 @@ root/dof/contact/rigid-body tensors (SURVEY.md 8d distributions).
            minibatch on every rank: critic gradients must agree to fp32 round-off.
 `cpu_baseline`: the CPU restatement of the reference (oracle/, pinned to golden vectors of the unmodified reference) on the host
            cores, bounded sample; `--impl reference` runs the same as its own arm (same `config`, the sample in `cpu_baseline`).
-           The port runs 1.245x faster than the unmodified reference on the same inputs (tools/port_vs_reference.py, measured in
+           The port runs 1.245x faster than the unmodified reference on the same inputs (tests/tools/port_vs_reference.py, measured in
            the build container where /root/reference exists: 3047 vs 2448 env-steps/s at 1024 envs on 8 cores).
 Timing   : CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  The per-iteration
            working set (717 MB rollout storage + its gathered copy) exceeds the 126 MB L2, so no explicit flush is used.
@@ -50,7 +50,7 @@ T_STEPS = 24
 # L2-resident when the kernel ends)
 TRAFFIC_GEMM_TC2 = 162128896
 TRAFFIC_FOOTHOLD_16384 = 11802112  # profiles/r2_foothold_v6_ncu_raw.csv: 10.82 MB read + 0.98 MB written
-PORT_OVER_REFERENCE = 1.245  # tools/port_vs_reference.py (build container, 1024 envs, 8 cores)
+PORT_OVER_REFERENCE = 1.245  # tests/tools/port_vs_reference.py (build container, 1024 envs, 8 cores)
 BYTES_STATE_PER_ENV = (13 + 12 * 2 + 17 * 3 + 17 * 13) * 4  # root, dof, contact, rigid body
 
 
@@ -462,7 +462,7 @@ def run_reference(args):
     sample = (f"each step = one full iteration (24 env steps + GAE + 5x4 minibatch update) on a bounded sample of {n} of the config's "
               f"{args.envs} environments ({n * T_STEPS} env-steps), torch CPU with {cores} threads; oracle/ = CPU restatement of the reference "
               f"pinned to golden vectors of the unmodified reference, which it outruns by {PORT_OVER_REFERENCE}x on the same inputs "
-              f"(tools/port_vs_reference.py)")
+              f"(tests/tools/port_vs_reference.py)")
     out = {"impl": "reference", "metric": "env-steps/sec (foothold+obs+PPO, sim stubbed)", "value": round(v, 1), "unit": "env-steps/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -1,6 +1,6 @@
 """Diagnostic: step-by-step gradient comparison of PPO.update() against the oracle."""
 import ctypes as C, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import dtc_b200
 from dtc_b200 import _lib as B

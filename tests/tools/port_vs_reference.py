@@ -2,7 +2,7 @@
 oracle port (oracle/*.py, what bench.py's CPU arm times) on the same synthetic states - the ratio that maps the port's
 env-steps/s to the real reference's.  /root/reference does not exist on the GPU box, so this number is measured here and quoted.
 
-    python tools/port_vs_reference.py [N=1024] [iters=2]
+    python tests/tools/port_vs_reference.py [N=1024] [iters=2]
 """
 import contextlib
 import io
@@ -15,7 +15,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import dtc_b200  # noqa: E402,F401
 from dtc_b200 import sim_stub  # noqa: E402
