@@ -1,6 +1,6 @@
 """Diagnostic: run one VAE step on both GEMM engines and report the first activation / gradient buffer that differs."""
 import ctypes as C, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import dtc_b200
 from dtc_b200 import _lib as B
