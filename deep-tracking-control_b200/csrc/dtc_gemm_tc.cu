@@ -233,7 +233,7 @@ __device__ __forceinline__ void tc_epilogue_tma(const TcParams& p, const CUtenso
   const int epi = partial ? EPI_STORE : p.epi;
   const bool has_bias = epi >= EPI_BIAS && epi <= EPI_BIAS_ELU, has_src = epi == EPI_DRELU || epi == EPI_DELU;
   const bool accum = !partial && p.accumulate;
-  const bool has_corr = p.has_alo || p.has_blo;
+  const bool has_corr = (p.has_alo || p.has_blo) && !(p.debug & 16);
   const bool want_lo = !partial && p.C_lo != nullptr;
   const bool colsum = (p.colsum_part || p.colsum_out) && !partial;
   int nchunks = (p.N - n0 + 31) / 32;  // live 32-column chunks of this tile
@@ -889,7 +889,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       const int buf = j & 1;
       tc_mbar_wait(&bar_acc_empty[buf], ((j >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this accumulator set
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t d_main = tmem + (uint32_t)buf * (2 * TC_BN), d_corr = d_main + TC_BN;
+      const uint32_t d_main = tmem + (uint32_t)buf * (2 * TC_BN), d_corr = (p.debug & 16) ? d_main : d_main + TC_BN;  // 16: precision experiment, one accumulator
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % TC2_STAGES;
         tc_mbar_wait((p.split_a | p.split_b) ? &bar_split[s] : &bar_full[s], (it / TC2_STAGES) & 1);
@@ -903,8 +903,9 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
           const uint32_t ka = k8 * tc_desc_k8_step<AMAJ>(), kb8 = k8 * tc_desc_k8_step<BMAJ>();
           const uint32_t first = (kb == kb0 && k8 == 0) ? 0u : 1u;
           tc_mma_lh<2>(d_main, a0 + ka, ahi, b0 + kb8, bhi, idesc, first);
-          if (p.has_alo) tc_mma_lh<2>(d_corr, al0 + ka, ahi, b0 + kb8, bhi, idesc, first);
-          if (p.has_blo) tc_mma_lh<2>(d_corr, a0 + ka, ahi, bl0 + kb8, bhi, idesc, (first || p.has_alo) ? 1u : 0u);
+          const uint32_t firstc = (p.debug & 16) ? 1u : first;  // shared accumulator: the correction products always accumulate
+          if (p.has_alo) tc_mma_lh<2>(d_corr, al0 + ka, ahi, b0 + kb8, bhi, idesc, firstc);
+          if (p.has_blo) tc_mma_lh<2>(d_corr, a0 + ka, ahi, bl0 + kb8, bhi, idesc, (firstc || p.has_alo) ? 1u : 0u);
         }
         tc2_commit(&bar_empty[s]);  // frees the stage in both CTAs once these MMAs have read it
       }
