@@ -130,8 +130,10 @@ class Terrain:
         self.cfg, self.num_robots, self.type = cfg, num_robots, cfg.mesh_type
         if self.type in ["none", "plane"]:
             return
-        self.device = torch.device(device)
-        if self.device.type != "cuda":
+        # device=None: lay the sub-terrains out (every numpy draw happens, `sub_terrains` holds the rectangle lists) but do not
+        # rasterise - there is no height field then.  Host-logic tests use it; anything else needs a CUDA device.
+        self.device = None if device is None else torch.device(device)
+        if self.device is not None and self.device.type != "cuda":
             raise B.DtcError("Terrain rasterises on a CUDA device only (no CPU fallback)")
         self.env_length, self.env_width = cfg.terrain_length, cfg.terrain_width
         self.proportions = [np.sum(cfg.terrain_proportions[:i + 1]) for i in range(len(cfg.terrain_proportions))]
@@ -148,7 +150,13 @@ class Terrain:
             raise NotImplementedError("cfg.terrain.selected (eval of a terrain_utils function name) is not supported")
         else:
             self.randomized_terrain()
-        self._paint()
+        if self.device is not None:
+            self._paint()
+
+    @property
+    def sub_terrains(self):
+        """[(background, [(x0, x1, y0, y1, h), ...]), ...] in row-major (row, col) order: what dtc_terrain_paint receives."""
+        return [(t.background, list(t.rects)) for t in self._subs]
 
     # ------------------------------------------------------------------ layout (terrain.py:45-63)
     def randomized_terrain(self):

@@ -1,5 +1,6 @@
 """Host-side helpers that need no GPU: the trajectory split / pad / unpad pair around the GRU `Memory`
 (reference rsl_rl/rsl_rl/utils/utils.py:33-71) against a step-by-step Python construction, and the GRU parameter count."""
+import numpy as np
 import torch
 
 import dtc_b200  # noqa: F401
@@ -85,3 +86,91 @@ def test_terrain_description_reproduces_the_host_generator():
             for x, y in zip(rng.integers(0, px, 2000), rng.integers(0, px, 2000)):
                 assert _terrain_cell(subs[s], tabs[s], int(x), int(y), px) == int(hs[b + i * px + x, b + j * px + y]), (kind, seed, s, x, y)
     assert not hs[:b].any() and not hs[:, :b].any()  # flat border
+
+
+# ------------------------------------------------------------------ host logic of the drop-in boundary (no GPU)
+def test_terrain_host_layout_reproduces_reference_maps(golden_dir):
+    """N3 on the CPU: the product `Terrain` class (same numpy draws, generators recording rectangle lists) against the heightmaps
+    recorded from the unmodified reference class - the rectangles are painted here with numpy, as `dtc_terrain_paint` does on the
+    device (last rectangle wins)."""
+    import os
+    from dtc_b200.legged_gym.utils.terrain import Terrain
+    from tests.test_oracle_golden import TERRAIN_CASES, terrain_cfg
+    for name, (seed, ov) in sorted(TERRAIN_CASES.items()):
+        G = np.load(os.path.join(golden_dir, f"terrain_{name}.npz"))
+        cfg = terrain_cfg(ov)
+        np.random.seed(seed)
+        t = Terrain(cfg, 16, device=None)  # layout only
+        hf = np.zeros((t.tot_rows, t.tot_cols), dtype=np.int16)
+        lp, wp, b = t.length_per_env_pixels, t.width_per_env_pixels, t.border
+        subs = t.sub_terrains
+        assert len(subs) == cfg.num_rows * cfg.num_cols
+        for s, (background, rects) in enumerate(subs):
+            i, j = divmod(s, cfg.num_cols)
+            tile = np.full((lp, wp), background, dtype=np.int16)
+            for x0, x1, y0, y1, h in rects:
+                tile[x0:x1, y0:y1] = h
+            hf[b + i * lp:b + (i + 1) * lp, b + j * wp:b + (j + 1) * wp] = tile
+        assert np.array_equal(hf, G["height_field_raw"]), (name, int((hf != G["height_field_raw"]).sum()))
+
+
+def test_cfg_resolution_follows_the_reference_rules():
+    """legged_gym/envs/base/cfg_resolve.py against the values LeggedRobot._parse_cfg / _prepare_reward_function / _init_buffers derive
+    from the Lite3 DTC config (legged_robot.py:929-952, 839-866, 1098-1109), and the loud failures for what the kernels cannot do."""
+    import copy
+    import pytest as _pt
+    from dtc_b200.legged_gym.envs import Lite3DTCCfg
+    from dtc_b200.legged_gym.envs.base.cfg_resolve import CfgError, resolve
+    from dtc_b200 import lite3 as L
+    r = resolve(Lite3DTCCfg())
+    assert abs(r.dt - 4 * 0.005) < 1e-12 and r.max_episode_length == int(np.ceil(20.0 / r.dt))
+    assert r.resampling_steps == int(10.0 / r.dt) and r.push_interval == int(np.ceil(15.0 / r.dt))
+    assert len(r.p_gains) == 12 and len(r.d_gains) == 12 and all(p > 0 for p in r.p_gains)
+    # reward scales are multiplied by dt and zero scales drop out of the episode sums
+    ref = {k: v * r.dt for k, v in L.REWARD_SCALES.items() if v != 0.0}
+    assert set(r.reward_scales) == set(ref)
+    assert all(abs(r.reward_scales[k] - ref[k]) <= 1e-12 * max(1.0, abs(ref[k])) for k in ref)
+    # edits are honoured ...
+    cfg = Lite3DTCCfg()
+    cfg.rewards = copy.deepcopy(cfg.rewards)
+
+    class _S(cfg.rewards.scales):
+        soft_tracking_lin_vel = 2.5
+        torques = 0.0
+
+    cfg.rewards.scales = _S
+    cfg.commands = copy.deepcopy(cfg.commands)
+
+    class _R(cfg.commands.ranges):
+        lin_vel_x = [-0.3, 0.9]
+
+    cfg.commands.ranges = _R
+    r2 = resolve(cfg)
+    assert abs(r2.reward_scales["soft_tracking_lin_vel"] - 2.5 * r2.dt) < 1e-12 and "torques" not in r2.reward_scales
+    assert r2.command_ranges["lin_vel_x"] == [-0.3, 0.9]
+    # ... and what the kernels cannot honour fails loudly
+    for path, value in (("control.control_type", "T"), ("control.decimation", 2), ("commands.heading_command", False),
+                        ("env.num_observations", 48), ("terrain.measure_heights", False), ("rewards.only_positive_rewards", True)):
+        bad = Lite3DTCCfg()
+        section, field = path.split(".")
+        sec = copy.deepcopy(getattr(bad, section))
+        sub = type("edited", (sec if isinstance(sec, type) else type(sec),), {field: value})
+        setattr(bad, section, sub)
+        with _pt.raises(CfgError):
+            resolve(bad)
+
+
+def test_get_load_path_picks_the_last_run_and_highest_checkpoint(tmp_path):
+    """legged_gym/utils/helpers.py:73-95."""
+    import pytest as _pt
+    from dtc_b200.legged_gym.utils.helpers import get_load_path
+    with _pt.raises(ValueError):
+        get_load_path(str(tmp_path / "nothing_here"))
+    for run, models in (("Jan01_10-00-00_a", (0, 50, 100)), ("Jan02_09-00-00_b", (0, 50, 1500, 200)), ("exported", ())):
+        d = tmp_path / run
+        d.mkdir()
+        for m in models:
+            (d / f"model_{m}.pt").write_bytes(b"")
+    assert get_load_path(str(tmp_path)).endswith("Jan02_09-00-00_b/model_1500.pt")          # 'exported' ignored, numeric order
+    assert get_load_path(str(tmp_path), load_run="Jan01_10-00-00_a").endswith("Jan01_10-00-00_a/model_100.pt")
+    assert get_load_path(str(tmp_path), load_run="Jan01_10-00-00_a", checkpoint=50).endswith("Jan01_10-00-00_a/model_50.pt")
