@@ -604,34 +604,40 @@ __global__ void __launch_bounds__(256) k_pack_inputs(int M, const float* __restr
                                                      const float* __restrict__ bv, int bv_ld, float* __restrict__ xh,
                                                      float* __restrict__ xp, float* __restrict__ xc, float* __restrict__ xh_lo,
                                                      float* __restrict__ xp_lo, float* __restrict__ xc_lo) {
-  const int W = LD_HIST + LD_PRIVA + LD_XC;
-  const long long total = (long long)M * W;
-  for (long long e = blockIdx.x * 256ll + threadIdx.x; e < total; e += gridDim.x * 256ll) {
-    int m = (int)(e / W), c = (int)(e - (long long)m * W);
-    if (c < LD_HIST) {
-      if (xh) {
-        const float v = c < 265 ? hist[(size_t)m * hist_ld + c] : 0.f;
-        xh[(size_t)m * LD_HIST + c] = v;
-        if (xh_lo) xh_lo[(size_t)m * LD_HIST + c] = tf32_lo(v);  // TF32 companions written here: no separate k_split_lo pass
-      }
-    } else if (c < LD_HIST + LD_PRIVA) {
-      c -= LD_HIST;
-      if (xp) {
-        const float v = c < 693 ? priv[(size_t)m * priv_ld + c] : 0.f;
-        xp[(size_t)m * LD_PRIVA + c] = v;
-        if (xp_lo) xp_lo[(size_t)m * LD_PRIVA + c] = tf32_lo(v);
-      }
+  // one thread per 16-byte piece of a packed row (67 + 174 + 188 pieces): 32-bit index arithmetic, 16-byte stores; the sources are
+  // read with scalar loads (the caller's row pitches and the 693-column offset of the critic part are not 16-byte multiples)
+  constexpr int W4 = (LD_HIST + LD_PRIVA + LD_XC) / 4, H4 = LD_HIST / 4, P4 = LD_PRIVA / 4;
+  const unsigned total = (unsigned)M * W4;
+  for (unsigned e = blockIdx.x * 256u + threadIdx.x; e < total; e += gridDim.x * 256u) {
+    const unsigned m = e / W4;
+    int c = (int)(e - m * W4);
+    float v[4];
+    float *dst, *dst_lo;
+    if (c < H4) {
+      if (!xh) continue;
+      const float* src = hist + (size_t)m * hist_ld + 4 * c;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = 4 * c + k < 265 ? src[k] : 0.f;
+      dst = xh + (size_t)m * LD_HIST + 4 * c; dst_lo = xh_lo ? xh_lo + (size_t)m * LD_HIST + 4 * c : nullptr;
+    } else if (c < H4 + P4) {
+      c -= H4;
+      if (!xp) continue;
+      const float* src = priv + (size_t)m * priv_ld + 4 * c;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = 4 * c + k < 693 ? src[k] : 0.f;
+      dst = xp + (size_t)m * LD_PRIVA + 4 * c; dst_lo = xp_lo ? xp_lo + (size_t)m * LD_PRIVA + 4 * c : nullptr;
     } else {
-      c -= LD_HIST + LD_PRIVA;
-      float v;
-      if (c < XC_OBS) v = priv[(size_t)m * priv_ld + 693 + c];
-      else if (c < XC_BV) v = obs[(size_t)m * obs_ld + (c - XC_OBS)];
-      else v = bv[(size_t)m * bv_ld + (c - XC_BV)];
-      if (xc) {
-        xc[(size_t)m * LD_XC + c] = v;
-        if (xc_lo) xc_lo[(size_t)m * LD_XC + c] = tf32_lo(v);
+      c -= H4 + P4;
+      if (!xc) continue;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int col = 4 * c + k;
+        v[k] = col < XC_OBS ? priv[(size_t)m * priv_ld + 693 + col] : col < XC_BV ? obs[(size_t)m * obs_ld + (col - XC_OBS)] : bv[(size_t)m * bv_ld + (col - XC_BV)];
       }
+      dst = xc + (size_t)m * LD_XC + 4 * c; dst_lo = xc_lo ? xc_lo + (size_t)m * LD_XC + 4 * c : nullptr;
     }
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    if (dst_lo) *reinterpret_cast<float4*>(dst_lo) = make_float4(tf32_lo(v[0]), tf32_lo(v[1]), tf32_lo(v[2]), tf32_lo(v[3]));
   }
 }
 
@@ -1215,7 +1221,7 @@ extern "C" int dtc_policy_act(dtc_learner* l, int32_t M, const float* obs, int32
   } else {
     memset(l->ext, 0, sizeof(l->ext));
   }
-  k_pack_inputs<<<grid1d((long long)M * (LD_HIST + LD_PRIVA + LD_XC), 256), 256, 0, st>>>(M, obs, obs_ld, hist, hist_ld, priv, priv_ld,
+  k_pack_inputs<<<grid1d((long long)M * ((LD_HIST + LD_PRIVA + LD_XC) / 4), 256), 256, 0, st>>>(M, obs, obs_ld, hist, hist_ld, priv, priv_ld,
                                                                                            base_vel, bv_ld, xh, xp, xc, lo_of(l, xh),
                                                                                            lo_of(l, xp), lo_of(l, xc));
   DTC_CHECK_LAUNCH("k_pack_inputs");
@@ -1237,7 +1243,7 @@ extern "C" int dtc_policy_evaluate(dtc_learner* l, int32_t M, const float* obs, 
   if (!l || !obs || !priv || !base_vel || !values) DTC_FAIL(DTC_ERR_ARG, "dtc_policy_evaluate: null argument");
   if (M <= 0 || M > l->R) DTC_FAIL(DTC_ERR_ARG, "dtc_policy_evaluate: M=%d outside (0,%d]", M, l->R);
   cudaStream_t st = (cudaStream_t)stream;
-  k_pack_inputs<<<grid1d((long long)M * (LD_HIST + LD_PRIVA + LD_XC), 256), 256, 0, st>>>(M, obs, obs_ld, nullptr, 0, priv, priv_ld,
+  k_pack_inputs<<<grid1d((long long)M * ((LD_HIST + LD_PRIVA + LD_XC) / 4), 256), 256, 0, st>>>(M, obs, obs_ld, nullptr, 0, priv, priv_ld,
                                                                                            base_vel, bv_ld, nullptr, nullptr, l->XC, nullptr,
                                                                                            nullptr, lo_of(l, l->XC));
   DTC_CHECK_LAUNCH("k_pack_inputs");
@@ -1279,7 +1285,7 @@ extern "C" int dtc_policy_act_teacher(dtc_learner* l, int32_t M, const float* ob
   cudaStream_t st = (cudaStream_t)stream;
   l->last_M = M;
   // base_vel is not an input of this path: the obs pointer doubles as a dummy source for the 3 base_vel columns
-  k_pack_inputs<<<grid1d((long long)M * (LD_HIST + LD_PRIVA + LD_XC), 256), 256, 0, st>>>(M, obs, obs_ld, hist, hist_ld, priv, priv_ld,
+  k_pack_inputs<<<grid1d((long long)M * ((LD_HIST + LD_PRIVA + LD_XC) / 4), 256), 256, 0, st>>>(M, obs, obs_ld, hist, hist_ld, priv, priv_ld,
                                                                                            obs, obs_ld, l->XH, l->XP, l->XC, lo_of(l, l->XH),
                                                                                            lo_of(l, l->XP), nullptr);
   DTC_CHECK_LAUNCH("k_pack_inputs");
