@@ -11,9 +11,14 @@ policy step).  env-steps/sec = world * N_envs * T * K / time, the quantity the r
 envs per GPU, ActorCriticDecoder = CE-net + 512-d terrain latent); the Isaac Gym call is replaced by synthetic
 root/dof/contact/rigid-body tensors (SURVEY.md 8d distributions).
 
-`value`  : simulator tensors already resident in HBM (a device-side pool refreshed by device-to-device copies).
+`value`  : simulator tensors already resident in HBM (a device-side pool refreshed by device-to-device copies).  From the second
+           iteration on OnPolicyRunner replays the rollout (24 x 28 launches) as one CUDA graph (DTC_CUDA_GRAPH=0: eager launches).
 `e2e`    : the same loop through the public Python API with the simulator tensors arriving from PINNED HOST memory every
-           environment step (host->device copies inside the timed region) and the iteration's statistics read back.
+           environment step (host->device copies inside the timed region: the 24 states of the next rollout travel on a copy stream
+           into a device ring while the update runs, the graph moves ring[t] into the simulator tensors) and the iteration's
+           statistics read back.
+N > 1    : one process per GPU, environments sharded; the per-optimizer-step gradient all-reduce is the library's own kernel over
+           NVLink peer memory (csrc/dtc_dp.cu; DTC_DP=nccl1 for the NCCL call it replaces).
 `roofline`: the dominant kernel, k_gemm_tc2 (CTA-pair tcgen05 GEMM): algorithmic 2*M*N*K FLOPs / CUDA-event time around every
            launch of one extra iteration (side streams serialised for it), against the measured sustained bf16 tensor peak of
            MEASURED_PEAKS.json; `traffic` = DRAM bytes of one launch from the committed ncu capture (profiles/).  The whole GEMM
