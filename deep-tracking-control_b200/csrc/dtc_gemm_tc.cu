@@ -46,6 +46,7 @@ struct TcParams {
   int split_a, split_b;  // 1: that operand's TF32 companion tile is computed in shared memory by the splitter warps (no *_lo array in HBM)
   int neff;   // 1: the MMA of a ragged / narrow n-tile covers only the live columns rounded up to the instruction granularity
   int splitk_atomic;  // TMA-store epilogue, splits > 1: partial tiles are ADDED into C by the TMA unit (no workspace, no reduce kernel)
+  int pdl_late;   // single-CTA kernel: griddepcontrol.launch_dependents after the last MMA instead of at kernel start (DTC_PDL=3)
   int lo_direct;  // TMA-store epilogue: 1 = the companion output leaves from registers (env DTC_TC_LO=direct)
   int direct; // epilogue variant: 1 = registers -> global without the shared-memory transpose (env DTC_TC_EPI=direct|staged)
   int debug;  // timing experiments only (env DTC_TC_DEBUG): 1 = epilogue skips its stores, 2 = producer stops loading after the first ring fill
@@ -615,7 +616,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt_n = (p.N + TC_BN - 1) / TC_BN, nt_m = (p.M + TC_BM - 1) / TC_BM;
   const int ntiles = nt_n * nt_m * p.splits;
-  tc_launch_dependents();
+  if (!p.pdl_late) tc_launch_dependents();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(&bar_full[s], 1); tc_mbar_init(&bar_empty[s], 1); tc_mbar_init(&bar_split[s], 4); }
@@ -707,6 +708,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       }
       tc_commit(&bar_acc_full[buf]);  // accumulator set complete
     }
+    // late trigger: the dependent grid may become resident now that this CTA has issued its last MMA - its prologue (barrier
+    // init, TMEM allocation, descriptor fetch) overlaps this grid's epilogue instead of spinning next to its main loop
+    if (p.pdl_late) tc_launch_dependents();
    }
   }
   } else if (warp >= 12) {
@@ -1214,7 +1218,7 @@ extern "C" int dtc_get_gemm_pair(void) { return tc_pair_mode(); }
 // side streams' small kernels run.
 static int g_tc_pdl = -1;
 static int tc_pdl_on() {
-  if (g_tc_pdl < 0) { const char* e = getenv("DTC_PDL"); g_tc_pdl = !e ? 0 : e[0] == '1' ? 1 : e[0] == '2' ? 2 : 0; }
+  if (g_tc_pdl < 0) { const char* e = getenv("DTC_PDL"); g_tc_pdl = !e ? 0 : e[0] == '1' ? 1 : e[0] == '2' ? 2 : e[0] == '3' ? 3 : 0; }
   return g_tc_pdl;  // 2: only grids that leave SMs free (the 4096-row rollout shapes)
 }
 template <typename K>
@@ -1226,7 +1230,7 @@ static int tc_launch_pdl(K kernel, dim3 grid, int smem, cudaStream_t st, const C
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (tc_pdl_on() == 1 || (tc_pdl_on() == 2 && grid.x <= 128)) ? 1 : 0;
+  cfg.numAttrs = (tc_pdl_on() == 1 || (tc_pdl_on() == 2 && grid.x <= 128) || (tc_pdl_on() == 3 && p.pdl_late)) ? 1 : 0;
   DTC_CUDA(cudaLaunchKernelEx(&cfg, kernel, mA, mAlo, mB, mBlo, mC, mClo, p));
   return DTC_OK;
 }
@@ -1324,6 +1328,7 @@ int dtc_gemm_tc_launch(GemmArgs a, cudaStream_t st) {
   static int pair_min = -1;  // fewest pair tiles worth a cluster launch (env DTC_GEMM_PAIR_MIN, default: one per SM pair)
   if (pair_min < 0) { const char* e = getenv("DTC_GEMM_PAIR_MIN"); pair_min = e ? atoi(e) : num_sms / 2; }
   const bool use_pair = tc_pair_mode() && a.M > TC_BM && pair_tiles >= pair_min;
+  p.pdl_late = (tc_pdl_on() == 3 && !use_pair && a.M <= 4096 && splits == 1) ? 1 : 0;  // the rollout's GEMM -> GEMM chains
   const bool use_tc3 = use_pair && !a.a_split && !a.b_split && dtc_gemm_tc3_shape(a.M, a.N, splits, pair_min);
   const int bmap = (use_pair && !use_tc3 && bmaj == 0) ? 2 : bmaj;  // tc2 stages 64 B rows per CTA, tc3 128
   CUtensorMap mA, mAlo, mB, mBlo;
