@@ -37,13 +37,15 @@ def _compare_step(o, c, tag, sel=None):
     for n, l in bad:
         s = sel["score"][n, :, l]
         assert abs(float(s[ci[n, l]] - s[oi[n, l]])) < 1e-6, (tag, "optimal idx", n, l, int(ci[n, l]), int(oi[n, l]))
-    assert len(bad) <= max(1, ci.numel() // 2000), (tag, "too many near-tie flips", len(bad))
+    # bit-exact is the bar: the inputs are seeded and neither side has a run-to-run source of variation; 0 differences in all
+    # 231 672 pairs of this suite.  (The near-tie analysis above stays so that a failure says what kind of difference it is.)
+    assert len(bad) == 0, (tag, "optimal foothold indices differ (all verified near-ties < 1e-6)", bad[:8])
     ni, on = c.nominal_footholds_indice.cpu(), o.nominal_footholds_indice
     bad_n = (ni != on).nonzero().tolist()
     for n, l in bad_n:
         d = (o.pred_footholds[n, l, :2][None] - o.heights_world[n, :, :2]).norm(dim=1)
         assert abs(float(d[ni[n, l]] - d[on[n, l]])) < 1e-6, (tag, "nominal idx", n, l, int(ni[n, l]), int(on[n, l]))
-    assert len(bad_n) <= max(1, ni.numel() // 2000), (tag, "too many nominal near-tie flips", len(bad_n))
+    assert len(bad_n) == 0, (tag, "nominal foothold indices differ (all verified near-ties < 1e-6)", bad_n[:8])
     FLIPS["pairs"] += ci.numel()
     FLIPS["optimal"] += len(bad)
     FLIPS["nominal"] += len(bad_n)
